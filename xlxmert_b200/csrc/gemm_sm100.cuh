@@ -1,0 +1,66 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   D[M,N] = epilogue( Σ_passes A_p[M,K] · B_p[N,K]ᵀ )
+//
+// Operands are "split-bf16" matrices (hi/lo bf16 pairs, x ≈ hi + lo): with passes = 3 the kernel
+// issues A_hi·B_hi + A_lo·B_hi + A_hi·B_lo into one fp32 TMEM accumulator, which reproduces an fp32
+// GEMM to ≈ 2^-16 relative (needed for the reference's fp32 parity bar);
+// passes = 1 uses the hi parts only (plain bf16 tensor-core GEMM).
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + UMMA issuer, warps 2-5 = epilogue
+// (TMEM → registers → global).  Shared memory is a ring of stages filled by TMA
+// (cp.async.bulk.tensor, hardware swizzle) and drained by tcgen05.mma; the accumulator is double
+// buffered in TMEM (2 × BN fp32 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// This is the workhorse behind every nn.Linear on the hot path (HF modeling_lxmert.py:217-350 Q/K/V,
+// attention output, intermediate, output; lxrt/modeling.py:38-53 cluster head) and their dgrad / wgrad.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xlx {
+
+enum EpiFlags : int {
+  EPI_GELU = 1,        // v = gelu_erf(v) after bias (pre-activation optionally saved to out_u)
+  EPI_GELU_GRAD = 2,   // v *= gelu'(u_in[m,n])
+  EPI_ACCUM = 4,       // out_f32 += v instead of = v
+  EPI_TANH = 8,        // v = tanh(v) after bias
+};
+
+struct GemmEpilogue {
+  const float* bias = nullptr;      // [N]
+  const float* addend = nullptr;    // [M, ld_addend] fp32, added last
+  const float* u_in = nullptr;      // [M, ld_u] pre-activation for EPI_GELU_GRAD
+  const __nv_bfloat16* addend_hi = nullptr;  // optional split addend (hi + lo), same ld as ld_addend
+  const __nv_bfloat16* addend_lo = nullptr;
+  float* out_f32 = nullptr;         // [M, ld_out]
+  float* out_u = nullptr;           // [M, ld_u] pre-activation save (EPI_GELU)
+  __nv_bfloat16* out_hi = nullptr;  // [M, ld_split]
+  __nv_bfloat16* out_lo = nullptr;
+  int ld_addend = 0, ld_u = 0, ld_out = 0, ld_split = 0;
+  int flags = 0;
+  float alpha = 1.0f;               // v = alpha * acc before bias
+};
+
+struct GemmOperand {
+  const __nv_bfloat16* hi = nullptr;
+  const __nv_bfloat16* lo = nullptr;   // may be null when passes == 1
+  int ld = 0;                          // leading dimension in elements
+  int mn_major = 0;                    // 0: stored [rows(M or N), K]; 1: stored [K, rows] (rows contiguous)
+};
+
+struct GemmProblem {
+  int M = 0, N = 0, K = 0;
+  GemmOperand a, b;
+  int passes = 3;
+  GemmEpilogue epi;
+};
+
+// Returns 0 on success, negative on invalid arguments, positive CUDA error otherwise.
+int gemm_launch(const GemmProblem& p, cudaStream_t stream);
+// Number of kernels launched by gemm_launch since process start (bench bookkeeping).
+long long gemm_launch_count();
+
+}  // namespace xlx

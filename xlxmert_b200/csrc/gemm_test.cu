@@ -1,0 +1,134 @@
+// Standalone correctness probe for the tcgen05 GEMM (run on the B200 box through gpurun):
+//   gemm_test M N K passes a_mn b_mn epi
+// epi bits: 1 bias, 2 gelu(+save u), 4 addend, 8 split output check, 16 gelu-grad, 32 accumulate
+// Compares against a double-precision CPU reference on sampled entries and prints max relative error.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "gemm_sm100.cuh"
+
+using namespace xlx;
+
+static float frand(uint64_t& s) {
+  s = s * 6364136223846793005ull + 1442695040888963407ull;
+  return static_cast<float>((s >> 40) & 0xFFFFFF) / 8388608.0f - 1.0f;
+}
+static void split_host(const std::vector<float>& x, std::vector<__nv_bfloat16>& hi, std::vector<__nv_bfloat16>& lo) {
+  hi.resize(x.size()); lo.resize(x.size());
+  for (size_t i = 0; i < x.size(); ++i) {
+    hi[i] = __float2bfloat16_rn(x[i]);
+    lo[i] = __float2bfloat16_rn(x[i] - __bfloat162float(hi[i]));
+  }
+}
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 2; } } while (0)
+
+int main(int argc, char** argv) {
+  if (argc < 8) { printf("usage: gemm_test M N K passes a_mn b_mn epi\n"); return 1; }
+  int M = atoi(argv[1]), N = atoi(argv[2]), K = atoi(argv[3]), passes = atoi(argv[4]);
+  int a_mn = atoi(argv[5]), b_mn = atoi(argv[6]), epi = atoi(argv[7]);
+  int reps = argc > 8 ? atoi(argv[8]) : 0;
+  uint64_t seed = 1234567;
+  // logical A[M,K], B[N,K]
+  std::vector<float> A(static_cast<size_t>(M) * K), B(static_cast<size_t>(N) * K);
+  for (auto& v : A) v = frand(seed);
+  for (auto& v : B) v = 0.05f * frand(seed);
+  // storage
+  auto store = [&](const std::vector<float>& L, int rows, int mn) {
+    std::vector<float> S(L.size());
+    if (!mn) return L;
+    for (int r = 0; r < rows; ++r) for (int k = 0; k < K; ++k) S[static_cast<size_t>(k) * rows + r] = L[static_cast<size_t>(r) * K + k];
+    return S;
+  };
+  std::vector<float> As = store(A, M, a_mn), Bs = store(B, N, b_mn);
+  std::vector<__nv_bfloat16> Ahi, Alo, Bhi, Blo;
+  split_host(As, Ahi, Alo); split_host(Bs, Bhi, Blo);
+  std::vector<float> bias(N), addend(static_cast<size_t>(M) * N), uin(static_cast<size_t>(M) * N), out0(static_cast<size_t>(M) * N);
+  for (auto& v : bias) v = frand(seed);
+  for (auto& v : addend) v = frand(seed);
+  for (auto& v : uin) v = 2.0f * frand(seed);
+  for (auto& v : out0) v = frand(seed);
+
+  __nv_bfloat16 *dAhi, *dAlo, *dBhi, *dBlo, *dOhi, *dOlo;
+  float *dbias, *dadd, *duin, *dout, *dusave;
+  size_t na = Ahi.size() * 2, nb = Bhi.size() * 2, nmn = static_cast<size_t>(M) * N;
+  CK(cudaMalloc(&dAhi, na)); CK(cudaMalloc(&dAlo, na)); CK(cudaMalloc(&dBhi, nb)); CK(cudaMalloc(&dBlo, nb));
+  CK(cudaMalloc(&dOhi, nmn * 2)); CK(cudaMalloc(&dOlo, nmn * 2));
+  CK(cudaMalloc(&dbias, N * 4)); CK(cudaMalloc(&dadd, nmn * 4)); CK(cudaMalloc(&duin, nmn * 4));
+  CK(cudaMalloc(&dout, nmn * 4)); CK(cudaMalloc(&dusave, nmn * 4));
+  CK(cudaMemcpy(dAhi, Ahi.data(), na, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dAlo, Alo.data(), na, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dBhi, Bhi.data(), nb, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dBlo, Blo.data(), nb, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dbias, bias.data(), N * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dadd, addend.data(), nmn * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(duin, uin.data(), nmn * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dout, out0.data(), nmn * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dOhi, 0, nmn * 2)); CK(cudaMemset(dOlo, 0, nmn * 2)); CK(cudaMemset(dusave, 0, nmn * 4));
+
+  GemmProblem p;
+  p.M = M; p.N = N; p.K = K; p.passes = passes;
+  p.a.hi = dAhi; p.a.lo = dAlo; p.a.mn_major = a_mn; p.a.ld = a_mn ? M : K;
+  p.b.hi = dBhi; p.b.lo = dBlo; p.b.mn_major = b_mn; p.b.ld = b_mn ? N : K;
+  p.epi.out_f32 = dout; p.epi.ld_out = N;
+  if (epi & 1) p.epi.bias = dbias;
+  if (epi & 2) { p.epi.flags |= EPI_GELU; p.epi.out_u = dusave; p.epi.ld_u = N; }
+  if (epi & 4) { p.epi.addend = dadd; p.epi.ld_addend = N; }
+  if (epi & 8) { p.epi.out_hi = dOhi; p.epi.out_lo = dOlo; p.epi.ld_split = N; }
+  if (epi & 16) { p.epi.flags |= EPI_GELU_GRAD; p.epi.u_in = duin; p.epi.ld_u = N; }
+  if (epi & 32) p.epi.flags |= EPI_ACCUM;
+  int rc = gemm_launch(p, 0);
+  if (rc) { printf("gemm_launch rc=%d\n", rc); return 3; }
+  CK(cudaDeviceSynchronize());
+  std::vector<float> out(nmn), usave(nmn);
+  std::vector<__nv_bfloat16> ohi(nmn), olo(nmn);
+  CK(cudaMemcpy(out.data(), dout, nmn * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(usave.data(), dusave, nmn * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ohi.data(), dOhi, nmn * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(olo.data(), dOlo, nmn * 2, cudaMemcpyDeviceToHost));
+
+  // sampled reference
+  size_t nsamp = nmn < 200000 ? nmn : 200000;
+  double max_err = 0, max_ref = 0, max_split_err = 0, max_u_err = 0;
+  uint64_t s2 = 99;
+  for (size_t t = 0; t < nsamp; ++t) {
+    size_t idx;
+    if (nsamp == nmn) idx = t; else { s2 = s2 * 6364136223846793005ull + 1442695040888963407ull; idx = (s2 >> 20) % nmn; }
+    if (t < 64 && nsamp != nmn) {  // force corners / edges into the sample
+      int r = (t & 1) ? M - 1 - static_cast<int>(t / 8) % M : static_cast<int>(t / 8) % M;
+      int c = (t & 2) ? N - 1 - static_cast<int>(t / 4) % N : static_cast<int>(t / 4) % N;
+      idx = static_cast<size_t>(r) * N + c;
+    }
+    int r = idx / N, c = idx % N;
+    double acc = 0;
+    const float* a = &A[static_cast<size_t>(r) * K];
+    const float* b = &B[static_cast<size_t>(c) * K];
+    for (int k = 0; k < K; ++k) acc += static_cast<double>(a[k]) * b[k];
+    double v = acc;
+    if (epi & 1) v += bias[c];
+    double u = v;
+    if (epi & 2) v = 0.5 * v * (1.0 + erf(v / sqrt(2.0)));
+    if (epi & 16) { double x = uin[idx]; v *= 0.5 * (1.0 + erf(x / sqrt(2.0))) + x * exp(-0.5 * x * x) / sqrt(2.0 * M_PI); }
+    if (epi & 4) v += addend[idx];
+    if (epi & 32) v += out0[idx];
+    max_err = fmax(max_err, fabs(out[idx] - v));
+    max_ref = fmax(max_ref, fabs(v));
+    if (epi & 8) max_split_err = fmax(max_split_err, fabs(static_cast<double>(__bfloat162float(ohi[idx])) + __bfloat162float(olo[idx]) - out[idx]));
+    if (epi & 2) max_u_err = fmax(max_u_err, fabs(usave[idx] - u));
+  }
+  double rel = max_err / fmax(max_ref, 1e-30);
+  double tol = passes == 3 ? 5e-5 : 2e-2;
+  bool ok = rel < tol && (!(epi & 8) || max_split_err < 1e-4 * max_ref) && (!(epi & 2) || max_u_err < tol * max_ref + 1e-5);
+  printf("M=%d N=%d K=%d passes=%d a_mn=%d b_mn=%d epi=%d : max_abs_err=%.3e max_ref=%.3e rel=%.3e split_err=%.3e u_err=%.3e %s\n",
+         M, N, K, passes, a_mn, b_mn, epi, max_err, max_ref, rel, max_split_err, max_u_err, ok ? "OK" : "FAIL");
+  if (reps > 0) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) gemm_launch(p, 0);
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i) gemm_launch(p, 0);
+    cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double t = ms / reps * 1e-3;
+    printf("  time %.3f us  algorithmic %.1f TFLOP/s (executed x%d)\n", t * 1e6, 2.0 * M * N * K / t * 1e-12, passes);
+  }
+  return ok ? 0 : 4;
+}
