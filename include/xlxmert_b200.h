@@ -1,0 +1,106 @@
+/*
+ * xlxmert_b200 — C ABI of the B200-native X-LXMERT hot path (libxlxmert_b200.so).
+ *
+ * The reference (allenai/x-lxmert) has no native layer: its hot path is Python calling torch.nn modules
+ * (SURVEY.md §2.2).  The entry points below are what a Python maintainer binds with ctypes to replace the
+ * *inside* of those modules; each cites the reference interface it replaces.  "HF" = the third-party
+ * transformers/models/lxmert/modeling_lxmert.py (5.5.0 line numbers) that the reference imports at
+ * x-lxmert/src/lxrt/modeling.py:5.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer on the calling thread's current device unless stated otherwise;
+ *    float = IEEE fp32, row-major, innermost dimension contiguous.  `params` arrays are HOST arrays of
+ *    device pointers.
+ *  - The library never allocates, frees or retains caller memory past return; workspaces are caller-owned
+ *    (size them with the *_bytes functions).  A workspace used by a forward with training=1 holds the
+ *    saved activations and must be passed unchanged to the matching backward.
+ *  - All work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no internal syncs.
+ *  - Return value: 0 = OK; < 0 = invalid argument / unsupported shape (see xlx_strerror); > 0 = CUDA error
+ *    code.  Nothing throws across the boundary and nothing is printed.
+ *  - `passes`: 3 = split-bf16 "bf16x3" tensor-core GEMMs (fp32-class accuracy, the parity mode);
+ *              1 = single bf16 pass (what the reference's mixed-precision flag would give, pretrain.bash:28).
+ */
+#ifndef XLXMERT_B200_H_
+#define XLXMERT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Static dimensions (HF LxmertConfig: configuration_lxmert.py:85-87 and the BERT-base sizes). */
+typedef struct xlx_dims {
+  int32_t hidden;        /* 768; multiple of 128, = heads * 64 */
+  int32_t heads;         /* 12; head_dim must be 64 */
+  int32_t intermediate;  /* 3072 */
+  int32_t feat_dim;      /* 2048 */
+  int32_t pos_dim;       /* 4 */
+  int32_t l_layers;      /* 9  language layers    (encoder.layer)    */
+  int32_t r_layers;      /* 5  vision layers      (encoder.r_layers) */
+  int32_t x_layers;      /* 5  cross-modal layers (encoder.x_layers) */
+  float ln_eps;          /* 1e-12 */
+} xlx_dims;
+
+const char* xlx_version(void);
+const char* xlx_strerror(int32_t code);
+/* number of kernels launched by this library in this process so far (bench bookkeeping) */
+int64_t xlx_launch_count(void);
+int64_t xlx_gemm_launch_count(void);
+/* Measurement aid for bench.py's roofline: between begin and end every tcgen05 GEMM launch is bracketed by
+ * CUDA events on its stream; end synchronises and returns the summed device time (ms), the summed
+ * algorithmic FLOPs (2*M*N*K per launch) and the launch count. */
+void xlx_profile_gemm_begin(void);
+int32_t xlx_profile_gemm_end(double* total_ms, double* total_flops, int64_t* launches);
+
+/* ---- LxmertEncoder (HF:487-565; reached from lxrt/modeling.py:195-206 via self.bert) -------------------
+ * Parameter slots, in order (`params[i]` = device pointer of slot i; shapes as in the state dict):
+ *   visn_fc.visn_fc.{weight[H,F],bias}, visn_fc.visn_layer_norm.{weight,bias},
+ *   visn_fc.box_fc.{weight[H,4],bias}, visn_fc.box_layer_norm.{weight,bias}                     (8)
+ *   then for each layer.i (i < l_layers) and each r_layers.i:   ATT(attention.self, attention.output), FFN
+ *   then for each x_layers.i: ATT(visual_attention.att, visual_attention.output),
+ *        ATT(lang_self_att.self, .output), ATT(visn_self_att.self, .output),
+ *        FFN(lang_inter, lang_output), FFN(visn_inter, visn_output)
+ *   ATT = query.weight, key.weight, value.weight, query.bias, key.bias, value.bias,
+ *         output.dense.weight, output.dense.bias, output.LayerNorm.weight, output.LayerNorm.bias   (10)
+ *   FFN = intermediate.dense.weight[I,H], .bias, output.dense.weight[H,I], .bias, LayerNorm.weight, .bias (6)
+ * The gradient arena written by xlx_encoder_bwd is one flat fp32 buffer with the slots packed in the same
+ * order (xlx_encoder_grad_offset gives each slot's element offset).
+ */
+int64_t xlx_encoder_num_params(const xlx_dims* d);
+int64_t xlx_encoder_param_elems(const xlx_dims* d, int64_t slot);
+int64_t xlx_encoder_grad_offset(const xlx_dims* d, int64_t slot);
+int64_t xlx_encoder_grad_elems(const xlx_dims* d);
+
+/* Bytes of the prepared-weights arena (bf16 hi/lo splits of every Linear weight, fused QKV). */
+size_t xlx_encoder_prep_bytes(const xlx_dims* d);
+/* Convert the fp32 parameters into the arena.  Call whenever the weights changed (every optimiser step). */
+int32_t xlx_encoder_prepare(const xlx_dims* d, const float* const* params, void* prep, void* stream);
+
+size_t xlx_encoder_workspace_bytes(const xlx_dims* d, int32_t B, int32_t L, int32_t V, int32_t training);
+
+/* LxmertEncoder.forward(lang_feats, lang_attention_mask, visual_feats, visual_pos, visual_attention_mask)
+ * (HF:506-565).  lang_in [B,L,H] = embedding output; lang_mask / vis_mask: additive masks [B,L] / [B,V]
+ * (0 or finfo.min, HF:766-782) or NULL; visual_feats [B,V,F]; visual_pos [B,V,4].
+ * Outputs: lang_out [B,L,H], vis_out [B,V,H] (last hidden states); optional per-layer hidden states
+ * lang_hidden [l_layers + x_layers, B, L, H], vis_hidden [r_layers + x_layers, B, V, H] (NULL to skip). */
+int32_t xlx_encoder_fwd(const xlx_dims* d, const float* const* params, const void* prep, int32_t B, int32_t L,
+                        int32_t V, const float* lang_in, const float* lang_mask, const float* visual_feats,
+                        const float* visual_pos, const float* vis_mask, float* lang_out, float* vis_out,
+                        float* lang_hidden, float* vis_hidden, void* workspace, size_t workspace_bytes,
+                        int32_t training, int32_t passes, void* stream);
+
+/* Backward of the above (the reference gets it from torch autograd: lxmert_pretrain.py:338).
+ * d_lang_out / d_vis_out: gradients wrt the two outputs (NULL = zero).  Writes d_lang_in [B,L,H],
+ * d_visual_feats [B,V,F] (NULL to skip) and every parameter gradient into `grads` (overwritten, not
+ * accumulated). */
+int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const void* prep, int32_t B, int32_t L,
+                        int32_t V, const float* visual_pos, const float* d_lang_out, const float* d_vis_out,
+                        float* d_lang_in, float* d_visual_feats, float* grads, void* workspace,
+                        size_t workspace_bytes, int32_t passes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XLXMERT_B200_H_ */

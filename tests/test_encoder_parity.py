@@ -1,0 +1,131 @@
+"""GPU parity of the sm_100a encoder (through the C ABI) against the CPU oracle and the committed goldens
+produced by the reference's own classes (HF LxmertModel, oracle/make_golden.py).
+
+Tolerance: north_star asks for 1e-3 relative fp32; the bf16x3 path is expected to sit two orders below it,
+so the tests assert 1e-4 on outputs (tensor-normalised max error) and 1e-3 on gradients.
+"""
+import pytest
+import torch
+
+from oracle import lxrt_oracle as O
+from xlxmert_b200 import params as P
+from xlxmert_b200 import synth
+from xlxmert_b200.config import DEFAULT_DIMS as D, TINY_DIMS, LxmertDims
+
+from util import load_golden, probes, rel_err
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+def _encoder(d, sd_enc, **kw):
+    from xlxmert_b200.encoder import B200LxmertEncoder
+    enc = B200LxmertEncoder(dims=d, **kw)
+    missing, unexpected = enc.load_state_dict(sd_enc, strict=True)
+    assert not missing and not unexpected
+    return enc.cuda()
+
+
+def _case(d, B, L, V, wseed, bseed):
+    sd = P.init_state_dict(P.model_param_specs(d), seed=wseed, randomize_ln_bias=True)
+    batch = synth.make_batch(d, B, L, V, seed=bseed)
+    feats = synth.visual_feats_from(synth.centroid_table(d), batch["cluster_ids"])
+    emb = O.embeddings(O.sub(sd, "embeddings"), batch["input_ids"])
+    mask = O.extended_mask(batch["attention_mask"], torch.float32)
+    return sd, batch, feats, emb, mask
+
+
+@pytest.mark.parametrize("name", ["model_b2_l20_v64", "model_b3_l13_v36"])
+def test_encoder_forward_matches_reference_golden(name):
+    g = load_golden(name)
+    B, L, V, wseed, bseed = (int(x) for x in g["meta"])
+    sd, batch, feats, emb, mask = _case(D, B, L, V, wseed, bseed)
+    enc = _encoder(D, O.sub(sd, "encoder"), output_hidden_states=True).eval()
+    with torch.no_grad():
+        (vs, _), (ls, _), _ = enc(emb.cuda(), mask.cuda(), feats.cuda(), batch["visual_pos"].cuda())
+    assert len(ls) == 14 and len(vs) == 10
+    assert rel_err(ls[-1].cpu(), g["lang"]) < OUT_TOL
+    assert rel_err(vs[-1].cpu(), g["vis"]) < OUT_TOL
+    for i, h in enumerate(ls):
+        assert rel_err(h.cpu()[:, ::4, ::8], g[f"lang_h{i}"]) < OUT_TOL, ("lang", i)
+    for i, h in enumerate(vs):
+        assert rel_err(h.cpu()[:, ::8, ::8], g[f"vis_h{i}"]) < OUT_TOL, ("vis", i)
+
+
+def test_encoder_inference_workspace_reuse_matches_training_layout():
+    """The inference plan (shared temporaries + ring of states) and the training plan (everything saved)
+    must give identical outputs."""
+    sd, batch, feats, emb, mask = _case(D, 3, 20, 64, 1, 2)
+    enc = _encoder(D, O.sub(sd, "encoder")).eval()
+    args = (emb.cuda(), mask.cuda(), feats.cuda(), batch["visual_pos"].cuda())
+    with torch.no_grad():
+        (v0, _), (l0, _), _ = enc(*args)
+    emb_g = args[0].clone().requires_grad_(True)
+    (v1, _), (l1, _), _ = enc(emb_g, *args[1:])
+    assert torch.equal(l0[-1], l1[-1].detach()) and torch.equal(v0[-1], v1[-1].detach())
+
+
+def _grad_check(d, B, L, V, wseed, bseed, passes=3, out_tol=OUT_TOL, grad_tol=GRAD_TOL):
+    sd, batch, feats, emb, mask = _case(d, B, L, V, wseed, bseed)
+    # oracle on CPU with autograd
+    sdo = {k: v.clone().requires_grad_(True) for k, v in O.sub(sd, "encoder").items()}
+    emb_o = emb.clone().requires_grad_(True)
+    feats_o = feats.clone().requires_grad_(True)
+    ls, vs = O.encoder(sdo, emb_o, mask, feats_o, batch["visual_pos"], None, heads=d.heads, n_l=d.l_layers,
+                       n_r=d.r_layers, n_x=d.x_layers)
+    pl, pv = probes([ls[-1].shape, vs[-1].shape], seed=bseed + 77)
+    ((ls[-1] * pl).sum() + (vs[-1] * pv).sum()).backward()
+
+    enc = _encoder(d, O.sub(sd, "encoder"), passes=passes).train()
+    emb_g = emb.cuda().requires_grad_(True)
+    feats_g = feats.cuda().requires_grad_(True)
+    (v, _), (l, _), _ = enc(emb_g, mask.cuda(), feats_g, batch["visual_pos"].cuda())
+    assert rel_err(l[-1].detach().cpu(), ls[-1].detach()) < out_tol
+    assert rel_err(v[-1].detach().cpu(), vs[-1].detach()) < out_tol
+    ((l[-1] * pl.cuda()).sum() + (v[-1] * pv.cuda()).sum()).backward()
+    assert rel_err(emb_g.grad.cpu(), emb_o.grad) < grad_tol
+    assert rel_err(feats_g.grad.cpu(), feats_o.grad) < grad_tol
+    worst = ("", 0.0)
+    for name, p in enc.named_parameters():
+        ref = sdo[name].grad
+        assert p.grad is not None, name
+        if float(ref.abs().max()) < 1e-6:     # mathematically zero (key bias: softmax shift invariance)
+            assert float(p.grad.abs().max()) < 1e-4, name
+            continue
+        e = rel_err(p.grad.cpu(), ref)
+        if e > worst[1]:
+            worst = (name, e)
+        assert e < grad_tol, (name, e)
+    return worst
+
+
+def test_encoder_backward_matches_oracle_default_dims():
+    worst = _grad_check(D, 2, 20, 64, 0, 0)
+    print("worst parameter-gradient error:", worst)
+
+
+def test_encoder_backward_ragged_shapes():
+    _grad_check(D, 3, 13, 36, 5, 9)
+
+
+def test_encoder_backward_tiny_dims_odd_batch():
+    _grad_check(TINY_DIMS, 5, 7, 9, 3, 4)
+
+
+def test_encoder_single_pass_bf16_is_mixed_precision_class():
+    """passes=1 (plain bf16 tensor-core GEMMs) is the mixed-precision mode: looser, but must stay sane."""
+    _grad_check(D, 2, 20, 64, 0, 0, passes=1, out_tol=3e-2, grad_tol=1e-1)
+
+
+def test_encoder_rejects_unsupported_shapes_loudly():
+    from xlxmert_b200 import _lib
+    sd, batch, feats, emb, mask = _case(TINY_DIMS, 1, 7, 9, 3, 4)
+    enc = _encoder(TINY_DIMS, O.sub(sd, "encoder")).eval()
+    long_emb = torch.zeros(1, 65, TINY_DIMS.hidden, device="cuda")
+    with pytest.raises(_lib.XlxError):
+        with torch.no_grad():
+            enc(long_emb, None, feats.cuda(), batch["visual_pos"].cuda())
+    with pytest.raises(RuntimeError):
+        enc(emb, None, feats, batch["visual_pos"])          # CPU tensors: no fallback

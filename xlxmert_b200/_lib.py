@@ -1,0 +1,99 @@
+"""ctypes binding of ``libxlxmert_b200.so`` (the C ABI in ``include/xlxmert_b200.h``).
+
+There is no fallback: if the library has not been built, ``load()`` raises — the product path never
+routes around the CUDA extension.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .config import LxmertDims
+
+_LIB = None
+
+
+class XlxDims(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("heads", C.c_int32), ("intermediate", C.c_int32),
+                ("feat_dim", C.c_int32), ("pos_dim", C.c_int32), ("l_layers", C.c_int32),
+                ("r_layers", C.c_int32), ("x_layers", C.c_int32), ("ln_eps", C.c_float)]
+
+    @classmethod
+    def from_dims(cls, d: LxmertDims) -> "XlxDims":
+        return cls(d.hidden, d.heads, d.intermediate, d.feat_dim, d.pos_dim, d.l_layers, d.r_layers,
+                   d.x_layers, d.ln_eps)
+
+
+class XlxError(RuntimeError):
+    def __init__(self, fn: str, code: int):
+        self.code = code
+        msg = load().xlx_strerror(code).decode()
+        super().__init__(f"{fn} failed with code {code}: {msg}")
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libxlxmert_b200.so")
+
+
+def _sig(lib):
+    P, I32, I64, SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    D = C.POINTER(XlxDims)
+    lib.xlx_version.restype = C.c_char_p
+    lib.xlx_strerror.restype = C.c_char_p
+    lib.xlx_strerror.argtypes = [I32]
+    lib.xlx_launch_count.restype = I64
+    lib.xlx_gemm_launch_count.restype = I64
+    lib.xlx_profile_gemm_begin.restype = None
+    lib.xlx_profile_gemm_end.restype = I32
+    lib.xlx_profile_gemm_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(I64)]
+    for name in ("xlx_encoder_num_params", "xlx_encoder_grad_elems"):
+        getattr(lib, name).restype = I64
+        getattr(lib, name).argtypes = [D]
+    for name in ("xlx_encoder_param_elems", "xlx_encoder_grad_offset"):
+        getattr(lib, name).restype = I64
+        getattr(lib, name).argtypes = [D, I64]
+    lib.xlx_encoder_prep_bytes.restype = SZ
+    lib.xlx_encoder_prep_bytes.argtypes = [D]
+    lib.xlx_encoder_prepare.restype = I32
+    lib.xlx_encoder_prepare.argtypes = [D, P, P, P]
+    lib.xlx_encoder_workspace_bytes.restype = SZ
+    lib.xlx_encoder_workspace_bytes.argtypes = [D, I32, I32, I32, I32]
+    lib.xlx_encoder_fwd.restype = I32
+    lib.xlx_encoder_fwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, SZ, I32, I32, P]
+    lib.xlx_encoder_bwd.restype = I32
+    lib.xlx_encoder_bwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, SZ, I32, P]
+    optional = {
+        "xlx_objhead_prep_bytes": (SZ, [D, I32]),
+        "xlx_objhead_prepare": (I32, [D, I32, P, P, P]),
+        "xlx_objhead_workspace_bytes": (SZ, [D, I32, I32, I32]),
+        "xlx_objhead_fwd": (I32, [D, I32, P, P, I32, P, P, P, P, P, P, P, SZ, I32, I32, P]),
+        "xlx_objhead_bwd": (I32, [D, I32, P, P, I32, P, P, C.c_float, P, P, P, SZ, I32, P]),
+        "xlx_generator_prep_bytes": (SZ, []),
+        "xlx_generator_prepare": (I32, [P, P, P]),
+        "xlx_generator_workspace_bytes": (SZ, [I32]),
+        "xlx_generator_fwd": (I32, [P, P, I32, P, I32, P, P, P, SZ, P]),
+    }
+    for name, (res, args) in optional.items():
+        if hasattr(lib, name):
+            getattr(lib, name).restype = res
+            getattr(lib, name).argtypes = args
+
+
+def load():
+    """The loaded library; raises if it has not been built (``python -m xlxmert_b200.build``)."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"{path} is missing: the B200 hot path has no CPU/PyTorch fallback. "
+                "Build it with `python -m xlxmert_b200.build` (needs nvcc).")
+        lib = C.CDLL(path)
+        _sig(lib)
+        _LIB = lib
+    return _LIB
+
+
+def check(fn: str, code: int) -> None:
+    if code != 0:
+        raise XlxError(fn, int(code))

@@ -1,0 +1,751 @@
+// Host-side orchestration of the LXMERT encoder forward / backward over the sm_100a kernels, and the
+// C ABI declared in include/xlxmert_b200.h.  Follows HF modeling_lxmert.py:487-565 (LxmertEncoder),
+// :353-366 (LxmertLayer), :369-457 (LxmertXLayer), :460-484 (LxmertVisualFeatureEncoder) — the arithmetic
+// the reference reaches through self.bert at x-lxmert/src/lxrt/modeling.py:195-206.
+#include <cstring>
+#include <vector>
+
+#include "../../include/xlxmert_b200.h"
+#include "gemm_sm100.cuh"
+#include "kernels.cuh"
+
+using namespace xlx;
+
+namespace {
+
+constexpr int N_ATT = 10, N_FFN = 6, N_VISN = 8;
+
+#define XLX_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__) return rc__;       \
+  } while (0)
+
+bool dims_ok(const xlx_dims* d) {
+  return d && d->hidden > 0 && d->hidden % 128 == 0 && d->hidden <= 1024 && d->heads * 64 == d->hidden &&
+         d->intermediate % 8 == 0 && d->feat_dim % 8 == 0 && d->pos_dim == 4 && d->l_layers >= 0 &&
+         d->r_layers >= 0 && d->x_layers >= 0;
+}
+
+// ---- parameter slots --------------------------------------------------------------------------
+struct SlotTable {
+  std::vector<int64_t> elems, offset;
+  int64_t total = 0;
+};
+void push_att(std::vector<int64_t>& e, int64_t H) {
+  const int64_t s[N_ATT] = {H * H, H * H, H * H, H, H, H, H * H, H, H, H};
+  e.insert(e.end(), s, s + N_ATT);
+}
+void push_ffn(std::vector<int64_t>& e, int64_t H, int64_t I) {
+  const int64_t s[N_FFN] = {I * H, I, H * I, H, H, H};
+  e.insert(e.end(), s, s + N_FFN);
+}
+SlotTable slot_table(const xlx_dims* d) {
+  SlotTable t;
+  const int64_t H = d->hidden, I = d->intermediate, F = d->feat_dim;
+  const int64_t v[N_VISN] = {H * F, H, H, H, H * 4, H, H, H};
+  t.elems.insert(t.elems.end(), v, v + N_VISN);
+  for (int i = 0; i < d->l_layers + d->r_layers; ++i) { push_att(t.elems, H); push_ffn(t.elems, H, I); }
+  for (int i = 0; i < d->x_layers; ++i) {
+    push_att(t.elems, H); push_att(t.elems, H); push_att(t.elems, H);
+    push_ffn(t.elems, H, I); push_ffn(t.elems, H, I);
+  }
+  t.offset.resize(t.elems.size());
+  for (size_t i = 0; i < t.elems.size(); ++i) { t.offset[i] = t.total; t.total += t.elems[i]; }
+  return t;
+}
+int att_slot(const xlx_dims* d, int blk) {  // slot index of attention block `blk` (plan order)
+  const int nlr = d->l_layers + d->r_layers;
+  if (blk < nlr) return N_VISN + blk * (N_ATT + N_FFN);
+  const int k = (blk - nlr) / 3, w = (blk - nlr) % 3;
+  return N_VISN + nlr * (N_ATT + N_FFN) + k * (3 * N_ATT + 2 * N_FFN) + w * N_ATT;
+}
+int ffn_slot(const xlx_dims* d, int blk) {
+  const int nlr = d->l_layers + d->r_layers;
+  if (blk < nlr) return N_VISN + blk * (N_ATT + N_FFN) + N_ATT;
+  const int k = (blk - nlr) / 2, w = (blk - nlr) % 2;
+  return N_VISN + nlr * (N_ATT + N_FFN) + k * (3 * N_ATT + 2 * N_FFN) + 3 * N_ATT + w * N_FFN;
+}
+
+// ---- bump allocator over a caller-owned buffer ---------------------------------------------------
+struct Bump {
+  char* base = nullptr;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    void* p = base + off;
+    off += bytes;
+    return p;
+  }
+  float* f32(size_t n) { return static_cast<float*>(take(n * 4)); }
+  Split split(size_t n) {
+    Split s;
+    s.hi = static_cast<bf16*>(take(n * 2));
+    s.lo = static_cast<bf16*>(take(n * 2));
+    return s;
+  }
+};
+inline Split rows(Split s, size_t row0, size_t ld) {
+  Split r;
+  r.hi = s.hi + row0 * ld;
+  r.lo = s.lo ? s.lo + row0 * ld : nullptr;
+  return r;
+}
+
+// ---- prepared weights ----------------------------------------------------------------------------
+struct AttW { Split wqkv; float* bqkv; Split wo; };
+struct FfnW { Split w1, w2; };
+struct Prep {
+  Split visn_w;
+  std::vector<AttW> att;
+  std::vector<FfnW> ffn;
+  size_t bytes = 0;
+};
+Prep prep_layout(const xlx_dims* d, void* base) {
+  Prep p;
+  Bump b;
+  b.base = static_cast<char*>(base);
+  const size_t H = d->hidden, I = d->intermediate, F = d->feat_dim;
+  p.visn_w = b.split(H * F);
+  const int natt = d->l_layers + d->r_layers + 3 * d->x_layers;
+  const int nffn = d->l_layers + d->r_layers + 2 * d->x_layers;
+  p.att.resize(natt);
+  p.ffn.resize(nffn);
+  for (auto& a : p.att) { a.wqkv = b.split(3 * H * H); a.bqkv = b.f32(3 * H); a.wo = b.split(H * H); }
+  for (auto& f : p.ffn) { f.w1 = b.split(I * H); f.w2 = b.split(H * I); }
+  p.bytes = b.off + 256;
+  return p;
+}
+
+// ---- activation plan -----------------------------------------------------------------------------
+struct AttSave {
+  float* qkv = nullptr;    // [M, 3H]
+  float* probs = nullptr;  // self: [B,heads,S,S]; cross: lang-query probs [B,heads,L,V]
+  float* probs2 = nullptr; // cross only: vis-query probs [B,heads,V,L]
+  Split ctx;               // [M, H]
+  float* y = nullptr;      // pre-LN [M, H]
+  float* mean = nullptr;
+  float* rstd = nullptr;
+  Split in, out;           // block input / LN output (row-sliced views)
+  int M = 0;
+};
+struct FfnSave {
+  float* u = nullptr;  // pre-GeLU [M, I]
+  Split h;             // gelu(u) [M, I]
+  float* y = nullptr;
+  float* mean = nullptr;
+  float* rstd = nullptr;
+  Split in, out;
+  int M = 0;
+};
+struct Plan {
+  int B, L, V, H, I, F, heads, Ml, Mv, Mt;
+  bool training;
+  Split feats, lang0, vis0;
+  float *y1 = nullptr, *y2 = nullptr, *tbox = nullptr, *vstats = nullptr;
+  std::vector<AttSave> att;
+  std::vector<FfnSave> ffn;
+  float* part = nullptr;
+  size_t part_elems = 0;
+  // backward scratch
+  float *dA = nullptr, *dB = nullptr, *dy = nullptr, *dctx = nullptr, *dy2 = nullptr;
+  Split dy_s, dqkv, du;
+  size_t bytes = 0;
+};
+
+Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base) {
+  Plan p;
+  p.B = B; p.L = L; p.V = V; p.H = d->hidden; p.I = d->intermediate; p.F = d->feat_dim; p.heads = d->heads;
+  p.Ml = B * L; p.Mv = B * V; p.Mt = p.Ml + p.Mv; p.training = training;
+  const size_t H = p.H, I = p.I, F = p.F, Ml = p.Ml, Mv = p.Mv, Mt = p.Mt;
+  const size_t Mmax = Ml > Mv ? Ml : Mv;
+  Bump b;
+  b.base = static_cast<char*>(base);
+  const int nl = d->l_layers, nr = d->r_layers, nx = d->x_layers;
+  p.att.resize(nl + nr + 3 * nx);
+  p.ffn.resize(nl + nr + 2 * nx);
+
+  size_t pe = 2 * static_cast<size_t>(reduce_max_blocks()) * H;
+  size_t widest = 3 * H > I ? 3 * H : I;
+  if (F > widest) widest = F;
+  if (128 * widest > pe) pe = 128 * widest;
+  if (5 * 129 * H > pe) pe = 5 * 129 * H;
+  p.part_elems = pe;
+  p.part = b.f32(pe);
+
+  p.feats = b.split(Mv * F);
+  p.y1 = b.f32(Mv * H);
+  p.y2 = b.f32(Mv * H);
+  p.tbox = b.f32(Mv * H);
+  p.vstats = b.f32(4 * Mv);
+  p.lang0 = b.split(Ml * H);
+  p.vis0 = b.split(Mv * H);
+  Split xin0 = b.split(Mt * H);  // input of the first cross-modality layer: [lang rows | vis rows]
+
+  // inference: every block shares one set of temporaries and layer outputs rotate through a small ring
+  float *sh_qkv = nullptr, *sh_y = nullptr;
+  Split sh_ctx, sh_h, ring[4];
+  int ring_i = 0;
+  if (!training) {
+    sh_qkv = b.f32(Mt * 3 * H);
+    sh_ctx = b.split(Mt * H);
+    sh_y = b.f32(Mt * H);
+    sh_h = b.split(Mmax * I);
+    for (auto& r : ring) r = b.split(Mt * H);
+  }
+  auto new_state = [&](size_t M) -> Split {
+    if (training) return b.split(M * H);
+    Split s = ring[ring_i];
+    ring_i = (ring_i + 1) & 3;
+    return s;
+  };
+  auto fill_att = [&](AttSave& a, size_t M, size_t probs_elems, size_t probs2_elems) {
+    a.M = static_cast<int>(M);
+    if (training) {
+      a.qkv = b.f32(M * 3 * H);
+      a.probs = b.f32(probs_elems);
+      if (probs2_elems) a.probs2 = b.f32(probs2_elems);
+      a.ctx = b.split(M * H);
+      a.y = b.f32(M * H);
+      a.mean = b.f32(M);
+      a.rstd = b.f32(M);
+    } else {
+      a.qkv = sh_qkv; a.ctx = sh_ctx; a.y = sh_y;
+    }
+  };
+  auto fill_ffn = [&](FfnSave& f, size_t M) {
+    f.M = static_cast<int>(M);
+    if (training) {
+      f.u = b.f32(M * I);
+      f.h = b.split(M * I);
+      f.y = b.f32(M * H);
+      f.mean = b.f32(M);
+      f.rstd = b.f32(M);
+    } else {
+      f.h = sh_h; f.y = sh_y;
+    }
+  };
+  const size_t nh = p.heads;
+  // single-modality stacks; the last layer of each writes its output straight into xin0
+  for (int s = 0; s < 2; ++s) {
+    const int n = s ? nr : nl, blk0 = s ? nl : 0;
+    const size_t M = s ? Mv : Ml, S = s ? V : L, row0 = s ? Ml : 0;
+    Split cur = s ? p.vis0 : p.lang0;
+    if (n == 0) {  // no layers of this kind: the embedding output itself is the cross-layer input
+      if (s) p.vis0 = rows(xin0, row0, H); else p.lang0 = rows(xin0, row0, H);
+    }
+    for (int i = 0; i < n; ++i) {
+      AttSave& a = p.att[blk0 + i];
+      FfnSave& f = p.ffn[blk0 + i];
+      fill_att(a, M, B * nh * S * S, 0);
+      a.in = cur;
+      a.out = new_state(M);
+      fill_ffn(f, M);
+      f.in = a.out;
+      f.out = (i == n - 1) ? rows(xin0, row0, H) : new_state(M);
+      cur = f.out;
+    }
+  }
+  Split X = xin0;
+  for (int k = 0; k < nx; ++k) {
+    AttSave& c = p.att[nl + nr + 3 * k];
+    AttSave& sl = p.att[nl + nr + 3 * k + 1];
+    AttSave& sv = p.att[nl + nr + 3 * k + 2];
+    FfnSave& fl = p.ffn[nl + nr + 2 * k];
+    FfnSave& fv = p.ffn[nl + nr + 2 * k + 1];
+    fill_att(c, Mt, B * nh * L * V, B * nh * V * L);
+    c.in = X;
+    c.out = new_state(Mt);
+    Split S2 = new_state(Mt);
+    if (training) {
+      fill_att(sl, Ml, B * nh * L * L, 0);
+      fill_att(sv, Mv, B * nh * V * V, 0);
+    } else {  // shared temporaries: give the two streams disjoint row ranges
+      fill_att(sl, Ml, 0, 0);
+      fill_att(sv, Mv, 0, 0);
+      sv.qkv = sh_qkv + Ml * 3 * H; sv.ctx = rows(sh_ctx, Ml, H); sv.y = sh_y + Ml * H;
+    }
+    sl.in = rows(c.out, 0, H); sl.out = rows(S2, 0, H);
+    sv.in = rows(c.out, Ml, H); sv.out = rows(S2, Ml, H);
+    Split O = new_state(Mt);
+    fill_ffn(fl, Ml);
+    fill_ffn(fv, Mv);
+    if (!training) fv.y = sh_y + Ml * H;   // fv.h may alias fl.h: the two FFNs run back to back on one stream
+    fl.in = sl.out; fl.out = rows(O, 0, H);
+    fv.in = sv.out; fv.out = rows(O, Ml, H);
+    X = O;
+  }
+  if (training) {
+    p.dA = b.f32(Mt * H);
+    p.dB = b.f32(Mt * H);
+    p.dy = b.f32(Mt * H);
+    p.dctx = b.f32(Mt * H);
+    p.dy2 = b.f32(Mv * H);
+    p.dy_s = b.split(Mt * H);
+    p.dqkv = b.split(Mt * 3 * H);
+    p.du = b.split(Mmax * I);
+  }
+  p.bytes = b.off + 256;
+  return p;
+}
+
+// ---- GEMM wrappers -------------------------------------------------------------------------------
+struct Run {
+  const xlx_dims* d;
+  const float* const* params;
+  Prep prep;
+  Plan plan;
+  int passes;
+  cudaStream_t st;
+  const float* lmask;
+  const float* vmask;
+};
+
+// Y[M,N] = X[M,K] · W[N,K]ᵀ (+ epilogue)
+int linear(const Run& r, Split x, int M, int K, Split w, int N, const GemmEpilogue& e) {
+  GemmProblem p;
+  p.M = M; p.N = N; p.K = K; p.passes = r.passes;
+  p.a.hi = x.hi; p.a.lo = x.lo; p.a.ld = K; p.a.mn_major = 0;
+  p.b.hi = w.hi; p.b.lo = w.lo; p.b.ld = K; p.b.mn_major = 0;
+  p.epi = e;
+  return gemm_launch(p, r.st);
+}
+// dX[M,K] = dY[M,N] · W[N,K]
+int dgrad(const Run& r, Split dy, int M, int N, Split w, int K, const GemmEpilogue& e) {
+  GemmProblem p;
+  p.M = M; p.N = K; p.K = N; p.passes = r.passes;
+  p.a.hi = dy.hi; p.a.lo = dy.lo; p.a.ld = N; p.a.mn_major = 0;
+  p.b.hi = w.hi; p.b.lo = w.lo; p.b.ld = K; p.b.mn_major = 1;   // W stored [N, K]: GEMM-N (= K) contiguous
+  p.epi = e;
+  return gemm_launch(p, r.st);
+}
+// dW[N,K] = dY[M,N]ᵀ · X[M,K]
+int wgrad(const Run& r, Split dy, int M, int N, Split x, int K, float* dw) {
+  GemmProblem p;
+  p.M = N; p.N = K; p.K = M; p.passes = r.passes;
+  p.a.hi = dy.hi; p.a.lo = dy.lo; p.a.ld = N; p.a.mn_major = 1;
+  p.b.hi = x.hi; p.b.lo = x.lo; p.b.ld = K; p.b.mn_major = 1;
+  p.epi.out_f32 = dw; p.epi.ld_out = K;
+  return gemm_launch(p, r.st);
+}
+
+const float* P(const Run& r, int slot) { return r.params[slot]; }
+
+// ---- forward blocks ------------------------------------------------------------------------------
+// residual + LayerNorm tail shared by the attention-output and FFN-output sub-blocks (HF:277-288, 339-350)
+int ln_tail(const Run& r, float* y, int M, const float* g, const float* b, Split out, float* out_f32, float* mean,
+            float* rstd) {
+  return layernorm_fwd(y, g, b, r.d->ln_eps, M, r.plan.H, 1.0f, nullptr, out, out_f32, mean, rstd, r.st);
+}
+
+int att_self_fwd(const Run& r, int blk, int S, const float* mask, float* out_f32) {
+  const Plan& p = r.plan;
+  const AttSave& a = p.att[blk];
+  const AttW& w = r.prep.att[blk];
+  const int s0 = att_slot(r.d, blk), H = p.H, M = a.M;
+  GemmEpilogue e;
+  e.bias = w.bqkv; e.out_f32 = a.qkv; e.ld_out = 3 * H;
+  XLX_TRY(linear(r, a.in, M, H, w.wqkv, 3 * H, e));
+  XLX_TRY(attention_fwd(a.qkv, a.qkv + H, a.qkv + 2 * H, 3 * H, mask, p.B, p.heads, S, S, a.ctx, nullptr, H, a.probs,
+                        r.st));
+  GemmEpilogue o;
+  o.bias = P(r, s0 + 7); o.addend_hi = a.in.hi; o.addend_lo = a.in.lo; o.ld_addend = H;
+  o.out_f32 = a.y; o.ld_out = H;
+  XLX_TRY(linear(r, a.ctx, M, H, w.wo, H, o));
+  return ln_tail(r, a.y, M, P(r, s0 + 8), P(r, s0 + 9), a.out, out_f32, a.mean, a.rstd);
+}
+
+// LxmertXLayer.cross_att (HF:385-406): one shared attention module, both directions read the layer inputs.
+int att_cross_fwd(const Run& r, int blk) {
+  const Plan& p = r.plan;
+  const AttSave& a = p.att[blk];
+  const AttW& w = r.prep.att[blk];
+  const int s0 = att_slot(r.d, blk), H = p.H;
+  const size_t H3 = 3 * static_cast<size_t>(H);
+  GemmEpilogue e;
+  e.bias = w.bqkv; e.out_f32 = a.qkv; e.ld_out = 3 * H;
+  XLX_TRY(linear(r, a.in, p.Mt, H, w.wqkv, 3 * H, e));   // Q, K, V of all B·(L+V) tokens in one GEMM
+  const float* ql = a.qkv;                  // language rows
+  const float* qv = a.qkv + p.Ml * H3;      // vision rows
+  // language queries over vision keys/values (mask = visual attention mask, normally none)
+  XLX_TRY(attention_fwd(ql, qv + H, qv + 2 * H, 3 * H, r.vmask, p.B, p.heads, p.L, p.V, a.ctx, nullptr, H, a.probs,
+                        r.st));
+  // vision queries over language keys/values (mask = language attention mask)
+  XLX_TRY(attention_fwd(qv, ql + H, ql + 2 * H, 3 * H, r.lmask, p.B, p.heads, p.V, p.L, rows(a.ctx, p.Ml, H), nullptr,
+                        H, a.probs2, r.st));
+  GemmEpilogue o;
+  o.bias = P(r, s0 + 7); o.addend_hi = a.in.hi; o.addend_lo = a.in.lo; o.ld_addend = H;
+  o.out_f32 = a.y; o.ld_out = H;
+  XLX_TRY(linear(r, a.ctx, p.Mt, H, w.wo, H, o));
+  return ln_tail(r, a.y, p.Mt, P(r, s0 + 8), P(r, s0 + 9), a.out, nullptr, a.mean, a.rstd);
+}
+
+int ffn_fwd(const Run& r, int blk, float* out_f32) {
+  const Plan& p = r.plan;
+  const FfnSave& f = p.ffn[blk];
+  const FfnW& w = r.prep.ffn[blk];
+  const int s0 = ffn_slot(r.d, blk), H = p.H, I = p.I, M = f.M;
+  GemmEpilogue e;
+  e.bias = P(r, s0 + 1); e.flags = EPI_GELU; e.out_u = f.u; e.ld_u = I;
+  e.out_hi = f.h.hi; e.out_lo = f.h.lo; e.ld_split = I;
+  XLX_TRY(linear(r, f.in, M, H, w.w1, I, e));
+  GemmEpilogue o;
+  o.bias = P(r, s0 + 3); o.addend_hi = f.in.hi; o.addend_lo = f.in.lo; o.ld_addend = H;
+  o.out_f32 = f.y; o.ld_out = H;
+  XLX_TRY(linear(r, f.h, M, I, w.w2, H, o));
+  return ln_tail(r, f.y, M, P(r, s0 + 4), P(r, s0 + 5), f.out, out_f32, f.mean, f.rstd);
+}
+
+// ---- backward blocks -----------------------------------------------------------------------------
+// All take the gradient wrt the block output in `dout` ([M,H] fp32) and leave the gradient wrt the block
+// input in `din`.  Parameter gradients go to the flat arena `grads` at the slot offsets.
+struct Bwd {
+  const Run* r;
+  float* grads;
+  SlotTable slots;
+  float* G(int slot) const { return grads + slots.offset[slot]; }
+};
+
+int ln_tail_bwd(const Bwd& bw, const float* dout, const float* y, int slot_g, const float* mean, const float* rstd,
+                int M, float* dy, Split dy_s) {
+  const Run& r = *bw.r;
+  int nblk = 0;
+  XLX_TRY(layernorm_bwd(dout, 1.0f, y, P(r, slot_g), mean, rstd, M, r.plan.H, dy, dy_s, r.plan.part, &nblk, r.st));
+  float* outs[2] = {bw.G(slot_g), bw.G(slot_g + 1)};
+  return colsum_finish(r.plan.part, 2, nblk, r.plan.H, outs, 0, r.st);
+}
+
+int ffn_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
+  const Run& r = *bw.r;
+  const Plan& p = r.plan;
+  const FfnSave& f = p.ffn[blk];
+  const FfnW& w = r.prep.ffn[blk];
+  const int s0 = ffn_slot(r.d, blk), H = p.H, I = p.I, M = f.M;
+  XLX_TRY(ln_tail_bwd(bw, dout, f.y, s0 + 4, f.mean, f.rstd, M, p.dy, p.dy_s));
+  XLX_TRY(colsum(p.dy, Split(), M, H, H, p.part, bw.G(s0 + 3), r.st));
+  XLX_TRY(wgrad(r, p.dy_s, M, H, f.h, I, bw.G(s0 + 2)));
+  GemmEpilogue e;   // du = (dy · W2) ∘ gelu'(u)
+  e.flags = EPI_GELU_GRAD; e.u_in = f.u; e.ld_u = I; e.out_hi = p.du.hi; e.out_lo = p.du.lo; e.ld_split = I;
+  XLX_TRY(dgrad(r, p.dy_s, M, H, w.w2, I, e));
+  XLX_TRY(colsum(nullptr, p.du, M, I, I, p.part, bw.G(s0 + 1), r.st));
+  XLX_TRY(wgrad(r, p.du, M, I, f.in, H, bw.G(s0)));
+  GemmEpilogue o;   // din = du · W1 + dy (residual path)
+  o.addend = p.dy; o.ld_addend = H; o.out_f32 = din; o.ld_out = H;
+  return dgrad(r, p.du, M, I, w.w1, H, o);
+}
+
+// common tail/head of the attention backward: everything except the attention-core call(s)
+int att_bwd_head(const Bwd& bw, int blk, const float* dout) {
+  const Run& r = *bw.r;
+  const Plan& p = r.plan;
+  const AttSave& a = p.att[blk];
+  const AttW& w = r.prep.att[blk];
+  const int s0 = att_slot(r.d, blk), H = p.H, M = a.M;
+  XLX_TRY(ln_tail_bwd(bw, dout, a.y, s0 + 8, a.mean, a.rstd, M, p.dy, p.dy_s));
+  XLX_TRY(colsum(p.dy, Split(), M, H, H, p.part, bw.G(s0 + 7), r.st));
+  XLX_TRY(wgrad(r, p.dy_s, M, H, a.ctx, H, bw.G(s0 + 6)));
+  GemmEpilogue e;
+  e.out_f32 = p.dctx; e.ld_out = H;
+  return dgrad(r, p.dy_s, M, H, w.wo, H, e);
+}
+int att_bwd_tail(const Bwd& bw, int blk, float* din) {
+  const Run& r = *bw.r;
+  const Plan& p = r.plan;
+  const AttSave& a = p.att[blk];
+  const AttW& w = r.prep.att[blk];
+  const int s0 = att_slot(r.d, blk), H = p.H, M = a.M;
+  XLX_TRY(colsum(nullptr, p.dqkv, M, 3 * H, 3 * H, p.part, bw.G(s0 + 3), r.st));   // q.bias | k.bias | v.bias
+  XLX_TRY(wgrad(r, p.dqkv, M, 3 * H, a.in, H, bw.G(s0)));                          // q.w | k.w | v.w
+  GemmEpilogue o;
+  o.addend = p.dy; o.ld_addend = H; o.out_f32 = din; o.ld_out = H;
+  return dgrad(r, p.dqkv, M, 3 * H, w.wqkv, H, o);
+}
+int att_self_bwd(const Bwd& bw, int blk, int S, const float* dout, float* din) {
+  const Run& r = *bw.r;
+  const Plan& p = r.plan;
+  const AttSave& a = p.att[blk];
+  const int H = p.H;
+  XLX_TRY(att_bwd_head(bw, blk, dout));
+  Split dq = p.dqkv, dk = p.dqkv, dv = p.dqkv;
+  dk.hi += H; dk.lo += H; dv.hi += 2 * H; dv.lo += 2 * H;
+  XLX_TRY(attention_bwd(p.dctx, H, a.qkv, a.qkv + H, a.qkv + 2 * H, 3 * H, a.probs, p.B, p.heads, S, S, dq, dk, dv,
+                        3 * H, r.st));
+  return att_bwd_tail(bw, blk, din);
+}
+int att_cross_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
+  const Run& r = *bw.r;
+  const Plan& p = r.plan;
+  const AttSave& a = p.att[blk];
+  const int H = p.H;
+  const size_t H3 = 3 * static_cast<size_t>(H);
+  XLX_TRY(att_bwd_head(bw, blk, dout));
+  const float* ql = a.qkv;
+  const float* qv = a.qkv + p.Ml * H3;
+  Split dl = p.dqkv, dvv = rows(p.dqkv, p.Ml, H3);   // language rows / vision rows of dqkv
+  auto col = [](Split s, int c) { s.hi += c; s.lo += c; return s; };
+  // language queries: dQ → language rows, dK/dV → vision rows
+  XLX_TRY(attention_bwd(p.dctx, H, ql, qv + H, qv + 2 * H, 3 * H, a.probs, p.B, p.heads, p.L, p.V, col(dl, 0),
+                        col(dvv, H), col(dvv, 2 * H), 3 * H, r.st));
+  // vision queries: dQ → vision rows, dK/dV → language rows
+  XLX_TRY(attention_bwd(p.dctx + static_cast<size_t>(p.Ml) * H, H, qv, ql + H, ql + 2 * H, 3 * H, a.probs2, p.B,
+                        p.heads, p.V, p.L, col(dvv, 0), col(dl, H), col(dl, 2 * H), 3 * H, r.st));
+  return att_bwd_tail(bw, blk, din);
+}
+
+// The caller (PyTorch) may have selected the device through a different copy of the CUDA runtime; make this
+// library's runtime agree with the device that owns the caller's buffers.
+int ensure_device(const void* ptr) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (at.type != cudaMemoryTypeDevice) return 0;
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur != at.device) {
+    cudaError_t e = cudaSetDevice(at.device);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  return 0;
+}
+
+int check_common(const xlx_dims* d, int B, int L, int V) {
+  if (!dims_ok(d)) return -20;
+  if (B < 1 || L < 1 || V < 1) return -21;
+  if (L > 64 || V > 64) return -22;
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* xlx_version(void) { return "xlxmert_b200 0.1.0 (sm_100a)"; }
+
+const char* xlx_strerror(int32_t code) {
+  switch (code) {
+    case 0: return "ok";
+    case -1: return "invalid GEMM arguments";
+    case -2: return "misaligned pointer or leading dimension (16-byte granularity required)";
+    case -3: return "GEMM tile does not fit shared memory";
+    case -4: return "unsupported hidden size for LayerNorm (128/256/512/768/1024)";
+    case -5: return "attention sequence length out of range (1..64)";
+    case -10: return "cuTensorMapEncodeTiled unavailable (driver too old?)";
+    case -11: return "cuTensorMapEncodeTiled failed";
+    case -20: return "unsupported xlx_dims";
+    case -21: return "batch / sequence sizes must be positive";
+    case -22: return "sequence length > 64 is not supported by the attention kernel";
+    case -23: return "workspace too small";
+    case -24: return "null pointer argument";
+    default: return code > 0 ? "CUDA error (see cudaGetErrorString)" : "unknown error";
+  }
+}
+
+int64_t xlx_launch_count(void) { return gemm_launch_count() + aux_launch_count(); }
+int64_t xlx_gemm_launch_count(void) { return gemm_launch_count(); }
+void xlx_profile_gemm_begin(void) { gemm_timing_begin(); }
+int32_t xlx_profile_gemm_end(double* total_ms, double* total_flops, int64_t* launches) {
+  long long n = 0;
+  int rc = gemm_timing_end(total_ms, total_flops, &n);
+  *launches = n;
+  return rc;
+}
+
+int64_t xlx_encoder_num_params(const xlx_dims* d) {
+  return dims_ok(d) ? static_cast<int64_t>(slot_table(d).elems.size()) : -20;
+}
+int64_t xlx_encoder_param_elems(const xlx_dims* d, int64_t slot) {
+  if (!dims_ok(d)) return -20;
+  SlotTable t = slot_table(d);
+  return (slot < 0 || slot >= static_cast<int64_t>(t.elems.size())) ? -1 : t.elems[slot];
+}
+int64_t xlx_encoder_grad_offset(const xlx_dims* d, int64_t slot) {
+  if (!dims_ok(d)) return -20;
+  SlotTable t = slot_table(d);
+  return (slot < 0 || slot >= static_cast<int64_t>(t.offset.size())) ? -1 : t.offset[slot];
+}
+int64_t xlx_encoder_grad_elems(const xlx_dims* d) { return dims_ok(d) ? slot_table(d).total : -20; }
+
+size_t xlx_encoder_prep_bytes(const xlx_dims* d) { return dims_ok(d) ? prep_layout(d, nullptr).bytes : 0; }
+
+int32_t xlx_encoder_prepare(const xlx_dims* d, const float* const* params, void* prep, void* stream) {
+  if (!dims_ok(d)) return -20;
+  if (!params || !prep) return -24;
+  XLX_TRY(ensure_device(prep));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Prep p = prep_layout(d, prep);
+  const size_t H = d->hidden, I = d->intermediate, F = d->feat_dim;
+  XLX_TRY(split_f32(params[0], p.visn_w, H * F, st));
+  for (size_t blk = 0; blk < p.att.size(); ++blk) {
+    const int s0 = att_slot(d, static_cast<int>(blk));
+    const AttW& a = p.att[blk];
+    for (int j = 0; j < 3; ++j) XLX_TRY(split_f32(params[s0 + j], rows(a.wqkv, j * H, H), H * H, st));
+    XLX_TRY(concat3_f32(params[s0 + 3], params[s0 + 4], params[s0 + 5], a.bqkv, static_cast<int>(H), st));
+    XLX_TRY(split_f32(params[s0 + 6], a.wo, H * H, st));
+  }
+  for (size_t blk = 0; blk < p.ffn.size(); ++blk) {
+    const int s0 = ffn_slot(d, static_cast<int>(blk));
+    XLX_TRY(split_f32(params[s0], p.ffn[blk].w1, I * H, st));
+    XLX_TRY(split_f32(params[s0 + 2], p.ffn[blk].w2, H * I, st));
+  }
+  return 0;
+}
+
+size_t xlx_encoder_workspace_bytes(const xlx_dims* d, int32_t B, int32_t L, int32_t V, int32_t training) {
+  if (check_common(d, B, L, V)) return 0;
+  return make_plan(d, B, L, V, training != 0, nullptr).bytes;
+}
+
+int32_t xlx_encoder_fwd(const xlx_dims* d, const float* const* params, const void* prep, int32_t B, int32_t L,
+                        int32_t V, const float* lang_in, const float* lang_mask, const float* visual_feats,
+                        const float* visual_pos, const float* vis_mask, float* lang_out, float* vis_out,
+                        float* lang_hidden, float* vis_hidden, void* workspace, size_t workspace_bytes,
+                        int32_t training, int32_t passes, void* stream) {
+  XLX_TRY(check_common(d, B, L, V));
+  if (!params || !prep || !lang_in || !visual_feats || !visual_pos || !lang_out || !vis_out || !workspace) return -24;
+  if (passes != 1 && passes != 3) return -1;
+  XLX_TRY(ensure_device(workspace));
+  Run r;
+  r.d = d; r.params = params; r.passes = passes; r.st = static_cast<cudaStream_t>(stream);
+  r.lmask = lang_mask; r.vmask = vis_mask;
+  r.prep = prep_layout(d, const_cast<void*>(prep));
+  r.plan = make_plan(d, B, L, V, training != 0, workspace);
+  const Plan& p = r.plan;
+  if (p.bytes > workspace_bytes) return -23;
+  const int H = p.H, F = p.F, Ml = p.Ml, Mv = p.Mv;
+  const int nl = d->l_layers, nr = d->r_layers, nx = d->x_layers;
+  const size_t lh = static_cast<size_t>(Ml) * H, vh = static_cast<size_t>(Mv) * H;
+  auto hidden_ptr = [&](float* base, int idx, size_t stride, bool last, float* final_out) -> float* {
+    if (base) return base + idx * stride;
+    return last ? final_out : nullptr;
+  };
+
+  // ---- visual feature encoder (HF:476-484): (LN(W·feat + b) + LN(Wp·pos + bp)) / 2
+  XLX_TRY(split_f32(visual_feats, p.feats, static_cast<size_t>(Mv) * F, r.st));
+  {
+    GemmEpilogue e;
+    e.bias = P(r, 1); e.out_f32 = p.y1; e.ld_out = H;
+    XLX_TRY(linear(r, p.feats, Mv, F, r.prep.visn_w, H, e));
+    XLX_TRY(box_linear_fwd(visual_pos, P(r, 4), P(r, 5), Mv, H, p.y2, r.st));
+    XLX_TRY(layernorm_fwd(p.y2, P(r, 6), P(r, 7), d->ln_eps, Mv, H, 0.5f, nullptr, Split(), p.tbox,
+                          p.training ? p.vstats + 2 * Mv : nullptr, p.training ? p.vstats + 3 * Mv : nullptr, r.st));
+    XLX_TRY(layernorm_fwd(p.y1, P(r, 2), P(r, 3), d->ln_eps, Mv, H, 0.5f, p.tbox, p.vis0, nullptr,
+                          p.training ? p.vstats : nullptr, p.training ? p.vstats + Mv : nullptr, r.st));
+  }
+  XLX_TRY(split_f32(lang_in, p.lang0, lh, r.st));
+
+  // ---- language layers (HF:524-529), then vision layers (HF:532-537)
+  for (int i = 0; i < nl; ++i) {
+    XLX_TRY(att_self_fwd(r, i, L, lang_mask, nullptr));
+    XLX_TRY(ffn_fwd(r, i, hidden_ptr(lang_hidden, i, lh, nx == 0 && i == nl - 1, lang_out)));
+  }
+  for (int i = 0; i < nr; ++i) {
+    XLX_TRY(att_self_fwd(r, nl + i, V, vis_mask, nullptr));
+    XLX_TRY(ffn_fwd(r, nl + i, hidden_ptr(vis_hidden, i, vh, nx == 0 && i == nr - 1, vis_out)));
+  }
+  // ---- cross-modality layers (HF:540-552): cross → self → FFN
+  for (int k = 0; k < nx; ++k) {
+    const int a0 = nl + nr + 3 * k, f0 = nl + nr + 2 * k;
+    const bool last = (k == nx - 1);
+    XLX_TRY(att_cross_fwd(r, a0));
+    XLX_TRY(att_self_fwd(r, a0 + 1, L, lang_mask, nullptr));
+    XLX_TRY(att_self_fwd(r, a0 + 2, V, vis_mask, nullptr));
+    XLX_TRY(ffn_fwd(r, f0, hidden_ptr(lang_hidden, nl + k, lh, last, lang_out)));
+    XLX_TRY(ffn_fwd(r, f0 + 1, hidden_ptr(vis_hidden, nr + k, vh, last, vis_out)));
+  }
+  // final outputs: when hidden states were requested the last state was written there — copy it out
+  const int n_lang_states = nl + nx, n_vis_states = nr + nx;
+  if (lang_hidden && n_lang_states > 0) {
+    cudaError_t e = cudaMemcpyAsync(lang_out, lang_hidden + (n_lang_states - 1) * lh, lh * 4, cudaMemcpyDeviceToDevice, r.st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  if (vis_hidden && n_vis_states > 0) {
+    cudaError_t e = cudaMemcpyAsync(vis_out, vis_hidden + (n_vis_states - 1) * vh, vh * 4, cudaMemcpyDeviceToDevice, r.st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  if (n_lang_states == 0) XLX_TRY(unsplit_f32(p.lang0, lang_out, lh, r.st));
+  if (n_vis_states == 0) XLX_TRY(unsplit_f32(p.vis0, vis_out, vh, r.st));
+  return 0;
+}
+
+int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const void* prep, int32_t B, int32_t L,
+                        int32_t V, const float* visual_pos, const float* d_lang_out, const float* d_vis_out,
+                        float* d_lang_in, float* d_visual_feats, float* grads, void* workspace,
+                        size_t workspace_bytes, int32_t passes, void* stream) {
+  XLX_TRY(check_common(d, B, L, V));
+  if (!params || !prep || !visual_pos || !d_lang_in || !grads || !workspace) return -24;
+  if (passes != 1 && passes != 3) return -1;
+  XLX_TRY(ensure_device(workspace));
+  Run r;
+  r.d = d; r.params = params; r.passes = passes; r.st = static_cast<cudaStream_t>(stream);
+  r.lmask = nullptr; r.vmask = nullptr;
+  r.prep = prep_layout(d, const_cast<void*>(prep));
+  r.plan = make_plan(d, B, L, V, true, workspace);
+  const Plan& p = r.plan;
+  if (p.bytes > workspace_bytes) return -23;
+  Bwd bw;
+  bw.r = &r; bw.grads = grads; bw.slots = slot_table(d);
+  const int H = p.H, F = p.F, Ml = p.Ml, Mv = p.Mv;
+  const int nl = d->l_layers, nr = d->r_layers, nx = d->x_layers;
+  const size_t lh = static_cast<size_t>(Ml) * H, vh = static_cast<size_t>(Mv) * H;
+
+  // gradient state: [language rows | vision rows], ping-pong between dA and dB
+  float* cur = p.dA;
+  float* nxt = p.dB;
+  auto load_grad = [&](float* dst, const float* src, size_t n) -> int {
+    cudaError_t e = src ? cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, r.st)
+                        : cudaMemsetAsync(dst, 0, n * 4, r.st);
+    return e == cudaSuccess ? 0 : static_cast<int>(e);
+  };
+  XLX_TRY(load_grad(cur, d_lang_out, lh));
+  XLX_TRY(load_grad(cur + lh, d_vis_out, vh));
+
+  for (int k = nx - 1; k >= 0; --k) {
+    const int a0 = nl + nr + 3 * k, f0 = nl + nr + 2 * k;
+    XLX_TRY(ffn_bwd(bw, f0, cur, nxt));
+    XLX_TRY(ffn_bwd(bw, f0 + 1, cur + lh, nxt + lh));
+    XLX_TRY(att_self_bwd(bw, a0 + 1, L, nxt, cur));
+    XLX_TRY(att_self_bwd(bw, a0 + 2, V, nxt + lh, cur + lh));
+    XLX_TRY(att_cross_bwd(bw, a0, cur, nxt));
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  for (int i = nr - 1; i >= 0; --i) {
+    XLX_TRY(ffn_bwd(bw, nl + i, cur + lh, nxt + lh));
+    XLX_TRY(att_self_bwd(bw, nl + i, V, nxt + lh, cur + lh));
+  }
+  for (int i = nl - 1; i >= 0; --i) {
+    XLX_TRY(ffn_bwd(bw, i, cur, nxt));
+    XLX_TRY(att_self_bwd(bw, i, L, nxt, cur));
+  }
+  // language embedding gradient
+  {
+    cudaError_t e = cudaMemcpyAsync(d_lang_in, cur, lh * 4, cudaMemcpyDeviceToDevice, r.st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  // visual feature encoder backward
+  {
+    const float* dvis = cur + lh;
+    int nblk = 0;
+    // box branch: d(0.5·LN_b(y2))
+    XLX_TRY(layernorm_bwd(dvis, 0.5f, p.y2, P(r, 6), p.vstats + 2 * Mv, p.vstats + 3 * Mv, Mv, H, p.dy2, Split(),
+                          p.part, &nblk, r.st));
+    float* o2[2] = {bw.G(6), bw.G(7)};
+    XLX_TRY(colsum_finish(p.part, 2, nblk, H, o2, 0, r.st));
+    XLX_TRY(box_linear_bwd(p.dy2, visual_pos, Mv, H, p.part, bw.G(4), bw.G(5), r.st));
+    // feature branch: d(0.5·LN_v(y1))
+    XLX_TRY(layernorm_bwd(dvis, 0.5f, p.y1, P(r, 2), p.vstats, p.vstats + Mv, Mv, H, p.dy, p.dy_s, p.part, &nblk, r.st));
+    float* o1[2] = {bw.G(2), bw.G(3)};
+    XLX_TRY(colsum_finish(p.part, 2, nblk, H, o1, 0, r.st));
+    XLX_TRY(colsum(p.dy, Split(), Mv, H, H, p.part, bw.G(1), r.st));
+    XLX_TRY(wgrad(r, p.dy_s, Mv, H, p.feats, F, bw.G(0)));
+    if (d_visual_feats) {
+      GemmEpilogue e;
+      e.out_f32 = d_visual_feats; e.ld_out = F;
+      XLX_TRY(dgrad(r, p.dy_s, Mv, H, r.prep.visn_w, F, e));
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

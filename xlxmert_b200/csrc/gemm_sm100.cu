@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "xlx_ptx.cuh"
 
@@ -360,6 +361,11 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 std::mutex g_maps_mu;
 std::atomic<long long> g_launches{0};
 
+// optional per-launch timing (bench.py roofline): events bracket every GEMM on its own stream
+struct TimedLaunch { cudaEvent_t e0, e1; double flops; };
+bool g_timing = false;
+std::vector<TimedLaunch> g_timed;
+
 // bf16 row-major [outer, inner] with leading dimension ld (elements); box = box0 (inner) × box1 (outer).
 int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box0,
              uint32_t box1, CUtensorMapSwizzle swz) {
@@ -446,7 +452,18 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   const int num_tiles = P.tiles_m * P.tiles_n;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   const size_t smem = static_cast<size_t>(stages) * P.stage_bytes + 1024;
+  TimedLaunch tl{};
+  if (g_timing) {
+    cudaEventCreate(&tl.e0);
+    cudaEventCreate(&tl.e1);
+    tl.flops = 2.0 * p.M * p.N * p.K;
+    cudaEventRecord(tl.e0, stream);
+  }
   gemm_kernel<BK><<<grid, GEMM_THREADS, smem, stream>>>(mAhi, mAlo, mBhi, mBlo, P);
+  if (g_timing) {
+    cudaEventRecord(tl.e1, stream);
+    g_timed.push_back(tl);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);
@@ -455,6 +472,27 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
 }  // namespace
 
 long long gemm_launch_count() { return g_launches.load(); }
+
+void gemm_timing_begin() {
+  g_timed.clear();
+  g_timing = true;
+}
+int gemm_timing_end(double* total_ms, double* total_flops, long long* launches) {
+  g_timing = false;
+  double ms = 0, fl = 0;
+  for (auto& t : g_timed) {
+    cudaError_t e = cudaEventSynchronize(t.e1);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    float m = 0;
+    cudaEventElapsedTime(&m, t.e0, t.e1);
+    ms += m; fl += t.flops;
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  *total_ms = ms; *total_flops = fl; *launches = static_cast<long long>(g_timed.size());
+  g_timed.clear();
+  return 0;
+}
 
 int gemm_launch(const GemmProblem& p, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return -1;

@@ -62,5 +62,8 @@ struct GemmProblem {
 int gemm_launch(const GemmProblem& p, cudaStream_t stream);
 // Number of kernels launched by gemm_launch since process start (bench bookkeeping).
 long long gemm_launch_count();
+// Per-launch CUDA-event timing of every GEMM between begin and end (algorithmic FLOPs = 2·M·N·K each).
+void gemm_timing_begin();
+int gemm_timing_end(double* total_ms, double* total_flops, long long* launches);
 
 }  // namespace xlx

@@ -1,0 +1,684 @@
+// Non-GEMM kernels of the X-LXMERT hot path — see kernels.cuh.
+#include "kernels.cuh"
+
+#include <atomic>
+
+#include "xlx_ptx.cuh"
+
+namespace xlx {
+
+namespace {
+
+std::atomic<long long> g_aux_launches{0};
+constexpr int kMaxBlocks = 592;  // 4 × 148 SMs: enough CTAs in flight for the HBM-bound reductions
+
+inline int launch_rc() {
+  g_aux_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float bf16lo_to_f32(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi_to_f32(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// store 4 floats as split bf16 (8 bytes to hi, 8 bytes to lo)
+__device__ __forceinline__ void store_split4(bf16* hi, bf16* lo, size_t idx, float4 v) {
+  bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+  split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+  *reinterpret_cast<uint2*>(hi + idx) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+  if (lo) *reinterpret_cast<uint2*>(lo + idx) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+}
+__device__ __forceinline__ float4 load_split4(const bf16* hi, const bf16* lo, size_t idx) {
+  uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + idx));
+  float4 v = make_float4(bf16lo_to_f32(h.x), bf16hi_to_f32(h.x), bf16lo_to_f32(h.y), bf16hi_to_f32(h.y));
+  if (lo) {
+    uint2 l = __ldg(reinterpret_cast<const uint2*>(lo + idx));
+    v.x += bf16lo_to_f32(l.x); v.y += bf16hi_to_f32(l.x); v.z += bf16lo_to_f32(l.y); v.w += bf16hi_to_f32(l.y);
+  }
+  return v;
+}
+
+// ---- elementwise -----------------------------------------------------------------------------
+__global__ void split_kernel(const float4* __restrict__ x, bf16* hi, bf16* lo, size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    store_split4(hi, lo, i * 4, __ldg(x + i));
+}
+__global__ void unsplit_kernel(const bf16* hi, const bf16* lo, float4* out, size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = load_split4(hi, lo, i * 4);
+}
+__global__ void fill_kernel(float* dst, float v, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = v;
+}
+__global__ void concat3_kernel(const float* a, const float* b, const float* c, float* dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3 * n) dst[i] = i < n ? a[i] : (i < 2 * n ? b[i - n] : c[i - 2 * n]);
+}
+// one CTA per output row
+__global__ void gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,
+                                   const uint8_t* __restrict__ mask, const float* __restrict__ fill, int cols,
+                                   float* out_f32, bf16* hi, bf16* lo) {
+  const int r = blockIdx.x;
+  const bool m = mask && mask[r];
+  const float4* src = reinterpret_cast<const float4*>(m ? fill : table + static_cast<size_t>(ids[r]) * cols);
+  for (int c = threadIdx.x; c < cols / 4; c += blockDim.x) {
+    float4 v = __ldg(src + c);
+    size_t idx = static_cast<size_t>(r) * cols + c * 4;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + idx) = v;
+    if (hi) store_split4(hi, lo, idx, v);
+  }
+}
+
+inline int grid_for(size_t n, int threads) {
+  size_t b = (n + threads - 1) / threads;
+  return static_cast<int>(b < 148 * 16 ? (b ? b : 1) : 148 * 16);
+}
+
+// ---- LayerNorm -------------------------------------------------------------------------------
+// One warp per row; a lane owns NV float4 chunks (columns 4·(lane + 32k) …).  H = NV·128.
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+              int M, float out_scale, const float* __restrict__ addend, bf16* hi, bf16* lo, float* out_f32,
+              float* mean, float* rstd) {
+  constexpr int H = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float4* src = reinterpret_cast<const float4*>(y + static_cast<size_t>(row) * H);
+  float4 x[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    x[k] = __ldg(src + lane + 32 * k);
+    s += (x[k].x + x[k].y) + (x[k].z + x[k].w);
+  }
+  const float mu = warp_sum(s) * (1.0f / H);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    x[k].x -= mu; x[k].y -= mu; x[k].z -= mu; x[k].w -= mu;
+    q += (x[k].x * x[k].x + x[k].y * x[k].y) + (x[k].z * x[k].z + x[k].w * x[k].w);
+  }
+  const float var = warp_sum(q) * (1.0f / H);
+  const float r = 1.0f / sqrtf(var + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = r;
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c4 = lane + 32 * k;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 o;
+    o.x = (x[k].x * r * g.x + b.x) * out_scale; o.y = (x[k].y * r * g.y + b.y) * out_scale;
+    o.z = (x[k].z * r * g.z + b.z) * out_scale; o.w = (x[k].w * r * g.w + b.w) * out_scale;
+    const size_t idx = static_cast<size_t>(row) * H + c4 * 4;
+    if (addend) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(addend + idx));
+      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + idx) = o;
+    if (hi) store_split4(hi, lo, idx, o);
+  }
+}
+
+// Warps stride over rows; per-lane dgamma/dbeta partials are reduced across the CTA's warps through
+// shared memory and written to part[0/1][blockIdx.x][H].
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ dy, float dy_scale, const float* __restrict__ y,
+              const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, int M,
+              float* dx, bf16* dx_hi, bf16* dx_lo, float* part) {
+  constexpr int H = NV * 128;
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  float4 dg[NV], db[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) { dg[k] = make_float4(0, 0, 0, 0); db[k] = make_float4(0, 0, 0, 0); }
+  for (int row = blockIdx.x * nwarp + warp; row < M; row += gridDim.x * nwarp) {
+    const float mu = mean[row], r = rstd[row];
+    const float4* py = reinterpret_cast<const float4*>(y + static_cast<size_t>(row) * H);
+    const float4* pd = reinterpret_cast<const float4*>(dy + static_cast<size_t>(row) * H);
+    float4 xh[NV], dxh[NV];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c4 = lane + 32 * k;
+      const float4 yv = __ldg(py + c4);
+      float4 d = pd[c4];
+      d.x *= dy_scale; d.y *= dy_scale; d.z *= dy_scale; d.w *= dy_scale;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      xh[k] = make_float4((yv.x - mu) * r, (yv.y - mu) * r, (yv.z - mu) * r, (yv.w - mu) * r);
+      dxh[k] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+      dg[k].x += d.x * xh[k].x; dg[k].y += d.y * xh[k].y; dg[k].z += d.z * xh[k].z; dg[k].w += d.w * xh[k].w;
+      db[k].x += d.x; db[k].y += d.y; db[k].z += d.z; db[k].w += d.w;
+      c1 += (dxh[k].x + dxh[k].y) + (dxh[k].z + dxh[k].w);
+      c2 += (dxh[k].x * xh[k].x + dxh[k].y * xh[k].y) + (dxh[k].z * xh[k].z + dxh[k].w * xh[k].w);
+    }
+    c1 = warp_sum(c1) * (1.0f / H);
+    c2 = warp_sum(c2) * (1.0f / H);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float4 o;
+      o.x = r * (dxh[k].x - c1 - xh[k].x * c2); o.y = r * (dxh[k].y - c1 - xh[k].y * c2);
+      o.z = r * (dxh[k].z - c1 - xh[k].z * c2); o.w = r * (dxh[k].w - c1 - xh[k].w * c2);
+      const size_t idx = static_cast<size_t>(row) * H + (lane + 32 * k) * 4;
+      if (dx) *reinterpret_cast<float4*>(dx + idx) = o;
+      if (dx_hi) store_split4(dx_hi, dx_lo, idx, o);
+    }
+  }
+  // cross-warp reduction of the column partials
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      __syncthreads();
+      red[warp][lane] = v ? db[k] : dg[k];
+      __syncthreads();
+      if (warp == 0) {
+        float4 a = red[0][lane];
+        for (int w = 1; w < nwarp; ++w) {
+          a.x += red[w][lane].x; a.y += red[w][lane].y; a.z += red[w][lane].z; a.w += red[w][lane].w;
+        }
+        float* dst = part + (static_cast<size_t>(v) * gridDim.x + blockIdx.x) * H + (lane + 32 * k) * 4;
+        *reinterpret_cast<float4*>(dst) = a;
+      }
+    }
+  }
+}
+
+// out_v[h] = Σ_blk part[v][blk][h]; grid (ceil(H/256), nvec)
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int nblk, int H, float* o0, float* o1, float* o2,
+                                     float* o3, float* o4, int accumulate) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = blockIdx.y;
+  float* out = v == 0 ? o0 : v == 1 ? o1 : v == 2 ? o2 : v == 3 ? o3 : o4;
+  if (h >= H || !out) return;
+  const float* p = part + static_cast<size_t>(v) * nblk * H + h;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int b = 0;
+  for (; b + 4 <= nblk; b += 4) {
+    a0 += p[static_cast<size_t>(b) * H]; a1 += p[static_cast<size_t>(b + 1) * H];
+    a2 += p[static_cast<size_t>(b + 2) * H]; a3 += p[static_cast<size_t>(b + 3) * H];
+  }
+  for (; b < nblk; ++b) a0 += p[static_cast<size_t>(b) * H];
+  const float sum = (a0 + a1) + (a2 + a3);
+  out[h] = accumulate ? out[h] + sum : sum;
+}
+
+// Column sums: CTA = 32 column quads (128 columns) × 8 row lanes; grid (ceil(N/128), nblk).
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ xf, const bf16* __restrict__ xh, const bf16* __restrict__ xl, int M, int N,
+              int ld, float* scratch) {
+  __shared__ float4 red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 4;
+  float4 a = make_float4(0, 0, 0, 0);
+  if (col < N) {
+    for (int m = blockIdx.y * 8 + ty; m < M; m += gridDim.y * 8) {
+      const size_t idx = static_cast<size_t>(m) * ld + col;
+      float4 v = xf ? __ldg(reinterpret_cast<const float4*>(xf + idx)) : load_split4(xh, xl, idx);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  }
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && col < N) {
+    for (int w = 1; w < 8; ++w) { a.x += red[w][tx].x; a.y += red[w][tx].y; a.z += red[w][tx].z; a.w += red[w][tx].w; }
+    *reinterpret_cast<float4*>(scratch + static_cast<size_t>(blockIdx.y) * N + col) = a;
+  }
+}
+
+// ---- box-position linear ------------------------------------------------------------------------
+__global__ void box_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ Wp,
+                               const float* __restrict__ bp, int M, int H, float* y2) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<size_t>(M) * H) return;
+  const int m = i / H, h = i % H;
+  const float4 p = __ldg(reinterpret_cast<const float4*>(pos) + m);
+  const float4 w = __ldg(reinterpret_cast<const float4*>(Wp) + h);
+  // same association as a K=4 dot product followed by the bias add
+  y2[i] = (((p.x * w.x + p.y * w.y) + p.z * w.z) + p.w * w.w) + __ldg(bp + h);
+}
+// CTA = 128 columns × 2 row lanes (256 threads); grid (ceil(H/128), nblk).  part[5][nblk][H]
+__global__ void __launch_bounds__(256)
+box_bwd_kernel(const float* __restrict__ dy2, const float* __restrict__ pos, int M, int H, float* part) {
+  __shared__ float red[5][128];
+  const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
+  const int h = blockIdx.x * 128 + tx;
+  float a[5] = {0, 0, 0, 0, 0};
+  if (h < H) {
+    for (int m = blockIdx.y * 2 + ty; m < M; m += gridDim.y * 2) {
+      const float d = __ldg(dy2 + static_cast<size_t>(m) * H + h);
+      const float4 p = __ldg(reinterpret_cast<const float4*>(pos) + m);
+      a[0] += d * p.x; a[1] += d * p.y; a[2] += d * p.z; a[3] += d * p.w; a[4] += d;
+    }
+  }
+  if (ty == 1) for (int v = 0; v < 5; ++v) red[v][tx] = a[v];
+  __syncthreads();
+  if (ty == 0 && h < H)
+    for (int v = 0; v < 5; ++v)
+      part[(static_cast<size_t>(v) * gridDim.y + blockIdx.y) * H + h] = a[v] + red[v][tx];
+}
+// dWp[h][j] = t[j][h]
+__global__ void box_pack_kernel(const float* t, int H, float* dWp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4 * H) dWp[i] = t[(i & 3) * H + (i >> 2)];
+}
+
+// ---- attention core -----------------------------------------------------------------------------
+// CTA (128 threads) per (head, sample).  Thread (ti = tid/8, tj = tid%8) owns rows {ti + 16·ii} and, for
+// score-shaped tiles, columns {tj + 8·jj}; for [rows, 64]-shaped outputs, feature columns 4·tj.. and 32+4·tj..
+// All shared tiles are row-major with a 68-float pitch (float4 aligned, conflict-free for these patterns).
+constexpr int AT = 128;
+constexpr int LDS = 68;
+
+__device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ src, int ld, int rows, int rows_pad) {
+  // rows × 64 fp32 → dst[rows_pad][LDS], zero padded
+  for (int idx = threadIdx.x; idx < rows_pad * 16; idx += AT) {
+    const int r = idx >> 4, c4 = idx & 15;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (r < rows) v = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(r) * ld) + c4);
+    *reinterpret_cast<float4*>(dst + r * LDS + c4 * 4) = v;
+  }
+}
+
+// acc[ii][jj] = Σ_d A[ti+16ii][d] · Bm[tj+8jj][d]   (A, Bm row-major tiles, contraction over 64 features)
+template <int NI, int NJ>
+__device__ __forceinline__ void tile_abt(const float* A, const float* Bm, int ti, int tj, float (&acc)[NI][NJ]) {
+#pragma unroll
+  for (int ii = 0; ii < NI; ++ii)
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) acc[ii][jj] = 0.f;
+#pragma unroll 4
+  for (int d = 0; d < 64; d += 4) {
+    float4 a[NI], b[NJ];
+#pragma unroll
+    for (int ii = 0; ii < NI; ++ii) a[ii] = *reinterpret_cast<const float4*>(A + (ti + 16 * ii) * LDS + d);
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) b[jj] = *reinterpret_cast<const float4*>(Bm + (tj + 8 * jj) * LDS + d);
+#pragma unroll
+    for (int ii = 0; ii < NI; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj)
+        acc[ii][jj] += (a[ii].x * b[jj].x + a[ii].y * b[jj].y) + (a[ii].z * b[jj].z + a[ii].w * b[jj].w);
+  }
+}
+
+// out[r][c] (r = ti + 16·rr, 8 feature columns per thread) = Σ_{t < T} W[r][t] · X[t][c]
+template <int NR>
+__device__ __forceinline__ void tile_ab(const float* W, const float* X, int T, int ti, int tj, float4 (&o0)[NR],
+                                        float4 (&o1)[NR]) {
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) { o0[rr] = make_float4(0, 0, 0, 0); o1[rr] = make_float4(0, 0, 0, 0); }
+  for (int t = 0; t < T; t += 4) {
+    float4 w[NR];
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr) w[rr] = *reinterpret_cast<const float4*>(W + (ti + 16 * rr) * LDS + t);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 x0 = *reinterpret_cast<const float4*>(X + (t + u) * LDS + 4 * tj);
+      const float4 x1 = *reinterpret_cast<const float4*>(X + (t + u) * LDS + 32 + 4 * tj);
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        const float wv = u == 0 ? w[rr].x : u == 1 ? w[rr].y : u == 2 ? w[rr].z : w[rr].w;
+        o0[rr].x += wv * x0.x; o0[rr].y += wv * x0.y; o0[rr].z += wv * x0.z; o0[rr].w += wv * x0.w;
+        o1[rr].x += wv * x1.x; o1[rr].y += wv * x1.y; o1[rr].z += wv * x1.z; o1[rr].w += wv * x1.w;
+      }
+    }
+  }
+}
+
+template <int NI, int NJ>
+__global__ void __launch_bounds__(AT)
+attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int ld,
+                const float* __restrict__ mask, int heads, int Sq, int Sk, bf16* ctx_hi, bf16* ctx_lo, float* ctx_f32,
+                int ld_ctx, float* probs) {
+  extern __shared__ float sm[];
+  constexpr int RI = NI * 16, RJ = NJ * 8;
+  float* Qs = sm;                 // [RI][LDS]
+  float* Ks = Qs + RI * LDS;      // [RJ][LDS]
+  float* Vs = Ks + RJ * LDS;      // [RJ][LDS]
+  float* Ps = Vs + RJ * LDS;      // [RI][LDS]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int ti = threadIdx.x >> 3, tj = threadIdx.x & 7;
+  const size_t qrow0 = static_cast<size_t>(b) * Sq, krow0 = static_cast<size_t>(b) * Sk;
+  load_tile(Qs, q + qrow0 * ld + h * 64, ld, Sq, RI);
+  load_tile(Ks, k + krow0 * ld + h * 64, ld, Sk, RJ);
+  load_tile(Vs, v + krow0 * ld + h * 64, ld, Sk, RJ);
+  __syncthreads();
+
+  float s[NI][NJ];
+  tile_abt<NI, NJ>(Qs, Ks, ti, tj, s);
+  float mk[NJ];
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
+    const int j = tj + 8 * jj;
+    mk[jj] = (j < Sk) ? (mask ? __ldg(mask + static_cast<size_t>(b) * Sk + j) : 0.f) : -INFINITY;
+  }
+#pragma unroll
+  for (int ii = 0; ii < NI; ++ii) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      s[ii][jj] = s[ii][jj] * 0.125f + mk[jj];   // scores / sqrt(64) then + mask (HF:255-259)
+      mx = fmaxf(mx, s[ii][jj]);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) { s[ii][jj] = expf(s[ii][jj] - mx); sum += s[ii][jj]; }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    const float inv = 1.0f / sum;
+    const int i = ti + 16 * ii;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const float p = s[ii][jj] * inv;
+      const int j = tj + 8 * jj;
+      Ps[i * LDS + j] = p;
+      if (probs && i < Sq && j < Sk) probs[((static_cast<size_t>(b) * heads + h) * Sq + i) * Sk + j] = p;
+    }
+  }
+  __syncthreads();
+  float4 o0[NI], o1[NI];
+  tile_ab<NI>(Ps, Vs, RJ, ti, tj, o0, o1);
+#pragma unroll
+  for (int ii = 0; ii < NI; ++ii) {
+    const int i = ti + 16 * ii;
+    if (i < Sq) {
+      const size_t idx = (qrow0 + i) * ld_ctx + h * 64 + 4 * tj;
+      if (ctx_hi) { store_split4(ctx_hi, ctx_lo, idx, o0[ii]); store_split4(ctx_hi, ctx_lo, idx + 32, o1[ii]); }
+      if (ctx_f32) {
+        *reinterpret_cast<float4*>(ctx_f32 + idx) = o0[ii];
+        *reinterpret_cast<float4*>(ctx_f32 + idx + 32) = o1[ii];
+      }
+    }
+  }
+}
+
+// Backward of the attention core.  dP = dO·Vᵀ; dS = P ∘ (dP − rowsum(P ∘ dP)) / 8;
+// dV = Pᵀ·dO, dK = dSᵀ·Q, dQ = dS·K.
+template <int NI, int NJ>
+__global__ void __launch_bounds__(AT)
+attn_bwd_kernel(const float* __restrict__ dctx, int ld_dctx, const float* __restrict__ q, const float* __restrict__ k,
+                const float* __restrict__ v, int ld, const float* __restrict__ probs, int heads, int Sq, int Sk,
+                bf16* dq_hi, bf16* dq_lo, bf16* dk_hi, bf16* dk_lo, bf16* dv_hi, bf16* dv_lo, int ld_d) {
+  extern __shared__ float sm[];
+  constexpr int RI = NI * 16, RJ = NJ * 8;
+  constexpr int RJ16 = ((RJ + 15) / 16) * 16;   // dK/dV rows are produced with the 16-row thread pattern
+  constexpr int NRJ = RJ16 / 16;
+  float* Qs = sm;                    // [RI][LDS]
+  float* Ks = Qs + RI * LDS;         // [RJ][LDS]
+  float* VPt = Ks + RJ * LDS;        // V [RJ][LDS], later Pᵀ [RJ16][LDS]
+  float* dOs = VPt + RJ16 * LDS;     // [RI][LDS]
+  float* dSs = dOs + RI * LDS;       // [RI][LDS]
+  float* dSt = dSs + RI * LDS;       // [RJ16][LDS]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int ti = threadIdx.x >> 3, tj = threadIdx.x & 7;
+  const size_t qrow0 = static_cast<size_t>(b) * Sq, krow0 = static_cast<size_t>(b) * Sk;
+  load_tile(Qs, q + qrow0 * ld + h * 64, ld, Sq, RI);
+  load_tile(Ks, k + krow0 * ld + h * 64, ld, Sk, RJ);
+  load_tile(VPt, v + krow0 * ld + h * 64, ld, Sk, RJ);
+  load_tile(dOs, dctx + qrow0 * ld_dctx + h * 64, ld_dctx, Sq, RI);
+  __syncthreads();
+
+  float dp[NI][NJ];
+  tile_abt<NI, NJ>(dOs, VPt, ti, tj, dp);
+  float p[NI][NJ];
+#pragma unroll
+  for (int ii = 0; ii < NI; ++ii) {
+    const int i = ti + 16 * ii;
+    float dot = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = tj + 8 * jj;
+      p[ii][jj] = (i < Sq && j < Sk) ? __ldg(probs + ((static_cast<size_t>(b) * heads + h) * Sq + i) * Sk + j) : 0.f;
+      dot += p[ii][jj] * dp[ii][jj];
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) dp[ii][jj] = p[ii][jj] * (dp[ii][jj] - dot) * 0.125f;   // now dS
+  }
+  __syncthreads();   // everyone is done reading V
+  for (int idx = threadIdx.x; idx < (RJ16 - RJ) * LDS; idx += AT) {   // zero the padding rows of the transposed tiles
+    VPt[RJ * LDS + idx] = 0.f;
+    dSt[RJ * LDS + idx] = 0.f;
+  }
+#pragma unroll
+  for (int ii = 0; ii < NI; ++ii) {
+    const int i = ti + 16 * ii;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = tj + 8 * jj;
+      dSs[i * LDS + j] = dp[ii][jj];
+      dSt[j * LDS + i] = dp[ii][jj];
+      VPt[j * LDS + i] = p[ii][jj];
+    }
+  }
+  __syncthreads();
+  {
+    float4 o0[NRJ], o1[NRJ];
+    tile_ab<NRJ>(VPt, dOs, RI, ti, tj, o0, o1);     // dV = Pᵀ · dO
+#pragma unroll
+    for (int rr = 0; rr < NRJ; ++rr) {
+      const int j = ti + 16 * rr;
+      if (j < Sk) {
+        const size_t idx = (krow0 + j) * ld_d + h * 64 + 4 * tj;
+        store_split4(dv_hi, dv_lo, idx, o0[rr]); store_split4(dv_hi, dv_lo, idx + 32, o1[rr]);
+      }
+    }
+    tile_ab<NRJ>(dSt, Qs, RI, ti, tj, o0, o1);      // dK = dSᵀ · Q
+#pragma unroll
+    for (int rr = 0; rr < NRJ; ++rr) {
+      const int j = ti + 16 * rr;
+      if (j < Sk) {
+        const size_t idx = (krow0 + j) * ld_d + h * 64 + 4 * tj;
+        store_split4(dk_hi, dk_lo, idx, o0[rr]); store_split4(dk_hi, dk_lo, idx + 32, o1[rr]);
+      }
+    }
+  }
+  {
+    float4 o0[NI], o1[NI];
+    tile_ab<NI>(dSs, Ks, RJ, ti, tj, o0, o1);       // dQ = dS · K
+#pragma unroll
+    for (int ii = 0; ii < NI; ++ii) {
+      const int i = ti + 16 * ii;
+      if (i < Sq) {
+        const size_t idx = (qrow0 + i) * ld_d + h * 64 + 4 * tj;
+        store_split4(dq_hi, dq_lo, idx, o0[ii]); store_split4(dq_hi, dq_lo, idx + 32, o1[ii]);
+      }
+    }
+  }
+}
+
+template <int NI, int NJ>
+int attn_fwd_launch(const float* q, const float* k, const float* v, int ld, const float* mask, int B, int heads, int Sq,
+                    int Sk, Split ctx, float* ctx_f32, int ld_ctx, float* probs, cudaStream_t s) {
+  constexpr size_t smem = static_cast<size_t>(2 * NI * 16 + 2 * NJ * 8) * LDS * sizeof(float);
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<NI, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    set = true;
+  }
+  attn_fwd_kernel<NI, NJ><<<dim3(heads, B), AT, smem, s>>>(q, k, v, ld, mask, heads, Sq, Sk, ctx.hi, ctx.lo, ctx_f32,
+                                                           ld_ctx, probs);
+  return launch_rc();
+}
+template <int NI, int NJ>
+int attn_bwd_launch(const float* dctx, int ld_dctx, const float* q, const float* k, const float* v, int ld,
+                    const float* probs, int B, int heads, int Sq, int Sk, Split dq, Split dk, Split dv, int ld_d,
+                    cudaStream_t s) {
+  constexpr int RI = NI * 16, RJ = NJ * 8, RJ16 = ((RJ + 15) / 16) * 16;
+  constexpr size_t smem = static_cast<size_t>(3 * RI + RJ + 2 * RJ16) * LDS * sizeof(float);
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<NI, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    set = true;
+  }
+  attn_bwd_kernel<NI, NJ><<<dim3(heads, B), AT, smem, s>>>(dctx, ld_dctx, q, k, v, ld, probs, heads, Sq, Sk, dq.hi,
+                                                           dq.lo, dk.hi, dk.lo, dv.hi, dv.lo, ld_d);
+  return launch_rc();
+}
+
+// pick the smallest instantiated (NI, NJ) ∈ {2,3,4} × {3,5,8} covering (Sq, Sk)
+#define XLX_ATTN_DISPATCH(FN, ...)                                             \
+  do {                                                                         \
+    const int ni = (Sq + 15) / 16, nj = (Sk + 7) / 8;                          \
+    if (ni <= 2) {                                                             \
+      if (nj <= 3) return FN<2, 3>(__VA_ARGS__);                               \
+      if (nj <= 5) return FN<2, 5>(__VA_ARGS__);                               \
+      return FN<2, 8>(__VA_ARGS__);                                            \
+    } else if (ni <= 3) {                                                      \
+      if (nj <= 3) return FN<3, 3>(__VA_ARGS__);                               \
+      if (nj <= 5) return FN<3, 5>(__VA_ARGS__);                               \
+      return FN<3, 8>(__VA_ARGS__);                                            \
+    } else {                                                                   \
+      if (nj <= 3) return FN<4, 3>(__VA_ARGS__);                               \
+      if (nj <= 5) return FN<4, 5>(__VA_ARGS__);                               \
+      return FN<4, 8>(__VA_ARGS__);                                            \
+    }                                                                          \
+  } while (0)
+
+}  // namespace
+
+long long aux_launch_count() { return g_aux_launches.load(); }
+int reduce_max_blocks() { return kMaxBlocks; }
+
+int split_f32(const float* x, Split out, size_t n, cudaStream_t s) {
+  if (n % 4) return -2;
+  if (!n) return 0;
+  split_kernel<<<grid_for(n / 4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(x), out.hi, out.lo, n / 4);
+  return launch_rc();
+}
+int unsplit_f32(Split in, float* out, size_t n, cudaStream_t s) {
+  if (n % 4) return -2;
+  if (!n) return 0;
+  unsplit_kernel<<<grid_for(n / 4, 256), 256, 0, s>>>(in.hi, in.lo, reinterpret_cast<float4*>(out), n / 4);
+  return launch_rc();
+}
+int fill_f32(float* dst, float v, size_t n, cudaStream_t s) {
+  if (!n) return 0;
+  fill_kernel<<<grid_for(n, 256), 256, 0, s>>>(dst, v, n);
+  return launch_rc();
+}
+int concat3_f32(const float* a, const float* b, const float* c, float* dst, int n, cudaStream_t s) {
+  concat3_kernel<<<(3 * n + 255) / 256, 256, 0, s>>>(a, b, c, dst, n);
+  return launch_rc();
+}
+int gather_rows(const float* table, const int64_t* ids, const uint8_t* mask, const float* fill, int rows, int cols,
+                float* out_f32, Split out, cudaStream_t s) {
+  if (cols % 4) return -2;
+  if (!rows) return 0;
+  gather_rows_kernel<<<rows, 256, 0, s>>>(table, ids, mask, fill, cols, out_f32, out.hi, out.lo);
+  return launch_rc();
+}
+
+#define XLX_LN_DISPATCH(KERNEL, H, ...)                        \
+  switch (H) {                                                 \
+    case 128: KERNEL<1> __VA_ARGS__; break;                    \
+    case 256: KERNEL<2> __VA_ARGS__; break;                    \
+    case 512: KERNEL<4> __VA_ARGS__; break;                    \
+    case 768: KERNEL<6> __VA_ARGS__; break;                    \
+    case 1024: KERNEL<8> __VA_ARGS__; break;                   \
+    default: return -4;                                        \
+  }
+
+int layernorm_fwd(const float* y, const float* gamma, const float* beta, float eps, int M, int H, float out_scale,
+                  const float* addend, Split out, float* out_f32, float* mean, float* rstd, cudaStream_t s) {
+  if (!M) return 0;
+  const int grid = (M + 7) / 8;
+  XLX_LN_DISPATCH(ln_fwd_kernel, H, <<<grid, 256, 0, s>>>(y, gamma, beta, eps, M, out_scale, addend, out.hi, out.lo,
+                                                         out_f32, mean, rstd));
+  return launch_rc();
+}
+int layernorm_bwd(const float* dy, float dy_scale, const float* y, const float* gamma, const float* mean,
+                  const float* rstd, int M, int H, float* dx, Split dx_split, float* part, int* nblk_out,
+                  cudaStream_t s) {
+  int grid = (M + 7) / 8;
+  if (grid > kMaxBlocks) grid = kMaxBlocks;
+  if (grid < 1) grid = 1;
+  *nblk_out = grid;
+  XLX_LN_DISPATCH(ln_bwd_kernel, H, <<<grid, 256, 0, s>>>(dy, dy_scale, y, gamma, mean, rstd, M, dx, dx_split.hi,
+                                                         dx_split.lo, part));
+  return launch_rc();
+}
+int colsum_finish(const float* part, int nvec, int nblk, int H, float* const* outs, int accumulate, cudaStream_t s) {
+  if (nvec < 1 || nvec > 5) return -1;
+  float* o[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int v = 0; v < nvec; ++v) o[v] = outs[v];
+  colsum_finish_kernel<<<dim3((H + 255) / 256, nvec), 256, 0, s>>>(part, nblk, H, o[0], o[1], o[2], o[3], o[4],
+                                                                   accumulate);
+  return launch_rc();
+}
+int colsum(const float* x_f32, Split x, int M, int N, int ld, float* scratch, float* out, cudaStream_t s) {
+  if ((N % 4) || (ld % 4)) return -2;
+  int nblk = (M + 63) / 64;
+  if (nblk > 128) nblk = 128;
+  if (nblk < 1) nblk = 1;
+  colsum_kernel<<<dim3((N + 127) / 128, nblk), 256, 0, s>>>(x_f32, x.hi, x.lo, M, N, ld, scratch);
+  int rc = launch_rc();
+  if (rc) return rc;
+  float* outs[1] = {out};
+  return colsum_finish(scratch, 1, nblk, N, outs, 0, s);
+}
+
+int box_linear_fwd(const float* pos, const float* Wp, const float* bp, int M, int H, float* y2, cudaStream_t s) {
+  const size_t n = static_cast<size_t>(M) * H;
+  if (!n) return 0;
+  box_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(pos, Wp, bp, M, H, y2);
+  return launch_rc();
+}
+int box_linear_bwd(const float* dy2, const float* pos, int M, int H, float* scratch, float* dWp, float* dbp,
+                   cudaStream_t s) {
+  int nblk = (M + 31) / 32;
+  if (nblk > 128) nblk = 128;
+  if (nblk < 1) nblk = 1;
+  box_bwd_kernel<<<dim3((H + 127) / 128, nblk), 256, 0, s>>>(dy2, pos, M, H, scratch);
+  int rc = launch_rc();
+  if (rc) return rc;
+  // reduce into a [4][H] temp placed after the partials, then interleave into dWp [H][4]
+  float* t = scratch + static_cast<size_t>(5) * nblk * H;
+  float* outs[5] = {t, t + H, t + 2 * H, t + 3 * H, dbp};
+  if ((rc = colsum_finish(scratch, 5, nblk, H, outs, 0, s))) return rc;
+  box_pack_kernel<<<(4 * H + 255) / 256, 256, 0, s>>>(t, H, dWp);
+  return launch_rc();
+}
+
+int attention_fwd(const float* q, const float* k, const float* v, int ld, const float* mask, int B, int heads,
+                  int Sq, int Sk, Split ctx, float* ctx_f32, int ld_ctx, float* probs, cudaStream_t s) {
+  if (Sq < 1 || Sk < 1 || Sq > 64 || Sk > 64) return -5;
+  if ((ld % 4) || (ld_ctx % 4)) return -2;
+  if (!B) return 0;
+  XLX_ATTN_DISPATCH(attn_fwd_launch, q, k, v, ld, mask, B, heads, Sq, Sk, ctx, ctx_f32, ld_ctx, probs, s);
+}
+int attention_bwd(const float* dctx, int ld_dctx, const float* q, const float* k, const float* v, int ld,
+                  const float* probs, int B, int heads, int Sq, int Sk, Split dq, Split dk, Split dv, int ld_d,
+                  cudaStream_t s) {
+  if (Sq < 1 || Sk < 1 || Sq > 64 || Sk > 64) return -5;
+  if ((ld % 4) || (ld_d % 4) || (ld_dctx % 4)) return -2;
+  if (!B) return 0;
+  XLX_ATTN_DISPATCH(attn_bwd_launch, dctx, ld_dctx, q, k, v, ld, probs, B, heads, Sq, Sk, dq, dk, dv, ld_d, s);
+}
+
+}  // namespace xlx

@@ -1,0 +1,307 @@
+"""Drop-in replacement for HF ``LxmertEncoder`` (``transformers/models/lxmert/modeling_lxmert.py:487-565``),
+the module the reference reaches as ``self.bert.encoder`` (``x-lxmert/src/lxrt/modeling.py:80,195-206``).
+
+``B200LxmertEncoder`` owns the *same* ``nn.Parameter`` objects under the same names as the module it
+replaces (``visn_fc.*``, ``layer.N.*``, ``r_layers.N.*``, ``x_layers.N.*``), so state dicts, optimisers and
+DDP see no difference; only ``forward`` changes: it hands raw device pointers to
+``xlx_encoder_fwd`` / ``xlx_encoder_bwd`` (``include/xlxmert_b200.h``) through a ``torch.autograd.Function``.
+There is no PyTorch fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from .config import LxmertDims
+from .params import encoder_param_names
+
+
+def dims_from_hf_config(cfg) -> LxmertDims:
+    return LxmertDims(hidden=cfg.hidden_size, heads=cfg.num_attention_heads,
+                      intermediate=cfg.intermediate_size, feat_dim=cfg.visual_feat_dim,
+                      pos_dim=cfg.visual_pos_dim, l_layers=cfg.l_layers, r_layers=cfg.r_layers,
+                      x_layers=cfg.x_layers, vocab=cfg.vocab_size, max_pos=cfg.max_position_embeddings,
+                      type_vocab=cfg.type_vocab_size, ln_eps=1e-12)
+
+
+# ---- a parameter skeleton with the HF names (used when no HF module is at hand) --------------------
+
+class _Att(nn.Module):            # LxmertAttention (HF:217-236)
+    def __init__(self, H):
+        super().__init__()
+        self.query, self.key, self.value = nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, H)
+
+
+class _AttOut(nn.Module):         # LxmertAttentionOutput / LxmertOutput (HF:277-288, 339-350)
+    def __init__(self, K, H):
+        super().__init__()
+        self.dense = nn.Linear(K, H)
+        self.LayerNorm = nn.LayerNorm(H, eps=1e-12)
+
+
+class _SelfAttLayer(nn.Module):   # LxmertSelfAttentionLayer (HF:306-324)
+    def __init__(self, H):
+        super().__init__()
+        self.self = _Att(H)
+        self.output = _AttOut(H, H)
+
+
+class _CrossAttLayer(nn.Module):  # LxmertCrossAttentionLayer (HF:291-303)
+    def __init__(self, H):
+        super().__init__()
+        self.att = _Att(H)
+        self.output = _AttOut(H, H)
+
+
+class _Inter(nn.Module):          # LxmertIntermediate (HF:327-336)
+    def __init__(self, H, I):
+        super().__init__()
+        self.dense = nn.Linear(H, I)
+
+
+class _Layer(nn.Module):          # LxmertLayer (HF:353-366)
+    def __init__(self, H, I):
+        super().__init__()
+        self.attention = _SelfAttLayer(H)
+        self.intermediate = _Inter(H, I)
+        self.output = _AttOut(I, H)
+
+
+class _XLayer(nn.Module):         # LxmertXLayer (HF:369-384)
+    def __init__(self, H, I):
+        super().__init__()
+        self.visual_attention = _CrossAttLayer(H)
+        self.lang_self_att = _SelfAttLayer(H)
+        self.visn_self_att = _SelfAttLayer(H)
+        self.lang_inter, self.lang_output = _Inter(H, I), _AttOut(I, H)
+        self.visn_inter, self.visn_output = _Inter(H, I), _AttOut(I, H)
+
+
+class _VisnFc(nn.Module):         # LxmertVisualFeatureEncoder (HF:460-474)
+    def __init__(self, H, F, P):
+        super().__init__()
+        self.visn_fc = nn.Linear(F, H)
+        self.visn_layer_norm = nn.LayerNorm(H, eps=1e-12)
+        self.box_fc = nn.Linear(P, H)
+        self.box_layer_norm = nn.LayerNorm(H, eps=1e-12)
+
+
+class _EncoderSkeleton(nn.Module):
+    def __init__(self, d: LxmertDims):
+        super().__init__()
+        self.visn_fc = _VisnFc(d.hidden, d.feat_dim, d.pos_dim)
+        self.layer = nn.ModuleList([_Layer(d.hidden, d.intermediate) for _ in range(d.l_layers)])
+        self.x_layers = nn.ModuleList([_XLayer(d.hidden, d.intermediate) for _ in range(d.x_layers)])
+        self.r_layers = nn.ModuleList([_Layer(d.hidden, d.intermediate) for _ in range(d.r_layers)])
+
+
+# ---- autograd bridge -------------------------------------------------------------------------------
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _EncoderFn(torch.autograd.Function):
+    """(lang_in, visual_feats, *params) → (lang_out, vis_out, lang_hidden, vis_hidden)."""
+
+    @staticmethod
+    def forward(ctx, enc: "B200LxmertEncoder", lang_mask, visual_pos, vis_mask, want_hidden: bool,
+                lang_in, visual_feats, *params):
+        lib = _lib.load()
+        d = enc.dims
+        B, L, H = lang_in.shape
+        V = visual_feats.shape[1]
+        dev = lang_in.device
+        training = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward; this is the signal
+        lang_in = lang_in.contiguous().float()
+        visual_feats = visual_feats.contiguous().float()
+        visual_pos = visual_pos.contiguous().float()
+        prep, parr = enc._prepared(params)
+        ws_bytes = lib.xlx_encoder_workspace_bytes(C.byref(enc._cdims), B, L, V, int(training))
+        if ws_bytes == 0:
+            raise _lib.XlxError("xlx_encoder_workspace_bytes", -22 if max(L, V) > 64 else -20)
+        ws = enc._workspace(ws_bytes, dev, training)
+        lang_out = torch.empty(B, L, H, device=dev, dtype=torch.float32)
+        vis_out = torch.empty(B, V, H, device=dev, dtype=torch.float32)
+        n_l, n_v = d.l_layers + d.x_layers, d.r_layers + d.x_layers
+        lang_hidden = torch.empty(n_l, B, L, H, device=dev, dtype=torch.float32) if want_hidden else None
+        vis_hidden = torch.empty(n_v, B, V, H, device=dev, dtype=torch.float32) if want_hidden else None
+        rc = lib.xlx_encoder_fwd(C.byref(enc._cdims), parr, prep.data_ptr(), B, L, V, lang_in.data_ptr(),
+                                 _ptr(lang_mask), visual_feats.data_ptr(), visual_pos.data_ptr(), _ptr(vis_mask),
+                                 lang_out.data_ptr(), vis_out.data_ptr(), _ptr(lang_hidden), _ptr(vis_hidden),
+                                 ws.data_ptr(), ws_bytes, int(training), enc.passes, _stream_ptr())
+        _lib.check("xlx_encoder_fwd", rc)
+        if training:
+            ctx.enc, ctx.ws, ctx.ws_bytes, ctx.shape = enc, ws, ws_bytes, (B, L, V)
+            ctx.prep, ctx.parr, ctx.params = prep, parr, params
+            ctx.visual_pos = visual_pos
+            ctx.need_dfeats = visual_feats.requires_grad
+        outs = [lang_out, vis_out]
+        if want_hidden:
+            ctx.mark_non_differentiable(lang_hidden, vis_hidden)
+            outs += [lang_hidden, vis_hidden]
+        else:
+            outs += [None, None]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, d_lang_out, d_vis_out, _dlh, _dvh):
+        lib = _lib.load()
+        enc = ctx.enc
+        B, L, V = ctx.shape
+        d = enc.dims
+        dev = ctx.ws.device
+        if d_lang_out is not None:
+            d_lang_out = d_lang_out.contiguous().float()
+        if d_vis_out is not None:
+            d_vis_out = d_vis_out.contiguous().float()
+        d_lang_in = torch.empty(B, L, d.hidden, device=dev, dtype=torch.float32)
+        d_feats = torch.empty(B, V, d.feat_dim, device=dev, dtype=torch.float32) if ctx.need_dfeats else None
+        grads = enc._grad_arena(dev)
+        rc = lib.xlx_encoder_bwd(C.byref(enc._cdims), ctx.parr, ctx.prep.data_ptr(), B, L, V,
+                                 ctx.visual_pos.data_ptr(), _ptr(d_lang_out), _ptr(d_vis_out),
+                                 d_lang_in.data_ptr(), _ptr(d_feats), grads.data_ptr(), ctx.ws.data_ptr(),
+                                 ctx.ws_bytes, enc.passes, _stream_ptr())
+        _lib.check("xlx_encoder_bwd", rc)
+        enc._release_workspace(ctx.ws)
+        pgrads = []
+        for p, (off, n) in zip(ctx.params, enc._grad_slices):
+            pgrads.append(grads[off:off + n].view(p.shape) if p.requires_grad else None)
+        ctx.ws = None
+        return (None, None, None, None, None, d_lang_in, d_feats, *pgrads)
+
+
+class B200LxmertEncoder(nn.Module):
+    """``LxmertEncoder`` with the same parameters and ``forward`` signature, running on sm_100a kernels.
+
+    ``passes``: 3 = bf16x3 split GEMMs (fp32-class accuracy, default); 1 = single bf16 pass.
+    ``output_hidden_states``: when False (default) the returned hidden-state tuples hold only the final
+    state (the reference never asks for the others); set True to get every layer's output like HF.
+    """
+
+    def __init__(self, source: Optional[nn.Module] = None, dims: Optional[LxmertDims] = None, passes: int = 3,
+                 output_hidden_states: bool = False):
+        super().__init__()
+        if source is None:
+            if dims is None:
+                raise ValueError("need either a source LxmertEncoder or dims")
+            source = _EncoderSkeleton(dims)
+        elif dims is None:
+            dims = dims_from_hf_config(source.config)
+        self.visn_fc = source.visn_fc
+        self.layer = source.layer
+        self.x_layers = source.x_layers
+        self.r_layers = source.r_layers
+        self.config = getattr(source, "config", None)
+        self.num_l_layers, self.num_x_layers, self.num_r_layers = dims.l_layers, dims.x_layers, dims.r_layers
+        self.dims = dims
+        self.passes = passes
+        self.output_hidden_states = output_hidden_states
+        self._names = encoder_param_names(dims)
+        self._cdims = _lib.XlxDims.from_dims(dims)
+        self._prep = None
+        self._prep_key = None
+        self._parr = None
+        self._ws_pool: List[torch.Tensor] = []
+        self._ws_busy: List[torch.Tensor] = []
+        self._grads = None
+        self._grad_slices = None
+
+    # -- parameters in C-ABI slot order
+    def _param_list(self) -> List[torch.Tensor]:
+        sd = dict(self.named_parameters())
+        return [sd[n] for n in self._names]
+
+    def _prepared(self, params):
+        """Split-bf16 copies of the weights, refreshed whenever any parameter changed."""
+        lib = _lib.load()
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        dev = params[0].device
+        if self._prep is None or self._prep.device != dev:
+            nbytes = lib.xlx_encoder_prep_bytes(C.byref(self._cdims))
+            self._prep = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._prep_key = None
+        if key != self._prep_key:
+            for p in params:
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise TypeError("B200LxmertEncoder parameters must be contiguous fp32")
+            self._parr = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+            rc = lib.xlx_encoder_prepare(C.byref(self._cdims), self._parr, self._prep.data_ptr(), _stream_ptr())
+            _lib.check("xlx_encoder_prepare", rc)
+            self._prep_key = key
+        return self._prep, self._parr
+
+    def _workspace(self, nbytes: int, dev, training: bool) -> torch.Tensor:
+        for i, t in enumerate(self._ws_pool):
+            if t.numel() >= nbytes and t.device == dev:
+                self._ws_pool.pop(i)
+                break
+        else:
+            t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if training:
+            self._ws_busy.append(t)        # returned to the pool by backward
+        else:
+            self._ws_pool.append(t)        # stream-ordered reuse is safe for inference
+        return t
+
+    def _release_workspace(self, t: torch.Tensor) -> None:
+        self._ws_busy = [b for b in self._ws_busy if b is not t]
+        if len(self._ws_pool) < 2:
+            self._ws_pool.append(t)
+
+    def _grad_arena(self, dev) -> torch.Tensor:
+        lib = _lib.load()
+        if self._grad_slices is None:
+            n = lib.xlx_encoder_num_params(C.byref(self._cdims))
+            self._grad_slices = [(lib.xlx_encoder_grad_offset(C.byref(self._cdims), i),
+                                  lib.xlx_encoder_param_elems(C.byref(self._cdims), i)) for i in range(n)]
+        total = lib.xlx_encoder_grad_elems(C.byref(self._cdims))
+        # a fresh arena per backward: the returned gradients are views into it
+        return torch.empty(total, dtype=torch.float32, device=dev)
+
+    def forward(self, lang_feats, lang_attention_mask, visual_feats, visual_pos, visual_attention_mask=None,
+                output_attentions=None):
+        if output_attentions:
+            raise NotImplementedError("attention probabilities are not exported by the fused path")
+        if not lang_feats.is_cuda:
+            raise RuntimeError("B200LxmertEncoder runs on CUDA (sm_100a) only; there is no CPU fallback")
+        B, L, _ = lang_feats.shape
+        V = visual_feats.shape[1]
+
+        def flat_mask(m, S):
+            if m is None:
+                return None
+            return m.to(torch.float32).expand(B, 1, 1, S).reshape(B, S).contiguous()
+
+        lmask = flat_mask(lang_attention_mask, L)
+        vmask = flat_mask(visual_attention_mask, V)
+        params = self._param_list()
+        lang_out, vis_out, lh, vh = _EncoderFn.apply(self, lmask, visual_pos, vmask, self.output_hidden_states,
+                                                     lang_feats, visual_feats, *params)
+        if self.output_hidden_states:
+            n_l, n_v = lh.shape[0], vh.shape[0]
+            lang_states = tuple(lh[i] for i in range(n_l - 1)) + (lang_out,)
+            vis_states = tuple(vh[i] for i in range(n_v - 1)) + (vis_out,)
+        else:
+            lang_states, vis_states = (lang_out,), (vis_out,)
+        return ((vis_states, None), (lang_states, None), None)
+
+
+def accelerate(model: nn.Module, passes: int = 3, output_hidden_states: bool = False) -> nn.Module:
+    """Swap every HF ``LxmertEncoder`` inside ``model`` for a ``B200LxmertEncoder`` sharing its parameters
+    (SURVEY.md §8b "Recommended interposition").  Works on ``XLxmertForPretraining`` (``.bert.encoder``),
+    bare ``LxmertModel`` (``.encoder``) and the fine-tune wrappers alike because the swap is per instance."""
+    for name, child in list(model.named_children()):
+        if type(child).__name__ == "LxmertEncoder":
+            setattr(model, name, B200LxmertEncoder(child, passes=passes, output_hidden_states=output_hidden_states))
+        else:
+            accelerate(child, passes=passes, output_hidden_states=output_hidden_states)
+    return model
