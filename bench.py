@@ -291,6 +291,13 @@ def run_ours(args):
             ms = float(t.item())
         return ms / steps, launches
 
+    if args.ncu:       # profiler mode: W warm-up + K plain steps, nothing printed that looks like a bench value
+        for _ in range(args.warmup + args.steps):
+            step_resident()
+        torch.cuda.synchronize()
+        print(json.dumps({"ncu_mode": True, "launches_per_step": int(lib.xlx_launch_count()) // (args.warmup + args.steps)}))
+        return
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -350,6 +357,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--passes", type=int, default=3, choices=[1, 3])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--ncu", action="store_true", help="profiler mode: run warmup+steps resident steps and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

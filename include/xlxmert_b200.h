@@ -100,6 +100,90 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
                         float* d_lang_in, float* d_visual_feats, float* grads, void* workspace,
                         size_t workspace_bytes, int32_t passes, void* stream);
 
+/* ---- visual input of XLxmertForPretraining.forward (x-lxmert/src/lxrt/modeling.py:185-193) ----------------------
+ * out[r,:] = vis_mask[r] ? mask_feat[:] : table[cluster_ids[r],:]   (vis_emb gather + torch.where), r < rows.
+ * vis_mask: one byte per row (torch.bool) or NULL.  Backward: d_mask_feat[:] = Σ_{r: vis_mask[r]} d_feats[r,:];
+ * the table is frozen (nn.Embedding.from_pretrained(freeze=True), modeling.py:146-149).
+ * scratch: 128·feat_dim floats. */
+int32_t xlx_visual_input_fwd(const float* table, const int64_t* cluster_ids, const uint8_t* vis_mask,
+                             const float* mask_feat, int32_t rows, int32_t feat_dim, float* out, void* stream);
+int32_t xlx_visual_input_bwd(const float* d_feats, const uint8_t* vis_mask, int32_t rows, int32_t feat_dim,
+                             float* d_mask_feat, float* scratch, void* stream);
+
+/* ---- LxmertEmbeddings (HF:179-214; reached through self.bert at lxrt/modeling.py:195-206) -----------------
+ * params (HOST array of 5 device pointers): word_embeddings.weight [vocab,H], position_embeddings.weight
+ * [max_pos,H], token_type_embeddings.weight [type_vocab,H], LayerNorm.weight, LayerNorm.bias.
+ * out[b,l,:] = LN(word[ids[b,l]] + pos[l] + type[tt[b,l]]); dropout is the caller's business (p = 0 / eval).
+ * input_ids / token_type_ids: int64 [B,L] (token_type_ids may be NULL = all zero, as in every reference caller).
+ * `save` (xlx_embeddings_save_bytes) receives what the backward needs; NULL for inference. */
+size_t xlx_embeddings_save_bytes(const xlx_dims* d, int32_t B, int32_t L);
+size_t xlx_embeddings_scratch_bytes(const xlx_dims* d, int32_t B, int32_t L);
+int32_t xlx_embeddings_fwd(const xlx_dims* d, int32_t B, int32_t L, const int64_t* input_ids,
+                           const int64_t* token_type_ids, const float* const* params, float* out, void* save,
+                           void* stream);
+/* grads: HOST array of 5 device pointers shaped like params, all overwritten.  Row 0 of each table gets no
+ * gradient (nn.Embedding(padding_idx=0), HF:184-186). */
+int32_t xlx_embeddings_bwd(const xlx_dims* d, int32_t B, int32_t L, int32_t vocab, int32_t max_pos,
+                           int32_t type_vocab, const int64_t* input_ids, const int64_t* token_type_ids,
+                           const float* const* params, const void* save, const float* d_out, float* const* grads,
+                           void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- LxmertPooler (HF:568-580): pooled = tanh(W · lang_out[:,0] + b) ---------------------------------------
+ * The workspace written by the forward must reach the backward unchanged.  d_lang_out [B,L,H] is fully
+ * written (zero except token 0 of every sample). */
+size_t xlx_pooler_workspace_bytes(const xlx_dims* d, int32_t B);
+int32_t xlx_pooler_fwd(const xlx_dims* d, int32_t B, int32_t L, const float* lang_out, const float* W,
+                       const float* bias, float* pooled, void* workspace, size_t workspace_bytes, int32_t passes,
+                       void* stream);
+int32_t xlx_pooler_bwd(const xlx_dims* d, int32_t B, int32_t L, const float* pooled, const float* d_pooled,
+                       float* d_lang_out, float* dW, float* dbias, void* workspace, size_t workspace_bytes,
+                       int32_t passes, void* stream);
+
+/* ---- prediction heads ---------------------------------------------------------------------------------------
+ * Cluster head = lxrt LxmertVisualObjHead (x-lxmert/src/lxrt/modeling.py:8-53, cluster mode):
+ *     t = LN(gelu(W1·h + b1));  feat = Wf·t + bf  [M, feat_dim];  obj = feat·Centroidsᵀ + bc  [M, classes]
+ *   params (8): transform.dense.{weight,bias}, transform.LayerNorm.{weight,bias}, linear_feat.{weight,bias},
+ *               out_cluster.{weight [classes,feat_dim] (the frozen centroid table, modeling.py:146-151), bias}
+ * LM head = HF LxmertLMPredictionHead (HF:597-607) as used by LxmertPreTrainingHeads (HF:656-665):
+ *     t = LN(gelu(W1·h + b1));  scores = t·Eᵀ + bias  [M, vocab]
+ *   params (6): predictions.transform.dense.{weight,bias}, predictions.transform.LayerNorm.{weight,bias},
+ *               predictions.decoder.weight [vocab,H] (tied to the word embeddings, modeling.py:86), predictions.bias
+ * `prep` holds split-bf16 weight copies (refresh with *_prepare when weights change).  hidden: [M,H] fp32.
+ * Optional outputs (NULL to skip): feat [M,feat_dim], logits/scores [M,classes], loss (device scalar =
+ * CrossEntropyLoss() over rows with label != -100, modeling.py:99,253-256; needs labels), and for the sampler
+ * pred_prob [M] / pred_id [M] = softmax(logits).max(-1) with torch's first-index tie rule
+ * (tasks/imggen_model.py:232-235).  The workspace written by a forward with labels must reach the backward
+ * unchanged.  Backward: d_loss = device scalar (upstream gradient of the loss); writes d_hidden [M,H] and
+ * grads (HOST array of device pointers shaped like params; out_cluster.weight is frozen and not written). */
+size_t xlx_objhead_prep_bytes(const xlx_dims* d, int32_t classes);
+int32_t xlx_objhead_prepare(const xlx_dims* d, int32_t classes, const float* const* params, void* prep, void* stream);
+size_t xlx_objhead_workspace_bytes(const xlx_dims* d, int32_t classes, int32_t M);
+int32_t xlx_objhead_fwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep, int32_t M,
+                        const float* hidden, const int64_t* labels, float* feat, float* logits, float* loss,
+                        float* pred_prob, int64_t* pred_id, void* workspace, size_t workspace_bytes, int32_t passes,
+                        void* stream);
+int32_t xlx_objhead_bwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep, int32_t M,
+                        const int64_t* labels, const float* d_loss, float* d_hidden, float* const* grads,
+                        void* workspace, size_t workspace_bytes, int32_t passes, void* stream);
+size_t xlx_lmhead_prep_bytes(const xlx_dims* d, int32_t classes);
+int32_t xlx_lmhead_prepare(const xlx_dims* d, int32_t classes, const float* const* params, void* prep, void* stream);
+size_t xlx_lmhead_workspace_bytes(const xlx_dims* d, int32_t classes, int32_t M);
+int32_t xlx_lmhead_fwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep, int32_t M,
+                       const float* hidden, const int64_t* labels, float* scores, float* loss, void* workspace,
+                       size_t workspace_bytes, int32_t passes, void* stream);
+int32_t xlx_lmhead_bwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep, int32_t M,
+                       const int64_t* labels, const float* d_loss, float* d_hidden, float* const* grads,
+                       void* workspace, size_t workspace_bytes, int32_t passes, void* stream);
+
+/* Matched head: cls.seq_relationship = Linear(H, 2) on the pooled output (HF:661,664) + CrossEntropyLoss
+ * (modeling.py:227-235).  scores [B,2]; scratch = xlx_matchhead_scratch_floats(B) floats, shared by fwd and bwd. */
+int64_t xlx_matchhead_scratch_floats(int32_t B);
+int32_t xlx_matchhead_fwd(const xlx_dims* d, int32_t B, const float* pooled, const float* W, const float* bias,
+                          const int64_t* labels, float* scores, float* loss, float* scratch, void* stream);
+int32_t xlx_matchhead_bwd(const xlx_dims* d, int32_t B, const float* pooled, const float* W, const int64_t* labels,
+                          const float* scores, const float* d_loss, float* d_pooled, float* dW, float* dbias,
+                          float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

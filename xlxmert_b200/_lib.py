@@ -55,28 +55,48 @@ def _sig(lib):
     lib.xlx_encoder_prep_bytes.restype = SZ
     lib.xlx_encoder_prep_bytes.argtypes = [D]
     lib.xlx_encoder_prepare.restype = I32
-    lib.xlx_encoder_prepare.argtypes = [D, P, P, P]
+    lib.xlx_encoder_prepare.argtypes = [D, C.c_void_p, P, P]
     lib.xlx_encoder_workspace_bytes.restype = SZ
     lib.xlx_encoder_workspace_bytes.argtypes = [D, I32, I32, I32, I32]
     lib.xlx_encoder_fwd.restype = I32
     lib.xlx_encoder_fwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, SZ, I32, I32, P]
     lib.xlx_encoder_bwd.restype = I32
     lib.xlx_encoder_bwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, SZ, I32, P]
-    optional = {
-        "xlx_objhead_prep_bytes": (SZ, [D, I32]),
-        "xlx_objhead_prepare": (I32, [D, I32, P, P, P]),
-        "xlx_objhead_workspace_bytes": (SZ, [D, I32, I32, I32]),
-        "xlx_objhead_fwd": (I32, [D, I32, P, P, I32, P, P, P, P, P, P, P, SZ, I32, I32, P]),
-        "xlx_objhead_bwd": (I32, [D, I32, P, P, I32, P, P, C.c_float, P, P, P, SZ, I32, P]),
-        "xlx_generator_prep_bytes": (SZ, []),
-        "xlx_generator_prepare": (I32, [P, P, P]),
-        "xlx_generator_workspace_bytes": (SZ, [I32]),
-        "xlx_generator_fwd": (I32, [P, P, I32, P, I32, P, P, P, SZ, P]),
-    }
-    for name, (res, args) in optional.items():
-        if hasattr(lib, name):
-            getattr(lib, name).restype = res
-            getattr(lib, name).argtypes = args
+    PP = P
+    lib.xlx_embeddings_save_bytes.restype = SZ
+    lib.xlx_embeddings_save_bytes.argtypes = [D, I32, I32]
+    lib.xlx_embeddings_scratch_bytes.restype = SZ
+    lib.xlx_embeddings_scratch_bytes.argtypes = [D, I32, I32]
+    lib.xlx_embeddings_fwd.restype = I32
+    lib.xlx_embeddings_fwd.argtypes = [D, I32, I32, P, P, PP, P, P, P]
+    lib.xlx_embeddings_bwd.restype = I32
+    lib.xlx_embeddings_bwd.argtypes = [D, I32, I32, I32, I32, I32, P, P, PP, P, P, PP, P, SZ, P]
+    lib.xlx_pooler_workspace_bytes.restype = SZ
+    lib.xlx_pooler_workspace_bytes.argtypes = [D, I32]
+    lib.xlx_pooler_fwd.restype = I32
+    lib.xlx_pooler_fwd.argtypes = [D, I32, I32, P, P, P, P, P, SZ, I32, P]
+    lib.xlx_pooler_bwd.restype = I32
+    lib.xlx_pooler_bwd.argtypes = [D, I32, I32, P, P, P, P, P, P, SZ, I32, P]
+    for kind in ("objhead", "lmhead"):
+        f = getattr(lib, f"xlx_{kind}_prep_bytes"); f.restype = SZ; f.argtypes = [D, I32]
+        f = getattr(lib, f"xlx_{kind}_prepare"); f.restype = I32; f.argtypes = [D, I32, P, P, P]
+        f = getattr(lib, f"xlx_{kind}_workspace_bytes"); f.restype = SZ; f.argtypes = [D, I32, I32]
+        f = getattr(lib, f"xlx_{kind}_bwd"); f.restype = I32
+        f.argtypes = [D, I32, P, P, I32, P, P, P, P, P, SZ, I32, P]
+    lib.xlx_objhead_fwd.restype = I32
+    lib.xlx_objhead_fwd.argtypes = [D, I32, P, P, I32, P, P, P, P, P, P, P, P, SZ, I32, P]
+    lib.xlx_lmhead_fwd.restype = I32
+    lib.xlx_lmhead_fwd.argtypes = [D, I32, P, P, I32, P, P, P, P, P, SZ, I32, P]
+    lib.xlx_visual_input_fwd.restype = I32
+    lib.xlx_visual_input_fwd.argtypes = [P, P, P, P, I32, I32, P, P]
+    lib.xlx_visual_input_bwd.restype = I32
+    lib.xlx_visual_input_bwd.argtypes = [P, P, I32, I32, P, P, P]
+    lib.xlx_matchhead_scratch_floats.restype = I64
+    lib.xlx_matchhead_scratch_floats.argtypes = [I32]
+    lib.xlx_matchhead_fwd.restype = I32
+    lib.xlx_matchhead_fwd.argtypes = [D, I32, P, P, P, P, P, P, P, P]
+    lib.xlx_matchhead_bwd.restype = I32
+    lib.xlx_matchhead_bwd.argtypes = [D, I32, P, P, P, P, P, P, P, P, P, P]
 
 
 def load():

@@ -6,20 +6,13 @@
 #include <vector>
 
 #include "../../include/xlxmert_b200.h"
-#include "gemm_sm100.cuh"
-#include "kernels.cuh"
+#include "host_util.cuh"
 
 using namespace xlx;
 
 namespace {
 
 constexpr int N_ATT = 10, N_FFN = 6, N_VISN = 8;
-
-#define XLX_TRY(expr)            \
-  do {                           \
-    int rc__ = (expr);           \
-    if (rc__) return rc__;       \
-  } while (0)
 
 bool dims_ok(const xlx_dims* d) {
   return d && d->hidden > 0 && d->hidden % 128 == 0 && d->hidden <= 1024 && d->heads * 64 == d->hidden &&
@@ -65,31 +58,6 @@ int ffn_slot(const xlx_dims* d, int blk) {
   if (blk < nlr) return N_VISN + blk * (N_ATT + N_FFN) + N_ATT;
   const int k = (blk - nlr) / 2, w = (blk - nlr) % 2;
   return N_VISN + nlr * (N_ATT + N_FFN) + k * (3 * N_ATT + 2 * N_FFN) + 3 * N_ATT + w * N_FFN;
-}
-
-// ---- bump allocator over a caller-owned buffer ---------------------------------------------------
-struct Bump {
-  char* base = nullptr;
-  size_t off = 0;
-  void* take(size_t bytes) {
-    off = (off + 255) & ~static_cast<size_t>(255);
-    void* p = base + off;
-    off += bytes;
-    return p;
-  }
-  float* f32(size_t n) { return static_cast<float*>(take(n * 4)); }
-  Split split(size_t n) {
-    Split s;
-    s.hi = static_cast<bf16*>(take(n * 2));
-    s.lo = static_cast<bf16*>(take(n * 2));
-    return s;
-  }
-};
-inline Split rows(Split s, size_t row0, size_t ld) {
-  Split r;
-  r.hi = s.hi + row0 * ld;
-  r.lo = s.lo ? s.lo + row0 * ld : nullptr;
-  return r;
 }
 
 // ---- prepared weights ----------------------------------------------------------------------------
@@ -301,32 +269,14 @@ struct Run {
   const float* vmask;
 };
 
-// Y[M,N] = X[M,K] · W[N,K]ᵀ (+ epilogue)
 int linear(const Run& r, Split x, int M, int K, Split w, int N, const GemmEpilogue& e) {
-  GemmProblem p;
-  p.M = M; p.N = N; p.K = K; p.passes = r.passes;
-  p.a.hi = x.hi; p.a.lo = x.lo; p.a.ld = K; p.a.mn_major = 0;
-  p.b.hi = w.hi; p.b.lo = w.lo; p.b.ld = K; p.b.mn_major = 0;
-  p.epi = e;
-  return gemm_launch(p, r.st);
+  return gemm_linear(r.passes, r.st, x, M, K, w, N, e);
 }
-// dX[M,K] = dY[M,N] · W[N,K]
 int dgrad(const Run& r, Split dy, int M, int N, Split w, int K, const GemmEpilogue& e) {
-  GemmProblem p;
-  p.M = M; p.N = K; p.K = N; p.passes = r.passes;
-  p.a.hi = dy.hi; p.a.lo = dy.lo; p.a.ld = N; p.a.mn_major = 0;
-  p.b.hi = w.hi; p.b.lo = w.lo; p.b.ld = K; p.b.mn_major = 1;   // W stored [N, K]: GEMM-N (= K) contiguous
-  p.epi = e;
-  return gemm_launch(p, r.st);
+  return gemm_dgrad(r.passes, r.st, dy, M, N, w, K, e);
 }
-// dW[N,K] = dY[M,N]ᵀ · X[M,K]
 int wgrad(const Run& r, Split dy, int M, int N, Split x, int K, float* dw) {
-  GemmProblem p;
-  p.M = N; p.N = K; p.K = M; p.passes = r.passes;
-  p.a.hi = dy.hi; p.a.lo = dy.lo; p.a.ld = N; p.a.mn_major = 1;
-  p.b.hi = x.hi; p.b.lo = x.lo; p.b.ld = K; p.b.mn_major = 1;
-  p.epi.out_f32 = dw; p.epi.ld_out = K;
-  return gemm_launch(p, r.st);
+  return gemm_wgrad(r.passes, r.st, dy, M, N, x, K, dw);
 }
 
 const float* P(const Run& r, int slot) { return r.params[slot]; }
@@ -490,21 +440,6 @@ int att_cross_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
   XLX_TRY(attention_bwd(p.dctx + static_cast<size_t>(p.Ml) * H, H, qv, ql + H, ql + 2 * H, 3 * H, a.probs2, p.B,
                         p.heads, p.V, p.L, col(dvv, 0), col(dl, H), col(dl, 2 * H), 3 * H, r.st));
   return att_bwd_tail(bw, blk, din);
-}
-
-// The caller (PyTorch) may have selected the device through a different copy of the CUDA runtime; make this
-// library's runtime agree with the device that owns the caller's buffers.
-int ensure_device(const void* ptr) {
-  cudaPointerAttributes at;
-  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
-  if (at.type != cudaMemoryTypeDevice) return 0;
-  int cur = -1;
-  cudaGetDevice(&cur);
-  if (cur != at.device) {
-    cudaError_t e = cudaSetDevice(at.device);
-    if (e != cudaSuccess) return static_cast<int>(e);
-  }
-  return 0;
 }
 
 int check_common(const xlx_dims* d, int B, int L, int V) {

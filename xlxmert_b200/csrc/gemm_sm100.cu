@@ -362,7 +362,7 @@ std::mutex g_maps_mu;
 std::atomic<long long> g_launches{0};
 
 // optional per-launch timing (bench.py roofline): events bracket every GEMM on its own stream
-struct TimedLaunch { cudaEvent_t e0, e1; double flops; };
+struct TimedLaunch { cudaEvent_t e0, e1; double flops; int M, N, K, passes, a_mn, b_mn, flags, grid; };
 bool g_timing = false;
 std::vector<TimedLaunch> g_timed;
 
@@ -437,15 +437,17 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   CUtensorMap mAhi, mAlo, mBhi, mBlo;
   const CUtensorMapSwizzle swzK = (BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   auto mk = [&](CUtensorMap* m, const GemmOperand& o, const __nv_bfloat16* ptr, int rows, int box_rows) -> int {
-    if (!o.mn_major) return make_map(m, ptr, p.K, rows, o.ld, BK, box_rows, swzK);
-    return make_map(m, ptr, rows, p.K, o.ld, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+    const int kext = o.kext ? o.kext : p.K;
+    if (!o.mn_major) return make_map(m, ptr, kext, rows, o.ld, BK, box_rows, swzK);
+    return make_map(m, ptr, rows, kext, o.ld, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B);
   };
   int rc;
-  if ((rc = mk(&mAhi, p.a, p.a.hi, p.M, BM))) return rc;
-  if ((rc = mk(&mBhi, p.b, p.b.hi, p.N, BN))) return rc;
+  const int a_rows = p.a.rows ? p.a.rows : p.M, b_rows = p.b.rows ? p.b.rows : p.N;
+  if ((rc = mk(&mAhi, p.a, p.a.hi, a_rows, BM))) return rc;
+  if ((rc = mk(&mBhi, p.b, p.b.hi, b_rows, BN))) return rc;
   if (P.nparts == 2) {
-    if ((rc = mk(&mAlo, p.a, p.a.lo, p.M, BM))) return rc;
-    if ((rc = mk(&mBlo, p.b, p.b.lo, p.N, BN))) return rc;
+    if ((rc = mk(&mAlo, p.a, p.a.lo, a_rows, BM))) return rc;
+    if ((rc = mk(&mBlo, p.b, p.b.lo, b_rows, BN))) return rc;
   } else {
     mAlo = mAhi; mBlo = mBhi;
   }
@@ -457,6 +459,10 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     cudaEventCreate(&tl.e0);
     cudaEventCreate(&tl.e1);
     tl.flops = 2.0 * p.M * p.N * p.K;
+    tl.M = p.M; tl.N = p.N; tl.K = p.K; tl.passes = p.passes; tl.a_mn = p.a.mn_major; tl.b_mn = p.b.mn_major;
+    tl.flags = p.epi.flags | (p.epi.out_f32 ? 256 : 0) | (p.epi.out_hi ? 512 : 0) | (p.epi.addend_hi ? 1024 : 0) |
+               (p.epi.out_u ? 2048 : 0) | (p.epi.addend ? 4096 : 0);
+    tl.grid = grid;
     cudaEventRecord(tl.e0, stream);
   }
   gemm_kernel<BK><<<grid, GEMM_THREADS, smem, stream>>>(mAhi, mAlo, mBhi, mBlo, P);
@@ -480,15 +486,20 @@ void gemm_timing_begin() {
 int gemm_timing_end(double* total_ms, double* total_flops, long long* launches) {
   g_timing = false;
   double ms = 0, fl = 0;
+  FILE* log = nullptr;
+  if (const char* path = getenv("XLX_GEMM_LOG")) log = fopen(path, "w");
+  if (log) fprintf(log, "M,N,K,passes,a_mn,b_mn,epi,grid,us\n");
   for (auto& t : g_timed) {
     cudaError_t e = cudaEventSynchronize(t.e1);
     if (e != cudaSuccess) return static_cast<int>(e);
     float m = 0;
     cudaEventElapsedTime(&m, t.e0, t.e1);
     ms += m; fl += t.flops;
+    if (log) fprintf(log, "%d,%d,%d,%d,%d,%d,%d,%d,%.2f\n", t.M, t.N, t.K, t.passes, t.a_mn, t.b_mn, t.flags, t.grid, m * 1e3);
     cudaEventDestroy(t.e0);
     cudaEventDestroy(t.e1);
   }
+  if (log) fclose(log);
   *total_ms = ms; *total_flops = fl; *launches = static_cast<long long>(g_timed.size());
   g_timed.clear();
   return 0;

@@ -49,6 +49,8 @@ struct GemmOperand {
   const __nv_bfloat16* lo = nullptr;   // may be null when passes == 1
   int ld = 0;                          // leading dimension in elements
   int mn_major = 0;                    // 0: stored [rows(M or N), K]; 1: stored [K, rows] (rows contiguous)
+  int rows = 0;                        // rows that exist in memory (0 → M or N); tiles beyond are zero-filled by TMA
+  int kext = 0;                        // extent along K that exists in memory (0 → K); zero-filled beyond
 };
 
 struct GemmProblem {

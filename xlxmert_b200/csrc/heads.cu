@@ -1,0 +1,417 @@
+// C ABI of the pieces around the encoder: LxmertEmbeddings (HF modeling_lxmert.py:179-214), LxmertPooler
+// (HF:568-580), and the pre-training heads — the reference's cluster head lxrt/modeling.py:8-53 with its
+// cross-entropy (:244-258) / sampler arg-max (tasks/imggen_model.py:232-235), and HF's LM head (HF:597-607,656-665).
+#include "../../include/xlxmert_b200.h"
+#include "host_util.cuh"
+
+using namespace xlx;
+
+namespace {
+
+bool hidden_ok(const xlx_dims* d) { return d && d->hidden > 0 && d->hidden % 128 == 0 && d->hidden <= 1024; }
+
+struct EmbSave { float *y, *mean, *rstd; size_t bytes; };
+EmbSave emb_layout(const xlx_dims* d, int M, void* base) {
+  Bump b; b.base = static_cast<char*>(base);
+  EmbSave s;
+  s.y = b.f32(static_cast<size_t>(M) * d->hidden);
+  s.mean = b.f32(M);
+  s.rstd = b.f32(M);
+  s.bytes = b.total();
+  return s;
+}
+
+struct PoolWs { Split x0, w, dpre; size_t bytes; };
+PoolWs pool_layout(const xlx_dims* d, int B, void* base) {
+  Bump b; b.base = static_cast<char*>(base);
+  const size_t H = d->hidden;
+  PoolWs w;
+  w.x0 = b.split(B * H);
+  w.w = b.split(H * H);
+  w.dpre = b.split(B * H);
+  w.bytes = b.total();
+  return w;
+}
+
+
+// ---- prediction heads ---------------------------------------------------------------------------------
+// Both heads are  t = LN(gelu(W1·h + b1))  [LxmertPredictionHeadTransform, HF:583-594]  followed by
+//   cluster head:  feat = Wf·t + bf  (H → F);  logits = feat·Centroidsᵀ + bc  (F → C)    lxrt/modeling.py:38-53
+//   LM head:       logits = t·Eᵀ + bias  (H → vocab, E tied to the word embeddings)       HF:597-607
+// `F == 0` selects the LM form.  Cp = C rounded up to a multiple of 8 (GEMM epilogue vector width).
+struct HeadDims { int H, F, C, Cp; float eps; };
+inline int pad8(int c) { return (c + 7) & ~7; }
+
+struct HeadPrep { Split w1, wf, wc; float* bc; size_t bytes; };
+HeadPrep head_prep_layout(const HeadDims& h, void* base) {
+  Bump b; b.base = static_cast<char*>(base);
+  HeadPrep p;
+  p.w1 = b.split(static_cast<size_t>(h.H) * h.H);
+  if (h.F) p.wf = b.split(static_cast<size_t>(h.F) * h.H);
+  p.wc = b.split(static_cast<size_t>(h.C) * (h.F ? h.F : h.H));
+  p.bc = b.f32(h.Cp);                                   // class bias, zero padded to Cp
+  p.bytes = b.total();
+  return p;
+}
+
+struct HeadWs {
+  Split x, t, feat, dlogits, dfeat, du;
+  float *u, *g, *mean, *rstd, *logits, *lse, *rowloss, *stats, *dt, *dg, *part, *dbc;
+  size_t bytes;
+};
+HeadWs head_ws_layout(const HeadDims& h, int M, void* base) {
+  Bump b; b.base = static_cast<char*>(base);
+  HeadWs w;
+  const size_t m = M, H = h.H, F = h.F, Cp = h.Cp;
+  w.x = b.split(m * H);
+  w.u = b.f32(m * H);
+  w.g = b.f32(m * H);
+  w.t = b.split(m * H);
+  w.mean = b.f32(m);
+  w.rstd = b.f32(m);
+  if (F) w.feat = b.split(m * F);
+  w.logits = b.f32(m * Cp);
+  w.lse = b.f32(m);
+  w.rowloss = b.f32(m);
+  w.stats = b.f32(4);
+  // backward scratch
+  w.dlogits = b.split(m * Cp);
+  if (F) w.dfeat = b.split(m * F);
+  w.dt = b.f32(m * H);
+  w.dg = b.f32(m * H);
+  w.du = b.split(m * H);
+  size_t pe = 2 * static_cast<size_t>(reduce_max_blocks()) * H;
+  const size_t widest = Cp > F ? Cp : F;
+  if (128 * widest > pe) pe = 128 * widest;
+  w.part = b.f32(pe);
+  w.dbc = b.f32(Cp);
+  w.bytes = b.total();
+  return w;
+}
+
+// params: [0] transform.dense.weight [1] .bias [2] transform.LayerNorm.weight [3] .bias, then
+//   cluster head: [4] linear_feat.weight [5] .bias [6] out_cluster.weight [7] out_cluster.bias
+//   LM head:      [4] decoder.weight [5] predictions.bias
+int head_prepare(const HeadDims& h, const float* const* params, void* prep, cudaStream_t st) {
+  HeadPrep p = head_prep_layout(h, prep);
+  const size_t H = h.H;
+  XLX_TRY(split_f32(params[0], p.w1, H * H, st));
+  const float* wc = params[h.F ? 6 : 4];
+  const float* bc = params[h.F ? 7 : 5];
+  if (h.F) XLX_TRY(split_f32(params[4], p.wf, static_cast<size_t>(h.F) * H, st));
+  XLX_TRY(split_f32(wc, p.wc, static_cast<size_t>(h.C) * (h.F ? h.F : H), st));
+  XLX_CUDA(cudaMemsetAsync(p.bc, 0, static_cast<size_t>(h.Cp) * 4, st));
+  XLX_CUDA(cudaMemcpyAsync(p.bc, bc, static_cast<size_t>(h.C) * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int head_fwd(const HeadDims& h, const float* const* params, const void* prep_base, int M, const float* hidden,
+             const int64_t* labels, float* feat_out, float* logits_out, float* loss, float* pred_prob,
+             int64_t* pred_id, void* ws_base, size_t ws_bytes, int passes, cudaStream_t st) {
+  HeadPrep p = head_prep_layout(h, const_cast<void*>(prep_base));
+  HeadWs w = head_ws_layout(h, M, ws_base);
+  if (w.bytes > ws_bytes) return -23;
+  const int H = h.H, F = h.F, C = h.C, Cp = h.Cp;
+  XLX_TRY(split_f32(hidden, w.x, static_cast<size_t>(M) * H, st));
+  {
+    GemmEpilogue e;   // u = W1·h + b1 (saved), g = gelu(u)
+    e.bias = params[1]; e.flags = EPI_GELU; e.out_u = w.u; e.ld_u = H; e.out_f32 = w.g; e.ld_out = H;
+    XLX_TRY(gemm_linear(passes, st, w.x, M, H, p.w1, H, e));
+  }
+  XLX_TRY(layernorm_fwd(w.g, params[2], params[3], h.eps, M, H, 1.0f, nullptr, w.t, nullptr, w.mean, w.rstd, st));
+  Split dec_in = w.t;
+  int Kc = H;
+  if (F) {
+    GemmEpilogue e;
+    e.bias = params[5]; e.out_f32 = feat_out; e.ld_out = F; e.out_hi = w.feat.hi; e.out_lo = w.feat.lo; e.ld_split = F;
+    XLX_TRY(gemm_linear(passes, st, w.t, M, H, p.wf, F, e));
+    dec_in = w.feat; Kc = F;
+  }
+  {
+    GemmEpilogue e;
+    e.bias = p.bc; e.out_f32 = w.logits; e.ld_out = Cp;
+    XLX_TRY(gemm_linear(passes, st, dec_in, M, Kc, p.wc, Cp, e, C));
+  }
+  if (logits_out)
+    XLX_CUDA(cudaMemcpy2DAsync(logits_out, static_cast<size_t>(C) * 4, w.logits, static_cast<size_t>(Cp) * 4,
+                               static_cast<size_t>(C) * 4, M, cudaMemcpyDeviceToDevice, st));
+  if (labels) {
+    XLX_TRY(ce_fwd(w.logits, Cp, M, C, labels, -100, w.lse, w.rowloss, w.stats, st));
+    if (loss) XLX_CUDA(cudaMemcpyAsync(loss, w.stats, 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (pred_prob && pred_id) XLX_TRY(softmax_argmax(w.logits, Cp, M, C, pred_prob, pred_id, st));
+  return 0;
+}
+
+// grads: device pointers shaped like params (overwritten).  The cluster head's out_cluster.weight ([6]) is the
+// frozen centroid table (lxrt/modeling.py:146-151) and gets no gradient; the LM head's decoder.weight ([4]) does.
+int head_bwd(const HeadDims& h, const float* const* params, const void* prep_base, int M, const int64_t* labels,
+             const float* d_loss, float* d_hidden, float* const* grads, void* ws_base, size_t ws_bytes, int passes,
+             cudaStream_t st) {
+  HeadPrep p = head_prep_layout(h, const_cast<void*>(prep_base));
+  HeadWs w = head_ws_layout(h, M, ws_base);
+  if (w.bytes > ws_bytes) return -23;
+  const int H = h.H, F = h.F, C = h.C, Cp = h.Cp;
+  XLX_TRY(ce_bwd(w.logits, Cp, M, C, Cp, labels, -100, w.lse, w.stats, d_loss, w.dlogits, st));
+  // class bias: column sums over the padded width into scratch, first C entries are the gradient
+  XLX_TRY(colsum(nullptr, w.dlogits, M, Cp, Cp, w.part, w.dbc, st));
+  XLX_CUDA(cudaMemcpyAsync(grads[F ? 7 : 5], w.dbc, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToDevice, st));
+  if (F) {
+    GemmEpilogue e;   // dfeat = dlogits · Centroids
+    e.out_hi = w.dfeat.hi; e.out_lo = w.dfeat.lo; e.ld_split = F;
+    XLX_TRY(gemm_dgrad(passes, st, w.dlogits, M, Cp, p.wc, F, e, C));
+    XLX_TRY(colsum(nullptr, w.dfeat, M, F, F, w.part, grads[5], st));
+    XLX_TRY(gemm_wgrad(passes, st, w.dfeat, M, F, w.t, H, grads[4]));
+    GemmEpilogue o;
+    o.out_f32 = w.dt; o.ld_out = H;
+    XLX_TRY(gemm_dgrad(passes, st, w.dfeat, M, F, p.wf, H, o));
+  } else {
+    XLX_TRY(gemm_wgrad(passes, st, w.dlogits, M, C, w.t, H, grads[4], false, Cp));   // dE [vocab, H]
+    GemmEpilogue o;
+    o.out_f32 = w.dt; o.ld_out = H;
+    XLX_TRY(gemm_dgrad(passes, st, w.dlogits, M, Cp, p.wc, H, o, C));
+  }
+  int nblk = 0;
+  XLX_TRY(layernorm_bwd(w.dt, 1.0f, w.g, params[2], w.mean, w.rstd, M, H, w.dg, Split(), w.part, &nblk, st));
+  float* o2[2] = {grads[2], grads[3]};
+  XLX_TRY(colsum_finish(w.part, 2, nblk, H, o2, 0, st));
+  XLX_TRY(gelu_bwd_split(w.dg, w.u, w.du, static_cast<size_t>(M) * H, st));
+  XLX_TRY(colsum(nullptr, w.du, M, H, H, w.part, grads[1], st));
+  XLX_TRY(gemm_wgrad(passes, st, w.du, M, H, w.x, H, grads[0]));
+  GemmEpilogue o;
+  o.out_f32 = d_hidden; o.ld_out = H;
+  return gemm_dgrad(passes, st, w.du, M, H, p.w1, H, o);
+}
+
+bool head_dims(const xlx_dims* d, int classes, bool cluster, HeadDims* h) {
+  if (!hidden_ok(d) || classes < 1) return false;
+  if (cluster && (d->feat_dim < 8 || d->feat_dim % 8)) return false;
+  h->H = d->hidden; h->F = cluster ? d->feat_dim : 0; h->C = classes; h->Cp = pad8(classes); h->eps = d->ln_eps;
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- visual input (lxrt/modeling.py:185-193) --------------------------------------------------------
+int32_t xlx_visual_input_fwd(const float* table, const int64_t* cluster_ids, const uint8_t* vis_mask,
+                             const float* mask_feat, int32_t rows, int32_t feat_dim, float* out, void* stream) {
+  if (rows < 1 || feat_dim < 4) return -21;
+  if (!table || !cluster_ids || !out || (vis_mask && !mask_feat)) return -24;
+  XLX_TRY(ensure_device(out));
+  return gather_rows(table, cluster_ids, vis_mask, mask_feat, rows, feat_dim, out, Split(),
+                     static_cast<cudaStream_t>(stream));
+}
+int32_t xlx_visual_input_bwd(const float* d_feats, const uint8_t* vis_mask, int32_t rows, int32_t feat_dim,
+                             float* d_mask_feat, float* scratch, void* stream) {
+  if (rows < 1 || feat_dim < 4) return -21;
+  if (!d_feats || !vis_mask || !d_mask_feat || !scratch) return -24;
+  XLX_TRY(ensure_device(d_mask_feat));
+  return colsum(d_feats, Split(), rows, feat_dim, feat_dim, scratch, d_mask_feat, static_cast<cudaStream_t>(stream),
+                vis_mask);
+}
+
+// ---- embeddings ---------------------------------------------------------------------------------
+size_t xlx_embeddings_save_bytes(const xlx_dims* d, int32_t B, int32_t L) {
+  return (hidden_ok(d) && B > 0 && L > 0) ? emb_layout(d, B * L, nullptr).bytes : 0;
+}
+size_t xlx_embeddings_scratch_bytes(const xlx_dims* d, int32_t B, int32_t L) {
+  if (!hidden_ok(d) || B < 1 || L < 1) return 0;
+  return (static_cast<size_t>(B) * L * d->hidden + 2 * static_cast<size_t>(reduce_max_blocks()) * d->hidden) * 4 + 512;
+}
+
+int32_t xlx_embeddings_fwd(const xlx_dims* d, int32_t B, int32_t L, const int64_t* input_ids,
+                           const int64_t* token_type_ids, const float* const* params, float* out, void* save,
+                           void* stream) {
+  if (!hidden_ok(d)) return -20;
+  if (B < 1 || L < 1) return -21;
+  if (!input_ids || !params || !out) return -24;
+  XLX_TRY(ensure_device(out));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int M = B * L, H = d->hidden;
+  // without a save buffer (inference) the pre-LayerNorm sum goes through `out` itself, normalised in place
+  EmbSave s = emb_layout(d, M, save);
+  float* y = save ? s.y : out;
+  XLX_TRY(embed_sum(input_ids, token_type_ids, params[0], params[1], params[2], M, L, H, y, st));
+  return layernorm_fwd(y, params[3], params[4], d->ln_eps, M, H, 1.0f, nullptr, Split(), out, save ? s.mean : nullptr,
+                       save ? s.rstd : nullptr, st);
+}
+
+int32_t xlx_embeddings_bwd(const xlx_dims* d, int32_t B, int32_t L, int32_t vocab, int32_t max_pos,
+                           int32_t type_vocab, const int64_t* input_ids, const int64_t* token_type_ids,
+                           const float* const* params, const void* save, const float* d_out, float* const* grads,
+                           void* scratch, size_t scratch_bytes, void* stream) {
+  if (!hidden_ok(d)) return -20;
+  if (B < 1 || L < 1 || L > max_pos) return -21;
+  if (!input_ids || !params || !save || !d_out || !grads || !scratch) return -24;
+  if (scratch_bytes < xlx_embeddings_scratch_bytes(d, B, L)) return -23;
+  XLX_TRY(ensure_device(scratch));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int M = B * L, H = d->hidden;
+  EmbSave s = emb_layout(d, M, const_cast<void*>(save));
+  Bump b; b.base = static_cast<char*>(scratch);
+  float* dy = b.f32(static_cast<size_t>(M) * H);
+  float* part = b.f32(2 * static_cast<size_t>(reduce_max_blocks()) * H);
+  int nblk = 0;
+  XLX_TRY(layernorm_bwd(d_out, 1.0f, s.y, params[3], s.mean, s.rstd, M, H, dy, Split(), part, &nblk, st));
+  float* o[2] = {grads[3], grads[4]};
+  XLX_TRY(colsum_finish(part, 2, nblk, H, o, 0, st));
+  XLX_CUDA(cudaMemsetAsync(grads[0], 0, static_cast<size_t>(vocab) * H * 4, st));
+  XLX_CUDA(cudaMemsetAsync(grads[1], 0, static_cast<size_t>(max_pos) * H * 4, st));
+  XLX_CUDA(cudaMemsetAsync(grads[2], 0, static_cast<size_t>(type_vocab) * H * 4, st));
+  return embed_scatter(input_ids, token_type_ids, dy, M, L, H, grads[0], grads[1], grads[2], st);
+}
+
+// ---- pooler -------------------------------------------------------------------------------------
+size_t xlx_pooler_workspace_bytes(const xlx_dims* d, int32_t B) {
+  return (hidden_ok(d) && B > 0) ? pool_layout(d, B, nullptr).bytes : 0;
+}
+
+int32_t xlx_pooler_fwd(const xlx_dims* d, int32_t B, int32_t L, const float* lang_out, const float* W,
+                       const float* bias, float* pooled, void* workspace, size_t workspace_bytes, int32_t passes,
+                       void* stream) {
+  if (!hidden_ok(d)) return -20;
+  if (B < 1 || L < 1) return -21;
+  if (!lang_out || !W || !bias || !pooled || !workspace) return -24;
+  if (passes != 1 && passes != 3) return -1;
+  XLX_TRY(ensure_device(workspace));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int H = d->hidden;
+  PoolWs w = pool_layout(d, B, workspace);
+  if (w.bytes > workspace_bytes) return -23;
+  XLX_TRY(split_rows_f32(lang_out, static_cast<size_t>(L) * H, B, H, w.x0, st));   // hidden_states[:, 0] (HF:577)
+  XLX_TRY(split_f32(W, w.w, static_cast<size_t>(H) * H, st));
+  GemmEpilogue e;
+  e.bias = bias; e.flags = EPI_TANH; e.out_f32 = pooled; e.ld_out = H;
+  return gemm_linear(passes, st, w.x0, B, H, w.w, H, e);
+}
+
+int32_t xlx_pooler_bwd(const xlx_dims* d, int32_t B, int32_t L, const float* pooled, const float* d_pooled,
+                       float* d_lang_out, float* dW, float* dbias, void* workspace, size_t workspace_bytes,
+                       int32_t passes, void* stream) {
+  if (!hidden_ok(d)) return -20;
+  if (B < 1 || L < 1) return -21;
+  if (!pooled || !d_pooled || !d_lang_out || !dW || !dbias || !workspace) return -24;
+  if (passes != 1 && passes != 3) return -1;
+  XLX_TRY(ensure_device(workspace));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int H = d->hidden;
+  PoolWs w = pool_layout(d, B, workspace);
+  if (w.bytes > workspace_bytes) return -23;
+  XLX_TRY(tanh_bwd_split(d_pooled, pooled, w.dpre, static_cast<size_t>(B) * H, st));
+  // dbias: column sums of dpre; the first H² floats of dW double as the partial-sum scratch before the wgrad
+  // GEMM overwrites them (needs reduce_max_blocks-independent bound: colsum uses ≤ 128 row blocks ≤ H rows)
+  XLX_TRY(colsum(nullptr, w.dpre, B, H, H, dW, dbias, st));
+  XLX_TRY(gemm_wgrad(passes, st, w.dpre, B, H, w.x0, H, dW));
+  XLX_CUDA(cudaMemsetAsync(d_lang_out, 0, static_cast<size_t>(B) * L * H * 4, st));
+  GemmEpilogue e;
+  e.out_f32 = d_lang_out; e.ld_out = L * H;     // row b of the GEMM lands on token 0 of sample b
+  return gemm_dgrad(passes, st, w.dpre, B, H, w.w, H, e);
+}
+
+
+// ---- cluster head (lxrt/modeling.py:8-53) and LM head (HF:597-607) ------------------------------------------
+#define XLX_HEAD_API(NAME, CLUSTER)                                                                                  \
+  size_t xlx_##NAME##_prep_bytes(const xlx_dims* d, int32_t classes) {                                              \
+    HeadDims h;                                                                                                      \
+    return head_dims(d, classes, CLUSTER, &h) ? head_prep_layout(h, nullptr).bytes : 0;                              \
+  }                                                                                                                  \
+  int32_t xlx_##NAME##_prepare(const xlx_dims* d, int32_t classes, const float* const* params, void* prep,           \
+                               void* stream) {                                                                       \
+    HeadDims h;                                                                                                      \
+    if (!head_dims(d, classes, CLUSTER, &h)) return -20;                                                             \
+    if (!params || !prep) return -24;                                                                                \
+    XLX_TRY(ensure_device(prep));                                                                                    \
+    return head_prepare(h, params, prep, static_cast<cudaStream_t>(stream));                                         \
+  }                                                                                                                  \
+  size_t xlx_##NAME##_workspace_bytes(const xlx_dims* d, int32_t classes, int32_t M) {                               \
+    HeadDims h;                                                                                                      \
+    return (head_dims(d, classes, CLUSTER, &h) && M > 0) ? head_ws_layout(h, M, nullptr).bytes : 0;                  \
+  }
+
+XLX_HEAD_API(objhead, true)
+XLX_HEAD_API(lmhead, false)
+
+int32_t xlx_objhead_fwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep, int32_t M,
+                        const float* hidden, const int64_t* labels, float* feat, float* logits, float* loss,
+                        float* pred_prob, int64_t* pred_id, void* workspace, size_t workspace_bytes, int32_t passes,
+                        void* stream) {
+  HeadDims h;
+  if (!head_dims(d, classes, true, &h)) return -20;
+  if (M < 1) return -21;
+  if (!params || !prep || !hidden || !workspace) return -24;
+  if (passes != 1 && passes != 3) return -1;
+  XLX_TRY(ensure_device(workspace));
+  return head_fwd(h, params, prep, M, hidden, labels, feat, logits, loss, pred_prob, pred_id, workspace,
+                  workspace_bytes, passes, static_cast<cudaStream_t>(stream));
+}
+int32_t xlx_objhead_bwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep, int32_t M,
+                        const int64_t* labels, const float* d_loss, float* d_hidden, float* const* grads,
+                        void* workspace, size_t workspace_bytes, int32_t passes, void* stream) {
+  HeadDims h;
+  if (!head_dims(d, classes, true, &h)) return -20;
+  if (M < 1) return -21;
+  if (!params || !prep || !labels || !d_loss || !d_hidden || !grads || !workspace) return -24;
+  if (passes != 1 && passes != 3) return -1;
+  XLX_TRY(ensure_device(workspace));
+  return head_bwd(h, params, prep, M, labels, d_loss, d_hidden, grads, workspace, workspace_bytes, passes,
+                  static_cast<cudaStream_t>(stream));
+}
+int32_t xlx_lmhead_fwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep, int32_t M,
+                       const float* hidden, const int64_t* labels, float* scores, float* loss, void* workspace,
+                       size_t workspace_bytes, int32_t passes, void* stream) {
+  HeadDims h;
+  if (!head_dims(d, classes, false, &h)) return -20;
+  if (M < 1) return -21;
+  if (!params || !prep || !hidden || !workspace) return -24;
+  if (passes != 1 && passes != 3) return -1;
+  XLX_TRY(ensure_device(workspace));
+  return head_fwd(h, params, prep, M, hidden, labels, nullptr, scores, loss, nullptr, nullptr, workspace,
+                  workspace_bytes, passes, static_cast<cudaStream_t>(stream));
+}
+int32_t xlx_lmhead_bwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep, int32_t M,
+                       const int64_t* labels, const float* d_loss, float* d_hidden, float* const* grads,
+                       void* workspace, size_t workspace_bytes, int32_t passes, void* stream) {
+  HeadDims h;
+  if (!head_dims(d, classes, false, &h)) return -20;
+  if (M < 1) return -21;
+  if (!params || !prep || !labels || !d_loss || !d_hidden || !grads || !workspace) return -24;
+  if (passes != 1 && passes != 3) return -1;
+  XLX_TRY(ensure_device(workspace));
+  return head_bwd(h, params, prep, M, labels, d_loss, d_hidden, grads, workspace, workspace_bytes, passes,
+                  static_cast<cudaStream_t>(stream));
+}
+
+// ---- matched head (HF:661,664: seq_relationship = Linear(H, 2) on the pooled output) + its cross-entropy -------
+// (lxrt/modeling.py:227-235).  scratch: xlx_matchhead_scratch_floats(B) floats, passed unchanged to the backward.
+int64_t xlx_matchhead_scratch_floats(int32_t B) { return B > 0 ? 3 * static_cast<int64_t>(B) + 8 : 0; }
+
+int32_t xlx_matchhead_fwd(const xlx_dims* d, int32_t B, const float* pooled, const float* W, const float* bias,
+                          const int64_t* labels, float* scores, float* loss, float* scratch, void* stream) {
+  if (!hidden_ok(d)) return -20;
+  if (B < 1) return -21;
+  if (!pooled || !W || !bias || !scores || (labels && !scratch)) return -24;
+  XLX_TRY(ensure_device(scores));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  XLX_TRY(small_linear_fwd(pooled, W, bias, B, d->hidden, 2, scores, st));
+  if (labels) {
+    XLX_TRY(small_ce_fwd(scores, B, 2, labels, -100, scratch + 8, scratch, st));
+    if (loss) XLX_CUDA(cudaMemcpyAsync(loss, scratch, 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+int32_t xlx_matchhead_bwd(const xlx_dims* d, int32_t B, const float* pooled, const float* W, const int64_t* labels,
+                          const float* scores, const float* d_loss, float* d_pooled, float* dW, float* dbias,
+                          float* scratch, void* stream) {
+  if (!hidden_ok(d)) return -20;
+  if (B < 1) return -21;
+  if (!pooled || !W || !labels || !scores || !d_loss || !d_pooled || !dW || !dbias || !scratch) return -24;
+  XLX_TRY(ensure_device(scores));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* dscores = scratch + 8 + B;
+  XLX_TRY(small_ce_bwd(scores, B, 2, labels, -100, scratch, d_loss, dscores, st));
+  return small_linear_bwd(dscores, pooled, W, B, d->hidden, 2, dW, dbias, d_pooled, st);
+}
+
+}  // extern "C"

@@ -78,6 +78,248 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const int64_
   }
 }
 
+// one CTA per row
+__global__ void split_rows_kernel(const float* __restrict__ x, size_t ld_in, int cols, bf16* hi, bf16* lo) {
+  const int r = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * ld_in);
+  for (int c = threadIdx.x; c < cols / 4; c += blockDim.x)
+    store_split4(hi, lo, static_cast<size_t>(r) * cols + c * 4, __ldg(src + c));
+}
+__global__ void tanh_bwd_kernel(const float4* __restrict__ d, const float4* __restrict__ y, bf16* hi, bf16* lo,
+                                size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 a = __ldg(d + i), t = __ldg(y + i);
+    store_split4(hi, lo, i * 4, make_float4(a.x * (1.f - t.x * t.x), a.y * (1.f - t.y * t.y),
+                                            a.z * (1.f - t.z * t.z), a.w * (1.f - t.w * t.w)));
+  }
+}
+// one CTA per token row
+__global__ void embed_sum_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ tt,
+                                 const float* __restrict__ word, const float* __restrict__ pos,
+                                 const float* __restrict__ type, int L, int H, float* y) {
+  const int r = blockIdx.x;
+  const float4* w = reinterpret_cast<const float4*>(word + static_cast<size_t>(ids[r]) * H);
+  const float4* p = reinterpret_cast<const float4*>(pos + static_cast<size_t>(r % L) * H);
+  const float4* t = reinterpret_cast<const float4*>(type + static_cast<size_t>(tt ? tt[r] : 0) * H);
+  for (int c = threadIdx.x; c < H / 4; c += blockDim.x) {
+    const float4 a = __ldg(w + c), b = __ldg(p + c), e = __ldg(t + c);
+    // same association as torch: (word + position) + token_type
+    *reinterpret_cast<float4*>(y + static_cast<size_t>(r) * H + c * 4) =
+        make_float4((a.x + b.x) + e.x, (a.y + b.y) + e.y, (a.z + b.z) + e.z, (a.w + b.w) + e.w);
+  }
+}
+__global__ void embed_scatter_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ tt,
+                                     const float* __restrict__ dy, int L, int H, float* dword, float* dpos,
+                                     float* dtype) {
+  const int r = blockIdx.x;
+  const int64_t id = ids[r], ty = tt ? tt[r] : 0;
+  const int l = r % L;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    const float g = __ldg(dy + static_cast<size_t>(r) * H + c);
+    if (id != 0) atomicAdd(dword + static_cast<size_t>(id) * H + c, g);
+    if (l != 0) atomicAdd(dpos + static_cast<size_t>(l) * H + c, g);
+    if (ty != 0) atomicAdd(dtype + static_cast<size_t>(ty) * H + c, g);
+  }
+}
+
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__global__ void gelu_bwd_kernel(const float4* __restrict__ dg, const float4* __restrict__ u, bf16* hi, bf16* lo,
+                                size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 a = __ldg(dg + i), x = __ldg(u + i);
+    store_split4(hi, lo, i * 4, make_float4(a.x * gelu_grad_f(x.x), a.y * gelu_grad_f(x.y), a.z * gelu_grad_f(x.z),
+                                            a.w * gelu_grad_f(x.w)));
+  }
+}
+
+// ---- cross-entropy ------------------------------------------------------------------------------
+constexpr int CE_T = 256;
+// online (max, Σexp) over a row; every thread ends with the block-wide result
+__device__ __forceinline__ void row_max_sumexp(const float* __restrict__ row, int C, float& mx_out, float& sum_out) {
+  __shared__ float s_m[CE_T / 32], s_s[CE_T / 32];
+  float m = -INFINITY, s = 0.f;
+  for (int c = threadIdx.x * 4; c < C; c += CE_T * 4) {
+    float v[4];
+    if (c + 4 <= C) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(row + c));
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (c + j < C) ? __ldg(row + c + j) : -INFINITY;
+    }
+    const float m2 = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+    if (m2 > m) { s *= expf(m - m2); m = m2; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += expf(v[j] - m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mm = fmaxf(m, m2);
+    s = (m == -INFINITY ? 0.f : s * expf(m - mm)) + (m2 == -INFINITY ? 0.f : s2 * expf(m2 - mm));
+    m = mm;
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) { s_m[w] = m; s_s[w] = s; }
+  __syncthreads();
+  float M = -INFINITY, S = 0.f;
+#pragma unroll
+  for (int i = 0; i < CE_T / 32; ++i) M = fmaxf(M, s_m[i]);
+#pragma unroll
+  for (int i = 0; i < CE_T / 32; ++i) S += (s_m[i] == -INFINITY) ? 0.f : s_s[i] * expf(s_m[i] - M);
+  mx_out = M; sum_out = S;
+}
+__global__ void __launch_bounds__(CE_T)
+ce_fwd_kernel(const float* __restrict__ logits, int ld, int C, const int64_t* __restrict__ labels, int64_t ignore,
+              float* lse, float* rowloss) {
+  const int m = blockIdx.x;
+  const float* row = logits + static_cast<size_t>(m) * ld;
+  float mx, sum;
+  row_max_sumexp(row, C, mx, sum);
+  if (threadIdx.x == 0) {
+    const float l = mx + logf(sum);
+    lse[m] = l;
+    const int64_t y = labels[m];
+    rowloss[m] = (y == ignore) ? 0.f : l - __ldg(row + y);
+  }
+}
+// single CTA, fixed reduction order: deterministic
+__global__ void __launch_bounds__(1024)
+ce_finish_kernel(const float* __restrict__ rowloss, const int64_t* __restrict__ labels, int64_t ignore, int M,
+                 float* stats) {
+  __shared__ double s_l[32];
+  __shared__ int s_n[32];
+  double acc = 0.0;
+  int n = 0;
+  for (int i = threadIdx.x; i < M; i += 1024)
+    if (labels[i] != ignore) { acc += static_cast<double>(rowloss[i]); ++n; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); n += __shfl_xor_sync(0xffffffffu, n, o); }
+  if ((threadIdx.x & 31) == 0) { s_l[threadIdx.x >> 5] = acc; s_n[threadIdx.x >> 5] = n; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    int c = 0;
+    for (int i = 0; i < 32; ++i) { t += s_l[i]; c += s_n[i]; }
+    stats[0] = static_cast<float>(t / static_cast<double>(c));   // 0/0 → NaN like torch when nothing is labelled
+    stats[1] = static_cast<float>(c);
+  }
+}
+__global__ void __launch_bounds__(CE_T)
+ce_bwd_kernel(const float* __restrict__ logits, int ld, int C, int Cp, const int64_t* __restrict__ labels, int64_t ignore,
+              const float* __restrict__ lse, const float* __restrict__ stats, const float* __restrict__ d_loss, bf16* hi,
+              bf16* lo) {
+  const int m = blockIdx.x;
+  const int64_t y = labels[m];
+  const float* row = logits + static_cast<size_t>(m) * ld;
+  const size_t o = static_cast<size_t>(m) * Cp;
+  const float scale = (y == ignore) ? 0.f : __ldg(d_loss) / __ldg(stats + 1);
+  const float l = lse[m];
+  for (int c = threadIdx.x * 4; c < Cp; c += CE_T * 4) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = c + j;
+      v[j] = (cc < C && scale != 0.f) ? (expf(__ldg(row + cc) - l) - (cc == y ? 1.f : 0.f)) * scale : 0.f;
+    }
+    store_split4(hi, lo, o + c, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+__global__ void __launch_bounds__(CE_T)
+softmax_argmax_kernel(const float* __restrict__ logits, int ld, int C, float* prob, int64_t* id) {
+  __shared__ float s_v[CE_T / 32];
+  __shared__ int s_i[CE_T / 32];
+  const int m = blockIdx.x;
+  const float* row = logits + static_cast<size_t>(m) * ld;
+  float mx, sum;
+  row_max_sumexp(row, C, mx, sum);
+  // first index whose probability exp(x − max)/Σ is maximal: exp is monotone, so that is the first index with
+  // exp(x − max) == 1, i.e. the first x that rounds to the maximum under expf (mirrors torch.max over softmax)
+  int best = 0x7fffffff;
+  for (int c = threadIdx.x; c < C; c += CE_T)
+    if (expf(__ldg(row + c) - mx) == 1.0f) { best = c; break; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_i[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int b = s_i[0];
+    for (int i = 1; i < CE_T / 32; ++i) b = min(b, s_i[i]);
+    id[m] = b;
+    prob[m] = 1.0f / sum;
+  }
+  (void)s_v;
+}
+
+// thread per row, C ≤ 8
+__global__ void small_ce_kernel(const float* __restrict__ logits, int M, int C, const int64_t* __restrict__ labels,
+                                int64_t ignore, float* rowloss, const float* __restrict__ stats,
+                                const float* __restrict__ d_loss, float* dlogits) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float* row = logits + static_cast<size_t>(m) * C;
+  float mx = -INFINITY;
+  for (int c = 0; c < C; ++c) mx = fmaxf(mx, row[c]);
+  float sum = 0.f;
+  for (int c = 0; c < C; ++c) sum += expf(row[c] - mx);
+  const float lse = mx + logf(sum);
+  const int64_t y = labels[m];
+  if (rowloss) rowloss[m] = (y == ignore) ? 0.f : lse - row[y];
+  if (dlogits) {
+    const float scale = (y == ignore) ? 0.f : __ldg(d_loss) / __ldg(stats + 1);
+    for (int c = 0; c < C; ++c)
+      dlogits[static_cast<size_t>(m) * C + c] = scale == 0.f ? 0.f : (expf(row[c] - lse) - (c == y ? 1.f : 0.f)) * scale;
+  }
+}
+
+// ---- tiny-N linear (matched head) ---------------------------------------------------------------------
+// one warp per row
+__global__ void small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                        const float* __restrict__ b, int M, int K, int N, float* y) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  for (int n = 0; n < N; ++n) {
+    float a = 0.f;
+    for (int k = lane; k < K; k += 32) a += __ldg(x + static_cast<size_t>(row) * K + k) * __ldg(W + static_cast<size_t>(n) * K + k);
+    a = warp_sum(a);
+    if (lane == 0) y[static_cast<size_t>(row) * N + n] = a + __ldg(b + n);
+  }
+}
+// dx[m,k] = Σ_n dy[m,n] W[n,k]
+__global__ void small_linear_dx_kernel(const float* __restrict__ dy, const float* __restrict__ W, int M, int K, int N,
+                                       float* dx) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<size_t>(M) * K) return;
+  const int m = i / K, k = i % K;
+  float a = 0.f;
+  for (int n = 0; n < N; ++n) a += __ldg(dy + static_cast<size_t>(m) * N + n) * __ldg(W + static_cast<size_t>(n) * K + k);
+  dx[i] = a;
+}
+// dW[n,k] = Σ_m dy[m,n] x[m,k] (thread per (n,k), fixed order); db[n] = Σ_m dy[m,n]
+__global__ void small_linear_dw_kernel(const float* __restrict__ dy, const float* __restrict__ x, int M, int K, int N,
+                                       float* dW, float* db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N * K) {
+    const int n = i / K, k = i % K;
+    float a = 0.f;
+    for (int m = 0; m < M; ++m) a += __ldg(dy + static_cast<size_t>(m) * N + n) * __ldg(x + static_cast<size_t>(m) * K + k);
+    dW[i] = a;
+  } else if (i < N * K + N) {
+    const int n = i - N * K;
+    float a = 0.f;
+    for (int m = 0; m < M; ++m) a += __ldg(dy + static_cast<size_t>(m) * N + n);
+    db[n] = a;
+  }
+}
+
 inline int grid_for(size_t n, int threads) {
   size_t b = (n + threads - 1) / threads;
   return static_cast<int>(b < 148 * 16 ? (b ? b : 1) : 148 * 16);
@@ -220,13 +462,14 @@ __global__ void colsum_finish_kernel(const float* __restrict__ part, int nblk, i
 // Column sums: CTA = 32 column quads (128 columns) × 8 row lanes; grid (ceil(N/128), nblk).
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ xf, const bf16* __restrict__ xh, const bf16* __restrict__ xl, int M, int N,
-              int ld, float* scratch) {
+              int ld, float* scratch, const uint8_t* __restrict__ rowmask) {
   __shared__ float4 red[8][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + tx) * 4;
   float4 a = make_float4(0, 0, 0, 0);
   if (col < N) {
     for (int m = blockIdx.y * 8 + ty; m < M; m += gridDim.y * 8) {
+      if (rowmask && !rowmask[m]) continue;
       const size_t idx = static_cast<size_t>(m) * ld + col;
       float4 v = xf ? __ldg(reinterpret_cast<const float4*>(xf + idx)) : load_split4(xh, xl, idx);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
@@ -594,6 +837,98 @@ int gather_rows(const float* table, const int64_t* ids, const uint8_t* mask, con
   return launch_rc();
 }
 
+int split_rows_f32(const float* x, size_t ld_in, int rows, int cols, Split out, cudaStream_t s) {
+  if ((cols % 4) || (ld_in % 4)) return -2;
+  if (!rows) return 0;
+  split_rows_kernel<<<rows, 192, 0, s>>>(x, ld_in, cols, out.hi, out.lo);
+  return launch_rc();
+}
+int tanh_bwd_split(const float* d, const float* y, Split out, size_t n, cudaStream_t s) {
+  if (n % 4) return -2;
+  if (!n) return 0;
+  tanh_bwd_kernel<<<grid_for(n / 4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(d),
+                                                        reinterpret_cast<const float4*>(y), out.hi, out.lo, n / 4);
+  return launch_rc();
+}
+int embed_sum(const int64_t* ids, const int64_t* tt, const float* word, const float* pos, const float* type, int rows,
+              int L, int H, float* y, cudaStream_t s) {
+  if (H % 4) return -2;
+  if (!rows) return 0;
+  embed_sum_kernel<<<rows, 192, 0, s>>>(ids, tt, word, pos, type, L, H, y);
+  return launch_rc();
+}
+int embed_scatter(const int64_t* ids, const int64_t* tt, const float* dy, int rows, int L, int H, float* dword,
+                  float* dpos, float* dtype, cudaStream_t s) {
+  if (!rows) return 0;
+  embed_scatter_kernel<<<rows, 256, 0, s>>>(ids, tt, dy, L, H, dword, dpos, dtype);
+  return launch_rc();
+}
+
+int gelu_bwd_split(const float* dg, const float* u, Split out, size_t n, cudaStream_t s) {
+  if (n % 4) return -2;
+  if (!n) return 0;
+  gelu_bwd_kernel<<<grid_for(n / 4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(dg),
+                                                        reinterpret_cast<const float4*>(u), out.hi, out.lo, n / 4);
+  return launch_rc();
+}
+int ce_fwd(const float* logits, int ld, int M, int C, const int64_t* labels, int64_t ignore_index, float* lse,
+           float* rowloss, float* stats, cudaStream_t s) {
+  if (ld % 4) return -2;
+  if (M < 1 || C < 1) return -21;
+  ce_fwd_kernel<<<M, CE_T, 0, s>>>(logits, ld, C, labels, ignore_index, lse, rowloss);
+  int rc = launch_rc();
+  if (rc) return rc;
+  ce_finish_kernel<<<1, 1024, 0, s>>>(rowloss, labels, ignore_index, M, stats);
+  return launch_rc();
+}
+int ce_bwd(const float* logits, int ld, int M, int C, int Cp, const int64_t* labels, int64_t ignore_index,
+           const float* lse, const float* stats, const float* d_loss, Split dlogits, cudaStream_t s) {
+  if ((ld % 4) || (Cp % 4) || Cp < C) return -2;
+  if (M < 1) return -21;
+  ce_bwd_kernel<<<M, CE_T, 0, s>>>(logits, ld, C, Cp, labels, ignore_index, lse, stats, d_loss, dlogits.hi, dlogits.lo);
+  return launch_rc();
+}
+int softmax_argmax(const float* logits, int ld, int M, int C, float* prob, int64_t* id, cudaStream_t s) {
+  if (ld % 4) return -2;
+  if (M < 1 || C < 1) return -21;
+  softmax_argmax_kernel<<<M, CE_T, 0, s>>>(logits, ld, C, prob, id);
+  return launch_rc();
+}
+int small_ce_fwd(const float* logits, int M, int C, const int64_t* labels, int64_t ignore_index, float* rowloss,
+                 float* stats, cudaStream_t s) {
+  if (C < 1 || C > 8) return -1;
+  if (M < 1) return -21;
+  small_ce_kernel<<<(M + 127) / 128, 128, 0, s>>>(logits, M, C, labels, ignore_index, rowloss, nullptr, nullptr, nullptr);
+  int rc = launch_rc();
+  if (rc) return rc;
+  ce_finish_kernel<<<1, 1024, 0, s>>>(rowloss, labels, ignore_index, M, stats);
+  return launch_rc();
+}
+int small_ce_bwd(const float* logits, int M, int C, const int64_t* labels, int64_t ignore_index, const float* stats,
+                 const float* d_loss, float* dlogits, cudaStream_t s) {
+  if (C < 1 || C > 8) return -1;
+  if (M < 1) return -21;
+  small_ce_kernel<<<(M + 127) / 128, 128, 0, s>>>(logits, M, C, labels, ignore_index, nullptr, stats, d_loss, dlogits);
+  return launch_rc();
+}
+int small_linear_fwd(const float* x, const float* W, const float* b, int M, int K, int N, float* y, cudaStream_t s) {
+  if (N < 1 || N > 8) return -1;
+  if (!M) return 0;
+  small_linear_fwd_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, W, b, M, K, N, y);
+  return launch_rc();
+}
+int small_linear_bwd(const float* dy, const float* x, const float* W, int M, int K, int N, float* dW, float* db,
+                     float* dx, cudaStream_t s) {
+  if (N < 1 || N > 8) return -1;
+  if (!M) return 0;
+  small_linear_dw_kernel<<<(N * K + N + 255) / 256, 256, 0, s>>>(dy, x, M, K, N, dW, db);
+  int rc = launch_rc();
+  if (rc) return rc;
+  const size_t n = static_cast<size_t>(M) * K;
+  small_linear_dx_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(dy, W, M, K, N, dx);
+  return launch_rc();
+}
+
 #define XLX_LN_DISPATCH(KERNEL, H, ...)                        \
   switch (H) {                                                 \
     case 128: KERNEL<1> __VA_ARGS__; break;                    \
@@ -631,12 +966,13 @@ int colsum_finish(const float* part, int nvec, int nblk, int H, float* const* ou
                                                                    accumulate);
   return launch_rc();
 }
-int colsum(const float* x_f32, Split x, int M, int N, int ld, float* scratch, float* out, cudaStream_t s) {
+int colsum(const float* x_f32, Split x, int M, int N, int ld, float* scratch, float* out, cudaStream_t s,
+           const uint8_t* rowmask) {
   if ((N % 4) || (ld % 4)) return -2;
   int nblk = (M + 63) / 64;
   if (nblk > 128) nblk = 128;
   if (nblk < 1) nblk = 1;
-  colsum_kernel<<<dim3((N + 127) / 128, nblk), 256, 0, s>>>(x_f32, x.hi, x.lo, M, N, ld, scratch);
+  colsum_kernel<<<dim3((N + 127) / 128, nblk), 256, 0, s>>>(x_f32, x.hi, x.lo, M, N, ld, scratch, rowmask);
   int rc = launch_rc();
   if (rc) return rc;
   float* outs[1] = {out};

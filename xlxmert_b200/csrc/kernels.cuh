@@ -32,6 +32,48 @@ int gather_rows(const float* table, const int64_t* ids, const uint8_t* mask, con
 int concat3_f32(const float* a, const float* b, const float* c, float* dst, int n, cudaStream_t s);
 int fill_f32(float* dst, float v, size_t n, cudaStream_t s);
 
+// x rows with stride ld_in (fp32) → contiguous split matrix [rows, cols]; cols % 4 == 0.
+int split_rows_f32(const float* x, size_t ld_in, int rows, int cols, Split out, cudaStream_t s);
+// dpre = d · (1 − y²) (tanh backward) → split; n % 4 == 0.
+int tanh_bwd_split(const float* d, const float* y, Split out, size_t n, cudaStream_t s);
+
+// LxmertEmbeddings (HF modeling_lxmert.py:191-214) before its LayerNorm:
+//   y[r,:] = word[ids[r],:] + pos[r % L,:] + type[tt ? tt[r] : 0,:]      r < B·L, H % 4 == 0
+int embed_sum(const int64_t* ids, const int64_t* tt, const float* word, const float* pos, const float* type, int rows,
+              int L, int H, float* y, cudaStream_t s);
+// Scatter-add of dy [rows,H] into the three (pre-zeroed) table gradients; row 0 of each table has
+// padding_idx semantics (no gradient, HF:184-186).
+int embed_scatter(const int64_t* ids, const int64_t* tt, const float* dy, int rows, int L, int H, float* dword,
+                  float* dpos, float* dtype, cudaStream_t s);
+
+// du = dg ∘ gelu'(u) → split; n % 4 == 0.
+int gelu_bwd_split(const float* dg, const float* u, Split out, size_t n, cudaStream_t s);
+
+// ---- cross-entropy / arg-max over a [M, C] logits matrix with row stride ld (fp32) ---------------------
+// torch.nn.CrossEntropyLoss() (mean over rows whose label != ignore, lxrt/modeling.py:99,102,253-256):
+// lse[m] = logsumexp(logits[m,:]); stats[0] = loss, stats[1] = number of valid rows (as float).
+int ce_fwd(const float* logits, int ld, int M, int C, const int64_t* labels, int64_t ignore_index, float* lse,
+           float* rowloss, float* stats, cudaStream_t s);
+// dlogits[m,c] = d_loss · (softmax(logits)[m,c] − 1[c == label]) / n_valid for valid rows, else 0; columns
+// C..Cp-1 are written as zero.  Output: split matrix [M, Cp].
+int ce_bwd(const float* logits, int ld, int M, int C, int Cp, const int64_t* labels, int64_t ignore_index,
+           const float* lse, const float* stats, const float* d_loss, Split dlogits, cudaStream_t s);
+// softmax(logits, -1).max(-1) → (prob, id); ties go to the first index like torch.max
+// (tasks/imggen_model.py:232-235).
+int softmax_argmax(const float* logits, int ld, int M, int C, float* prob, int64_t* id, cudaStream_t s);
+
+// Same loss for a tiny class count (C ≤ 8, row stride C): rowloss/stats as ce_fwd; dlogits fp32 [M,C].
+int small_ce_fwd(const float* logits, int M, int C, const int64_t* labels, int64_t ignore_index, float* rowloss,
+                 float* stats, cudaStream_t s);
+int small_ce_bwd(const float* logits, int M, int C, const int64_t* labels, int64_t ignore_index, const float* stats,
+                 const float* d_loss, float* dlogits, cudaStream_t s);
+
+// y[M,N] = x[M,K]·W[N,K]ᵀ + b for tiny N (≤ 8) — the 2-way matched head (HF:661,664).
+int small_linear_fwd(const float* x, const float* W, const float* b, int M, int K, int N, float* y, cudaStream_t s);
+// dW[N,K] = dyᵀ·x, db[N] = Σ dy, dx[M,K] = dy·W.
+int small_linear_bwd(const float* dy, const float* x, const float* W, int M, int K, int N, float* dW, float* db,
+                     float* dx, cudaStream_t s);
+
 // LayerNorm over the last axis (biased variance; HF modeling_lxmert.py:188,281,343 use eps 1e-12):
 //   o = out_scale · LN(y) + addend;   y [M,H] fp32 → split out and/or fp32 out; optionally saves mean / rstd.
 int layernorm_fwd(const float* y, const float* gamma, const float* beta, float eps, int M, int H, float out_scale,
@@ -46,8 +88,9 @@ int reduce_max_blocks();  // upper bound on nblk for every partial-sum kernel he
 int colsum_finish(const float* part, int nvec, int nblk, int H, float* const* outs, int accumulate, cudaStream_t s);
 
 // column sums: out[N] = Σ_m x[m, n]  (bias gradients) of an fp32 or split matrix with leading dimension ld.
-// scratch: [reduce_max_blocks(), N] floats.
-int colsum(const float* x_f32, Split x, int M, int N, int ld, float* scratch, float* out, cudaStream_t s);
+// scratch: [128, N] floats.  rowmask (optional, one byte per row): only rows with a non-zero byte are summed.
+int colsum(const float* x_f32, Split x, int M, int N, int ld, float* scratch, float* out, cudaStream_t s,
+           const uint8_t* rowmask = nullptr);
 
 // box branch of LxmertVisualFeatureEncoder (HF:479-480): y2[m,h] = bp[h] + Σ_j pos[m,j]·Wp[h,j], j < 4.
 int box_linear_fwd(const float* pos, const float* Wp, const float* bp, int M, int H, float* y2, cudaStream_t s);

@@ -166,6 +166,7 @@ class _EncoderFn(torch.autograd.Function):
         d_lang_in = torch.empty(B, L, d.hidden, device=dev, dtype=torch.float32)
         d_feats = torch.empty(B, V, d.feat_dim, device=dev, dtype=torch.float32) if ctx.need_dfeats else None
         grads = enc._grad_arena(dev)
+        enc.last_grad_arena = grads
         rc = lib.xlx_encoder_bwd(C.byref(enc._cdims), ctx.parr, ctx.prep.data_ptr(), B, L, V,
                                  ctx.visual_pos.data_ptr(), _ptr(d_lang_out), _ptr(d_vis_out),
                                  d_lang_in.data_ptr(), _ptr(d_feats), grads.data_ptr(), ctx.ws.data_ptr(),
@@ -212,8 +213,10 @@ class B200LxmertEncoder(nn.Module):
         self._parr = None
         self._ws_pool: List[torch.Tensor] = []
         self._ws_busy: List[torch.Tensor] = []
-        self._grads = None
         self._grad_slices = None
+        #: flat fp32 arena holding every parameter gradient of the most recent backward (the ``.grad`` tensors
+        #: are views into it) — one contiguous buffer for the data-parallel all-reduce (lxmert_pretrain.py:104-106)
+        self.last_grad_arena: Optional[torch.Tensor] = None
 
     # -- parameters in C-ABI slot order
     def _param_list(self) -> List[torch.Tensor]:
@@ -238,6 +241,11 @@ class B200LxmertEncoder(nn.Module):
             _lib.check("xlx_encoder_prepare", rc)
             self._prep_key = key
         return self._prep, self._parr
+
+    def invalidate_prepared(self) -> None:
+        """Force the split-bf16 weight copies to be rebuilt on the next forward (after an in-place update
+        that bypassed the tensors' version counters, e.g. a fused optimiser writing through raw pointers)."""
+        self._prep_key = None
 
     def _workspace(self, nbytes: int, dev, training: bool) -> torch.Tensor:
         for i, t in enumerate(self._ws_pool):
