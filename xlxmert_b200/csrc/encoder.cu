@@ -98,7 +98,7 @@ struct AttSave {
   int M = 0;
 };
 struct FfnSave {
-  float* u = nullptr;  // pre-GeLU [M, I]
+  float* u = nullptr;  // gelu'(pre-activation) [M, I], saved by the forward epilogue for the backward
   Split h;             // gelu(u) [M, I]
   float* y = nullptr;
   float* mean = nullptr;
@@ -115,6 +115,7 @@ struct Plan {
   std::vector<FfnSave> ffn;
   float* part = nullptr;
   size_t part_elems = 0;
+  float* splitk = nullptr;   // split-K partial sums of the weight-gradient GEMMs
   // backward scratch
   float *dA = nullptr, *dB = nullptr, *dy = nullptr, *dctx = nullptr, *dy2 = nullptr;
   Split dy_s, dqkv, du;
@@ -252,6 +253,7 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
     p.dy_s = b.split(Mt * H);
     p.dqkv = b.split(Mt * 3 * H);
     p.du = b.split(Mmax * I);
+    p.splitk = b.f32(gemm_splitk_ws_floats());
   }
   p.bytes = b.off + 256;
   return p;
@@ -276,7 +278,7 @@ int dgrad(const Run& r, Split dy, int M, int N, Split w, int K, const GemmEpilog
   return gemm_dgrad(r.passes, r.st, dy, M, N, w, K, e);
 }
 int wgrad(const Run& r, Split dy, int M, int N, Split x, int K, float* dw) {
-  return gemm_wgrad(r.passes, r.st, dy, M, N, x, K, dw);
+  return gemm_wgrad(r.passes, r.st, dy, M, N, x, K, dw, false, 0, r.plan.splitk);
 }
 
 const float* P(const Run& r, int slot) { return r.params[slot]; }
@@ -336,7 +338,7 @@ int ffn_fwd(const Run& r, int blk, float* out_f32) {
   const FfnW& w = r.prep.ffn[blk];
   const int s0 = ffn_slot(r.d, blk), H = p.H, I = p.I, M = f.M;
   GemmEpilogue e;
-  e.bias = P(r, s0 + 1); e.flags = EPI_GELU; e.out_u = f.u; e.ld_u = I;
+  e.bias = P(r, s0 + 1); e.flags = EPI_GELU | EPI_SAVE_DGELU; e.out_u = f.u; e.ld_u = I;   // f.u ← gelu'(pre-activation)
   e.out_hi = f.h.hi; e.out_lo = f.h.lo; e.ld_split = I;
   XLX_TRY(linear(r, f.in, M, H, w.w1, I, e));
   GemmEpilogue o;
@@ -374,8 +376,8 @@ int ffn_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
   XLX_TRY(ln_tail_bwd(bw, dout, f.y, s0 + 4, f.mean, f.rstd, M, p.dy, p.dy_s));
   XLX_TRY(colsum(p.dy, Split(), M, H, H, p.part, bw.G(s0 + 3), r.st));
   XLX_TRY(wgrad(r, p.dy_s, M, H, f.h, I, bw.G(s0 + 2)));
-  GemmEpilogue e;   // du = (dy · W2) ∘ gelu'(u)
-  e.flags = EPI_GELU_GRAD; e.u_in = f.u; e.ld_u = I; e.out_hi = p.du.hi; e.out_lo = p.du.lo; e.ld_split = I;
+  GemmEpilogue e;   // du = (dy · W2) ∘ gelu'(u), the derivative was saved by the forward
+  e.flags = EPI_MUL; e.u_in = f.u; e.ld_u = I; e.out_hi = p.du.hi; e.out_lo = p.du.lo; e.ld_split = I;
   XLX_TRY(dgrad(r, p.dy_s, M, H, w.w2, I, e));
   XLX_TRY(colsum(nullptr, p.du, M, I, I, p.part, bw.G(s0 + 1), r.st));
   XLX_TRY(wgrad(r, p.du, M, I, f.in, H, bw.G(s0)));

@@ -16,7 +16,13 @@ namespace xlx {
 namespace {
 
 constexpr int BM = 128;            // UMMA M (one TMEM lane per output row)
-constexpr int GEMM_THREADS = 192;  // 6 warps: TMA, MMA, 4 × epilogue
+#ifndef XLX_EPI_WARPS
+#define XLX_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = XLX_EPI_WARPS;  // EPI_WARPS/4 warps per TMEM lane quadrant, alternating 32-column chunks
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;  // warp 0: TMA, warp 1: MMA, then the epilogue warps
+constexpr int STAGE_PITCH = 36;    // floats per staged row: 16-byte aligned, conflict-free for both phases
+constexpr int STAGE_BYTES = EPI_WARPS * 32 * STAGE_PITCH * 4;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA on sm_100
 
@@ -29,12 +35,12 @@ struct KParams {
   int tiles_m, tiles_n;
   uint32_t stage_bytes, a_part_bytes, b_part_bytes;
   uint32_t tmem_cols;
+  int splits;          // split-K factor (1 = none); work item = (tile, split)
+  int kb_per_split;    // k-blocks per split (last split may be shorter)
+  float* part;         // [splits][M][N] fp32 partial sums when splits > 1
   GemmEpilogue epi;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   // d/dx [x·Φ(x)] = Φ(x) + x·φ(x)
   float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
@@ -42,107 +48,73 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// One thread's slice of the epilogue: 32 consecutive columns of one output row.
-__device__ __forceinline__ void epilogue_row(const KParams& P, int row, int n, int nvalid, uint32_t (&r)[32]) {
+// Epilogue on 4 consecutive columns of one output row.  Called in the "coalesced domain": the 8 lanes of a
+// quarter warp hold 32 consecutive columns of the same row, so every global access below is a full 128-byte
+// (fp32) or 64-byte (bf16) segment.
+__device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, float4 acc) {
   const GemmEpilogue& E = P.epi;
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * E.alpha;
+  float v[4] = {acc.x * E.alpha, acc.y * E.alpha, acc.z * E.alpha, acc.w * E.alpha};
   if (E.bias) {
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (g * 4 < nvalid) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(E.bias + n + g * 4));
-        v[g * 4 + 0] += b.x; v[g * 4 + 1] += b.y; v[g * 4 + 2] += b.z; v[g * 4 + 3] += b.w;
-      }
-    }
-  }
-  if (E.out_u) {
-    float* dst = E.out_u + static_cast<size_t>(row) * E.ld_u + n;
-#pragma unroll
-    for (int g = 0; g < 8; ++g)
-      if (g * 4 < nvalid)
-        *reinterpret_cast<float4*>(dst + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(E.bias + n));
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
   }
   if (E.flags & EPI_GELU) {
+    float dg[4];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 4; ++j) {
+      // gelu(x) = x·Φ(x), gelu'(x) = Φ(x) + x·φ(x): one erf serves both
+      const float x = v[j];
+      const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+      dg[j] = (E.flags & EPI_SAVE_DGELU) ? cdf + x * (0.39894228040143267794f * __expf(-0.5f * x * x)) : x;
+      v[j] = x * cdf;
+    }
+    if (E.out_u)
+      *reinterpret_cast<float4*>(E.out_u + static_cast<size_t>(row) * E.ld_u + n) = make_float4(dg[0], dg[1], dg[2], dg[3]);
+  } else if (E.out_u) {
+    *reinterpret_cast<float4*>(E.out_u + static_cast<size_t>(row) * E.ld_u + n) = make_float4(v[0], v[1], v[2], v[3]);
   }
   if (E.flags & EPI_TANH) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+    for (int j = 0; j < 4; ++j) v[j] = tanhf(v[j]);
   }
   if (E.flags & EPI_GELU_GRAD) {
-    const float* src = E.u_in + static_cast<size_t>(row) * E.ld_u + n;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (g * 4 < nvalid) {
-        float4 u = __ldg(reinterpret_cast<const float4*>(src + g * 4));
-        v[g * 4 + 0] *= gelu_erf_grad(u.x); v[g * 4 + 1] *= gelu_erf_grad(u.y);
-        v[g * 4 + 2] *= gelu_erf_grad(u.z); v[g * 4 + 3] *= gelu_erf_grad(u.w);
-      }
-    }
+    const float4 u = __ldg(reinterpret_cast<const float4*>(E.u_in + static_cast<size_t>(row) * E.ld_u + n));
+    v[0] *= gelu_erf_grad(u.x); v[1] *= gelu_erf_grad(u.y); v[2] *= gelu_erf_grad(u.z); v[3] *= gelu_erf_grad(u.w);
+  }
+  if (E.flags & EPI_MUL) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(E.u_in + static_cast<size_t>(row) * E.ld_u + n));
+    v[0] *= u.x; v[1] *= u.y; v[2] *= u.z; v[3] *= u.w;
   }
   if (E.addend) {
-    const float* src = E.addend + static_cast<size_t>(row) * E.ld_addend + n;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (g * 4 < nvalid) {
-        float4 a = __ldg(reinterpret_cast<const float4*>(src + g * 4));
-        v[g * 4 + 0] += a.x; v[g * 4 + 1] += a.y; v[g * 4 + 2] += a.z; v[g * 4 + 3] += a.w;
-      }
-    }
+    const float4 a = __ldg(reinterpret_cast<const float4*>(E.addend + static_cast<size_t>(row) * E.ld_addend + n));
+    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
   }
   if (E.addend_hi) {
-    const __nv_bfloat16* sh = E.addend_hi + static_cast<size_t>(row) * E.ld_addend + n;
-    const __nv_bfloat16* sl = E.addend_lo + static_cast<size_t>(row) * E.ld_addend + n;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g * 8 < nvalid) {
-        uint4 h = __ldg(reinterpret_cast<const uint4*>(sh + g * 8));
-        uint4 l = __ldg(reinterpret_cast<const uint4*>(sl + g * 8));
-        const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          v[g * 8 + 2 * t] += __uint_as_float(hh[t] << 16) + __uint_as_float(ll[t] << 16);
-          v[g * 8 + 2 * t + 1] += __uint_as_float(hh[t] & 0xffff0000u) + __uint_as_float(ll[t] & 0xffff0000u);
-        }
-      }
-    }
+    const size_t idx = static_cast<size_t>(row) * E.ld_addend + n;
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(E.addend_hi + idx));
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(E.addend_lo + idx));
+    v[0] += __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+    v[1] += __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+    v[2] += __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+    v[3] += __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
   }
   if (E.out_f32) {
-    float* dst = E.out_f32 + static_cast<size_t>(row) * E.ld_out + n;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (g * 4 < nvalid) {
-        float4 o = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        if (E.flags & EPI_ACCUM) {
-          float4 old = *reinterpret_cast<const float4*>(dst + g * 4);
-          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-        }
-        *reinterpret_cast<float4*>(dst + g * 4) = o;
-      }
+    float4* dst = reinterpret_cast<float4*>(E.out_f32 + static_cast<size_t>(row) * E.ld_out + n);
+    float4 o = make_float4(v[0], v[1], v[2], v[3]);
+    if (E.flags & EPI_ACCUM) {
+      const float4 old = *dst;
+      o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
     }
+    *dst = o;
   }
   if (E.out_hi) {
-    __nv_bfloat16* dh = E.out_hi + static_cast<size_t>(row) * E.ld_split + n;
-    __nv_bfloat16* dl = E.out_lo ? E.out_lo + static_cast<size_t>(row) * E.ld_split + n : nullptr;
+    const size_t idx = static_cast<size_t>(row) * E.ld_split + n;
+    __nv_bfloat16 h[4], l[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g * 8 < nvalid) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v[g * 8 + 2 * t], h0, l0);
-          split_bf16(v[g * 8 + 2 * t + 1], h1, l1);
-          hw[t] = pack_bf16x2(h0, h1);
-          lw[t] = pack_bf16x2(l0, l1);
-        }
-        *reinterpret_cast<uint4*>(dh + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        if (dl) *reinterpret_cast<uint4*>(dl + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      }
-    }
+    for (int j = 0; j < 4; ++j) split_bf16(v[j], h[j], l[j]);
+    *reinterpret_cast<uint2*>(E.out_hi + idx) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+    if (E.out_lo)
+      *reinterpret_cast<uint2*>(E.out_lo + idx) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
   }
 }
 
@@ -163,6 +135,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024B alignment
 
   const int num_tiles = P.tiles_m * P.tiles_n;
+  const int num_items = num_tiles * P.splits;
   const int nkb = (P.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
@@ -178,7 +151,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_tmem_full[b]), 1);
-      mbar_init(smem_u32(&bar_tmem_empty[b]), 4);  // one arrival per epilogue warp
+      mbar_init(smem_u32(&bar_tmem_empty[b]), EPI_WARPS);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -196,10 +169,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int tile = item % num_tiles, split = item / num_tiles;
         const int m0 = (tile / P.tiles_n) * BM;
         const int n0 = (tile % P.tiles_n) * P.BN;
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int kb0 = split * P.kb_per_split, kb1 = min(nkb, kb0 + P.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
           const uint32_t full = smem_u32(&bar_full[s]);
           mbar_arrive_expect_tx(full, P.stage_bytes);
@@ -241,13 +216,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+        const int split = item / num_tiles;
+        const int kb0 = split * P.kb_per_split, kb1 = min(nkb, kb0 + P.kb_per_split);
         const int buf = local & 1;
         const uint32_t acc_ph = (local >> 1) & 1;
         mbar_wait(smem_u32(&bar_tmem_empty[buf]), acc_ph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * P.BN;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bar_full[s]), ph);
           tc_fence_after();
           const uint32_t sA = smem_base + s * P.stage_bytes;
@@ -260,7 +237,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
                                          : umma_smem_desc(sA + offA, 16, kSboK, kSwzK);
             const uint64_t dBhi = P.b_mn ? umma_smem_desc(sB + offB, kLboMN, kSboMN, UMMA_SWZ_128B)
                                          : umma_smem_desc(sB + offB, 16, kSboK, kSwzK);
-            const uint32_t first = (kb | kk) ? 1u : 0u;
+            const uint32_t first = ((kb - kb0) | kk) ? 1u : 0u;
             if (P.nparts == 2) {
               const uint64_t dAlo = P.a_mn ? umma_smem_desc(sA + P.a_part_bytes + offA, kLboMN, kSboMN, UMMA_SWZ_128B)
                                            : umma_smem_desc(sA + P.a_part_bytes + offA, 16, kSboK, kSwzK);
@@ -275,38 +252,70 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
             }
           }
           umma_commit(smem_u32(&bar_empty[s]));              // smem slot reusable once these MMAs retire
-          if (kb == nkb - 1) umma_commit(smem_u32(&bar_tmem_full[buf]));
+          if (kb == kb1 - 1) umma_commit(smem_u32(&bar_tmem_full[buf]));
           if (++s == P.num_stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // TMEM → registers (thread = row) → shared-memory transpose → coalesced global traffic (quarter warp = 128 B
+    // of one row).  Warps e and e + 4 share TMEM lane quadrant q = warp % 4 and alternate 32-column chunks.
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int e = warp - 2;                 // epilogue warp index 0 … EPI_WARPS-1
+    const int half = e >> 2;                // which of the EPI_WARPS/4 warps of the quadrant
+    float* stage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + P.num_stages * P.stage_bytes) +
+                   e * 32 * STAGE_PITCH;
+    const int sub = lane >> 3, cq = lane & 7;
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+      const int tile = item % num_tiles, split = item / num_tiles;
       const int buf = local & 1;
       const uint32_t acc_ph = (local >> 1) & 1;
       const int m0 = (tile / P.tiles_n) * BM;
       const int n0 = (tile % P.tiles_n) * P.BN;
       mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_ph);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * P.BN;
       const int nchunks = P.BN / 32;
-      for (int c = 0; c < nchunks; ++c) {
-        const int n = n0 + c * 32;
-        if (n >= P.N) break;
+      // last chunk this warp will read (chunks beyond N are skipped by both warps alike)
+      int last_c = -1;
+      for (int c = half; c < nchunks; c += EPI_WARPS / 4)
+        if (n0 + c * 32 < P.N) last_c = c;
+      if (last_c < 0) {   // nothing to read from this accumulator: hand it back right away
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
+      }
+      for (int c = half; c <= last_c; c += EPI_WARPS / 4) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
-        const bool last = (c == nchunks - 1) || (n + 32 >= P.N);
-        if (last) {  // accumulator fully read: hand the TMEM buffer back before the global stores
+        if (c == last_c) {  // accumulator fully read by this warp: release before the global traffic
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
         }
-        if (row < P.M) epilogue_row(P, row, n, min(32, P.N - n), r);
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(stage + lane * STAGE_PITCH + g * 4) =
+              make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]),
+                          __uint_as_float(r[g * 4 + 3]));
+        __syncwarp();
+        const int n = n0 + c * 32 + cq * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + sub;
+          const int row = m0 + q * 32 + rr;
+          const float4 acc = *reinterpret_cast<const float4*>(stage + rr * STAGE_PITCH + cq * 4);
+          if (row < P.M && n < P.N) {
+            if (P.splits > 1)   // raw partial sums; the reduce kernel finishes the job
+              *reinterpret_cast<float4*>(P.part + (static_cast<size_t>(split) * P.M + row) * P.N + n) = acc;
+            else
+              epilogue_vec4(P, row, n, acc);
+          }
+        }
+        __syncwarp();
       }
     }
   }
@@ -316,6 +325,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, P.tmem_cols);
+  }
+}
+
+// out[m, n] (+)= Σ_s part[s][m][n]  — second phase of a split-K GEMM (plain fp32 output only)
+__global__ void splitk_reduce_kernel(const float4* __restrict__ part, int splits, size_t mn4, int n4, float* out,
+                                     int ld_out, int accumulate) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < mn4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 a = __ldg(part + i);
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = __ldg(part + s * mn4 + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const size_t m = i / n4, c = i % n4;
+    float4* dst = reinterpret_cast<float4*>(out + m * ld_out) + c;
+    if (accumulate) {
+      const float4 o = *dst;
+      a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+    }
+    *dst = a;
   }
 }
 
@@ -423,7 +452,7 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   P.a_part_bytes = BM * BK * 2;
   P.b_part_bytes = BN * BK * 2;
   P.stage_bytes = P.nparts * (P.a_part_bytes + P.b_part_bytes);
-  int stages = (SMEM_LIMIT - 2048 - 1024) / static_cast<int>(P.stage_bytes);
+  int stages = (SMEM_LIMIT - 2048 - 1024 - STAGE_BYTES) / static_cast<int>(P.stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return -3;
   P.num_stages = stages;
@@ -452,8 +481,34 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     mAlo = mAhi; mBlo = mBhi;
   }
   const int num_tiles = P.tiles_m * P.tiles_n;
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  const size_t smem = static_cast<size_t>(stages) * P.stage_bytes + 1024;
+  const int nkb = (p.K + BK - 1) / BK;
+  // split-K: only for plain fp32-output GEMMs (weight gradients) whose tile count leaves most SMs idle
+  P.splits = 1; P.kb_per_split = nkb; P.part = nullptr;
+  const bool plain = p.epi.out_f32 && !p.epi.bias && !p.epi.addend && !p.epi.addend_hi && !p.epi.out_hi &&
+                     !p.epi.out_u && !(p.epi.flags & ~EPI_ACCUM) && p.epi.alpha == 1.0f;
+  static const int splitk_on = env_int("XLX_GEMM_SPLITK", 1);
+  if (splitk_on && plain && p.splitk_ws && num_tiles < num_sms) {
+    // pick the split count whose work items fill whole waves of SMs best (ties → fewer splits)
+    const size_t need = static_cast<size_t>(p.M) * p.N;
+    int maxS = nkb / 8;                                         // ≥ 8 k-blocks per split
+    if (maxS > 16) maxS = 16;
+    int best = 1;
+    double best_eff = 0.0;
+    for (int S = 1; S <= maxS && need * S <= p.splitk_ws_floats; ++S) {
+      const int items = num_tiles * S;
+      const int waves = (items + num_sms - 1) / num_sms;
+      const double eff = static_cast<double>(items) / (static_cast<double>(waves) * num_sms);
+      if (eff > best_eff + 0.03) { best_eff = eff; best = S; }
+    }
+    if (best > 1) {
+      P.kb_per_split = (nkb + best - 1) / best;
+      P.splits = (nkb + P.kb_per_split - 1) / P.kb_per_split;
+      P.part = p.splitk_ws;
+    }
+  }
+  const int num_items = num_tiles * P.splits;
+  const int grid = num_items < num_sms ? num_items : num_sms;
+  const size_t smem = static_cast<size_t>(stages) * P.stage_bytes + 1024 + STAGE_BYTES;
   TimedLaunch tl{};
   if (g_timing) {
     cudaEventCreate(&tl.e0);
@@ -466,6 +521,15 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     cudaEventRecord(tl.e0, stream);
   }
   gemm_kernel<BK><<<grid, GEMM_THREADS, smem, stream>>>(mAhi, mAlo, mBhi, mBlo, P);
+  if (P.splits > 1) {
+    const size_t mn4 = static_cast<size_t>(p.M) * p.N / 4;
+    size_t blocks = (mn4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(P.part), P.splits, mn4, p.N / 4, p.epi.out_f32, p.epi.ld_out,
+        (p.epi.flags & EPI_ACCUM) ? 1 : 0);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   if (g_timing) {
     cudaEventRecord(tl.e1, stream);
     g_timed.push_back(tl);
@@ -478,6 +542,8 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
 }  // namespace
 
 long long gemm_launch_count() { return g_launches.load(); }
+// splits · tiles ≤ 2 · #SMs and every tile is ≤ 128 × 256 outputs
+size_t gemm_splitk_ws_floats() { return static_cast<size_t>(2 * 148) * BM * 256; }
 
 void gemm_timing_begin() {
   g_timed.clear();
@@ -510,15 +576,15 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream) {
   if (p.passes != 1 && p.passes != 3) return -1;
   if (!p.a.hi || !p.b.hi) return -1;
   if (p.passes == 3 && (!p.a.lo || !p.b.lo)) return -1;
-  if ((p.a.ld % 8) || (p.b.ld % 8) || (p.N % 8)) return -2;  // TMA: 16-byte global strides; epilogue: 16B vectors
+  if ((p.a.ld % 8) || (p.b.ld % 8) || (p.N % 4)) return -2;  // TMA: 16-byte global strides; epilogue: 4-column vectors
   if ((reinterpret_cast<uintptr_t>(p.a.hi) | reinterpret_cast<uintptr_t>(p.b.hi) |
        reinterpret_cast<uintptr_t>(p.a.lo) | reinterpret_cast<uintptr_t>(p.b.lo)) & 15)
     return -2;
   const GemmEpilogue& E = p.epi;
-  if ((E.out_f32 && (E.ld_out % 4)) || (E.out_hi && (E.ld_split % 8)) ||
-      ((E.addend || E.addend_hi) && (E.ld_addend % 8)) || ((E.out_u || E.u_in) && (E.ld_u % 4)))
+  if ((E.out_f32 && (E.ld_out % 4)) || (E.out_hi && (E.ld_split % 4)) ||
+      ((E.addend || E.addend_hi) && (E.ld_addend % 4)) || ((E.out_u || E.u_in) && (E.ld_u % 4)))
     return -2;
-  if ((E.flags & EPI_GELU_GRAD) && !E.u_in) return -1;
+  if ((E.flags & (EPI_GELU_GRAD | EPI_MUL)) && !E.u_in) return -1;
   if (E.addend_hi && !E.addend_lo) return -1;
   static const int bk = env_int("XLX_GEMM_BK", 32);
   return bk == 64 ? launch_bk<64>(p, stream) : launch_bk<32>(p, stream);

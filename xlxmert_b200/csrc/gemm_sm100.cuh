@@ -27,6 +27,8 @@ enum EpiFlags : int {
   EPI_GELU_GRAD = 2,   // v *= gelu'(u_in[m,n])
   EPI_ACCUM = 4,       // out_f32 += v instead of = v
   EPI_TANH = 8,        // v = tanh(v) after bias
+  EPI_SAVE_DGELU = 16, // with EPI_GELU: out_u receives gelu'(pre-activation) instead of the pre-activation
+  EPI_MUL = 32,        // v *= u_in[m,n]  (backward of an activation whose derivative was saved by the forward)
 };
 
 struct GemmEpilogue {
@@ -58,7 +60,13 @@ struct GemmProblem {
   GemmOperand a, b;
   int passes = 3;
   GemmEpilogue epi;
+  // Optional split-K scratch (fp32).  When given, GEMMs with a plain fp32 epilogue whose output has too few
+  // tiles to occupy the SMs (weight gradients: small M·N, huge K) are split along K into partial sums here
+  // and reduced by a second kernel.  gemm_splitk_ws_floats() is always enough.
+  float* splitk_ws = nullptr;
+  size_t splitk_ws_floats = 0;
 };
+size_t gemm_splitk_ws_floats();
 
 // Returns 0 on success, negative on invalid arguments, positive CUDA error otherwise.
 int gemm_launch(const GemmProblem& p, cudaStream_t stream);

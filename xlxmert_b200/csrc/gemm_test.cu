@@ -1,6 +1,7 @@
 // Standalone correctness probe for the tcgen05 GEMM (run on the B200 box through gpurun):
 //   gemm_test M N K passes a_mn b_mn epi
-// epi bits: 1 bias, 2 gelu(+save u), 4 addend, 8 split output check, 16 gelu-grad, 32 accumulate
+// epi bits: 1 bias, 2 gelu(+save u), 4 addend, 8 split output check, 16 gelu-grad, 32 accumulate,
+//           64 multiply by u_in, 128 (with 2) save gelu'(u) instead of u
 // Compares against a double-precision CPU reference on sampled entries and prints max relative error.
 #include <cmath>
 #include <cstdio>
@@ -76,6 +77,8 @@ int main(int argc, char** argv) {
   if (epi & 8) { p.epi.out_hi = dOhi; p.epi.out_lo = dOlo; p.epi.ld_split = N; }
   if (epi & 16) { p.epi.flags |= EPI_GELU_GRAD; p.epi.u_in = duin; p.epi.ld_u = N; }
   if (epi & 32) p.epi.flags |= EPI_ACCUM;
+  if (epi & 64) { p.epi.flags |= EPI_MUL; p.epi.u_in = duin; p.epi.ld_u = N; }
+  if (epi & 128) p.epi.flags |= EPI_SAVE_DGELU;
   int rc = gemm_launch(p, 0);
   if (rc) { printf("gemm_launch rc=%d\n", rc); return 3; }
   CK(cudaDeviceSynchronize());
@@ -106,7 +109,9 @@ int main(int argc, char** argv) {
     double v = acc;
     if (epi & 1) v += bias[c];
     double u = v;
+    if (epi & 128) u = 0.5 * (1.0 + erf(v / sqrt(2.0))) + v * exp(-0.5 * v * v) / sqrt(2.0 * M_PI);
     if (epi & 2) v = 0.5 * v * (1.0 + erf(v / sqrt(2.0)));
+    if (epi & 64) v *= uin[idx];
     if (epi & 16) { double x = uin[idx]; v *= 0.5 * (1.0 + erf(x / sqrt(2.0))) + x * exp(-0.5 * x * x) / sqrt(2.0 * M_PI); }
     if (epi & 4) v += addend[idx];
     if (epi & 32) v += out0[idx];

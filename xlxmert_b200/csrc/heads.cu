@@ -56,7 +56,7 @@ HeadPrep head_prep_layout(const HeadDims& h, void* base) {
 
 struct HeadWs {
   Split x, t, feat, dlogits, dfeat, du;
-  float *u, *g, *mean, *rstd, *logits, *lse, *rowloss, *stats, *dt, *dg, *part, *dbc;
+  float *u, *g, *mean, *rstd, *logits, *lse, *rowloss, *stats, *dt, *dg, *part, *dbc, *splitk;
   size_t bytes;
 };
 HeadWs head_ws_layout(const HeadDims& h, int M, void* base) {
@@ -85,6 +85,7 @@ HeadWs head_ws_layout(const HeadDims& h, int M, void* base) {
   if (128 * widest > pe) pe = 128 * widest;
   w.part = b.f32(pe);
   w.dbc = b.f32(Cp);
+  w.splitk = b.f32(gemm_splitk_ws_floats());
   w.bytes = b.total();
   return w;
 }
@@ -161,12 +162,12 @@ int head_bwd(const HeadDims& h, const float* const* params, const void* prep_bas
     e.out_hi = w.dfeat.hi; e.out_lo = w.dfeat.lo; e.ld_split = F;
     XLX_TRY(gemm_dgrad(passes, st, w.dlogits, M, Cp, p.wc, F, e, C));
     XLX_TRY(colsum(nullptr, w.dfeat, M, F, F, w.part, grads[5], st));
-    XLX_TRY(gemm_wgrad(passes, st, w.dfeat, M, F, w.t, H, grads[4]));
+    XLX_TRY(gemm_wgrad(passes, st, w.dfeat, M, F, w.t, H, grads[4], false, 0, w.splitk));
     GemmEpilogue o;
     o.out_f32 = w.dt; o.ld_out = H;
     XLX_TRY(gemm_dgrad(passes, st, w.dfeat, M, F, p.wf, H, o));
   } else {
-    XLX_TRY(gemm_wgrad(passes, st, w.dlogits, M, C, w.t, H, grads[4], false, Cp));   // dE [vocab, H]
+    XLX_TRY(gemm_wgrad(passes, st, w.dlogits, M, C, w.t, H, grads[4], false, Cp, w.splitk));   // dE [vocab, H]
     GemmEpilogue o;
     o.out_f32 = w.dt; o.ld_out = H;
     XLX_TRY(gemm_dgrad(passes, st, w.dlogits, M, Cp, p.wc, H, o, C));
@@ -177,7 +178,7 @@ int head_bwd(const HeadDims& h, const float* const* params, const void* prep_bas
   XLX_TRY(colsum_finish(w.part, 2, nblk, H, o2, 0, st));
   XLX_TRY(gelu_bwd_split(w.dg, w.u, w.du, static_cast<size_t>(M) * H, st));
   XLX_TRY(colsum(nullptr, w.du, M, H, H, w.part, grads[1], st));
-  XLX_TRY(gemm_wgrad(passes, st, w.du, M, H, w.x, H, grads[0]));
+  XLX_TRY(gemm_wgrad(passes, st, w.du, M, H, w.x, H, grads[0], false, 0, w.splitk));
   GemmEpilogue o;
   o.out_f32 = d_hidden; o.ld_out = H;
   return gemm_dgrad(passes, st, w.du, M, H, p.w1, H, o);

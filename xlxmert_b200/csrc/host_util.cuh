@@ -87,13 +87,14 @@ inline int gemm_dgrad(int passes, cudaStream_t st, Split dy, int M, int N, Split
 }
 // dW[N,K] (+)= dY[M,N]ᵀ · X[M,K];  ld_dy: leading dimension of dY (0 → N)
 inline int gemm_wgrad(int passes, cudaStream_t st, Split dy, int M, int N, Split x, int K, float* dw,
-                      bool accumulate = false, int ld_dy = 0) {
+                      bool accumulate = false, int ld_dy = 0, float* splitk_ws = nullptr) {
   GemmProblem p;
   p.M = N; p.N = K; p.K = M; p.passes = passes;
   p.a.hi = dy.hi; p.a.lo = dy.lo; p.a.ld = ld_dy ? ld_dy : N; p.a.mn_major = 1;
   p.b.hi = x.hi; p.b.lo = x.lo; p.b.ld = K; p.b.mn_major = 1;
   p.epi.out_f32 = dw; p.epi.ld_out = K;
   if (accumulate) p.epi.flags |= EPI_ACCUM;
+  p.splitk_ws = splitk_ws; p.splitk_ws_floats = splitk_ws ? gemm_splitk_ws_floats() : 0;
   return gemm_launch(p, st);
 }
 

@@ -10,7 +10,7 @@ namespace xlx {
 namespace {
 
 std::atomic<long long> g_aux_launches{0};
-constexpr int kMaxBlocks = 592;  // 4 × 148 SMs: enough CTAs in flight for the HBM-bound reductions
+constexpr int kMaxBlocks = 296;  // 2 × 148 SMs: enough CTAs in flight for the HBM-bound reductions
 
 inline int launch_rc() {
   g_aux_launches.fetch_add(1, std::memory_order_relaxed);
@@ -440,23 +440,31 @@ ln_bwd_kernel(const float* __restrict__ dy, float dy_scale, const float* __restr
   }
 }
 
-// out_v[h] = Σ_blk part[v][blk][h]; grid (ceil(H/256), nvec)
-__global__ void colsum_finish_kernel(const float* __restrict__ part, int nblk, int H, float* o0, float* o1, float* o2,
-                                     float* o3, float* o4, int accumulate) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+// out_v[h] = Σ_blk part[v][blk][h]; CTA = 32 columns × 8 block lanes, grid (ceil(H/32), nvec); fixed order
+__global__ void __launch_bounds__(256)
+colsum_finish_kernel(const float* __restrict__ part, int nblk, int H, float* o0, float* o1, float* o2, float* o3,
+                     float* o4, int accumulate) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int h = blockIdx.x * 32 + tx;
   const int v = blockIdx.y;
   float* out = v == 0 ? o0 : v == 1 ? o1 : v == 2 ? o2 : v == 3 ? o3 : o4;
-  if (h >= H || !out) return;
-  const float* p = part + static_cast<size_t>(v) * nblk * H + h;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int b = 0;
-  for (; b + 4 <= nblk; b += 4) {
-    a0 += p[static_cast<size_t>(b) * H]; a1 += p[static_cast<size_t>(b + 1) * H];
-    a2 += p[static_cast<size_t>(b + 2) * H]; a3 += p[static_cast<size_t>(b + 3) * H];
+  if (!out) return;
+  float a0 = 0.f, a1 = 0.f;
+  if (h < H) {
+    const float* p = part + static_cast<size_t>(v) * nblk * H + h;
+    int b = ty;
+    for (; b + 8 < nblk; b += 16) { a0 += __ldg(p + static_cast<size_t>(b) * H); a1 += __ldg(p + static_cast<size_t>(b + 8) * H); }
+    if (b < nblk) a0 += __ldg(p + static_cast<size_t>(b) * H);
   }
-  for (; b < nblk; ++b) a0 += p[static_cast<size_t>(b) * H];
-  const float sum = (a0 + a1) + (a2 + a3);
-  out[h] = accumulate ? out[h] + sum : sum;
+  red[ty][tx] = a0 + a1;
+  __syncthreads();
+  if (ty == 0 && h < H) {
+    float sum = red[0][tx];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) sum += red[w][tx];
+    out[h] = accumulate ? out[h] + sum : sum;
+  }
 }
 
 // Column sums: CTA = 32 column quads (128 columns) × 8 row lanes; grid (ceil(N/128), nblk).
@@ -962,7 +970,7 @@ int colsum_finish(const float* part, int nvec, int nblk, int H, float* const* ou
   if (nvec < 1 || nvec > 5) return -1;
   float* o[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int v = 0; v < nvec; ++v) o[v] = outs[v];
-  colsum_finish_kernel<<<dim3((H + 255) / 256, nvec), 256, 0, s>>>(part, nblk, H, o[0], o[1], o[2], o[3], o[4],
+  colsum_finish_kernel<<<dim3((H + 31) / 32, nvec), 256, 0, s>>>(part, nblk, H, o[0], o[1], o[2], o[3], o[4],
                                                                    accumulate);
   return launch_rc();
 }
