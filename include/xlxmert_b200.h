@@ -184,6 +184,29 @@ int32_t xlx_matchhead_bwd(const xlx_dims* d, int32_t B, const float* pooled, con
                           const float* scores, const float* d_loss, float* d_pooled, float* dW, float* dbias,
                           float* scratch, void* stream);
 
+/* ---- Generator.forward (image_generator/src/layers.py:223-253) ----------------------------------------------
+ * Canonical architecture only (scripts/train_generator.bash, tasks/sample_images.py:53-67): base_dim 32, emb_dim
+ * 2048, codebook_dim 256, norm 'spade_in', SN, 8×8 grid → 256×256 RGB, five up-sampling residual blocks.
+ * params: HOST array of xlx_generator_num_params() = 150 device pointers in this order:
+ *   bottleneck_emb.0.{weight,bias}; learned_init_conv.0.{weight_orig,bias,weight_u,weight_v}; style_init_conv.0.{…};
+ *   per block i: cbn1.{shared.0,gamma,beta}.{weight,bias}, cbn2.{…}, conv1.{weight_orig,bias,weight_u,weight_v},
+ *   conv2.{…}, res_branch.1.{…}, noise1.weight, noise2.weight;  then to_RGB_blocks.i.conv.{weight,bias}.
+ * Spectral norm has eval semantics: weight = weight_orig / (uᵀ·W·v) with the stored u, v (folded by *_prepare).
+ * emb: [B, 64, 2048] fp32, grid-cell major (the memory layout behind the sampler's
+ * code.permute(0,2,1).view(B,2048,8,8), tasks/imggen_model.py:254, and layers.py:231-233's [B,8,8,2048]).
+ * noise: NULL (forward(train=False)) or HOST array of 10 device pointers, [B,R,R] standard-normal maps for
+ * noise1 / noise2 of each block (R = 8,16, 16,32, …, 128,256; layers.py:56-62).
+ * img: [B,3,256,256] fp32 (NCHW like the reference); pre_tanh (optional) same shape; block_out (optional): HOST
+ * array of 5 device pointers receiving each block's output as NHWC [B,2R,2R,32]. */
+int64_t xlx_generator_num_params(void);
+int64_t xlx_generator_launch_count(void);
+size_t xlx_generator_prep_bytes(void);
+int32_t xlx_generator_prepare(const float* const* params, void* prep, void* stream);
+size_t xlx_generator_workspace_bytes(int32_t B);
+int32_t xlx_generator_fwd(const float* const* params, const void* prep, int32_t B, const float* emb,
+                          const float* const* noise, float* img, float* pre_tanh, float* const* block_out,
+                          void* workspace, size_t workspace_bytes, int32_t passes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

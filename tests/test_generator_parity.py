@@ -1,0 +1,68 @@
+"""GPU parity of the generator forward against the golden produced by the reference's own ``Generator``
+(oracle/make_golden.py::golden_generator; eval mode, noise off, converged spectral-norm buffers).  Compared:
+every residual block's output, the pre-tanh accumulator and the image (not the image alone —
+tanh saturation hides errors).  Tolerance: 1e-3 tensor-normalised (north_star), observed far below."""
+import pytest
+import torch
+
+from xlxmert_b200 import params as P
+from xlxmert_b200 import synth
+from xlxmert_b200.config import DEFAULT_DIMS as D
+
+from util import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    from xlxmert_b200.generator import B200Generator
+    g = load_golden("generator_b2")
+    B, wseed, bseed = (int(x) for x in g["meta"])
+    G = B200Generator(base_dim=32, emb_dim=2048, norm_type="spade_in", target_size=256, init_H=8, init_W=8, SN=True,
+                      codebook_dim=256)
+    sd = P.init_generator_state_dict(seed=wseed)
+    missing, unexpected = G.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    G = G.cuda().eval()
+    batch = synth.make_batch(D, B, 20, 64, seed=bseed)
+    code = synth.visual_feats_from(synth.centroid_table(D), batch["cluster_ids"]).cuda()      # [B, 64, 2048]
+    return g, G, code, B
+
+
+def test_generator_matches_reference_golden():
+    g, G, code, B = _setup()
+    emb = code.permute(0, 2, 1).view(B, 2048, 8, 8)        # exactly what the sampler passes (imggen_model.py:254)
+    img, pre, hs = G(emb, train=False, return_intermediates=True)
+    assert img.shape == (B, 3, 256, 256)
+    for i, h in enumerate(hs):
+        s = max(1, h.shape[-1] // 16)
+        e = rel_err(h[:, :, ::s, ::s].cpu(), g[f"h{i}_sub"])
+        assert e < 1e-3, (i, e)
+        assert abs(float(h.abs().mean()) - float(g[f"h{i}_absmean"])) < 1e-3 * float(g[f"h{i}_absmean"])
+    assert rel_err(pre[:, :, ::4, ::4].cpu(), g["pre_tanh_sub"]) < 1e-3
+    assert float((img[:, :, ::4, ::4].cpu() - torch.from_numpy(g["img_sub"])).abs().max()) < 1e-3
+    assert abs(float(img.mean()) - float(g["img_mean"])) < 1e-4
+    # the golden is not a vacuous target: most pixels are away from tanh saturation
+    assert float(g["saturated_frac"]) < 0.5
+
+
+def test_generator_input_layouts_and_noise_flag_agree():
+    g, G, code, B = _setup()
+    a = G(code.permute(0, 2, 1).view(B, 2048, 8, 8), train=False)
+    b = G(code.view(B, 8, 8, 2048), train=False)            # layers.py:231-233 accepts cell-major input too
+    c = G(code.permute(0, 2, 1).view(B, 2048, 8, 8).contiguous(), train=True)   # noise weights are 0 ⇒ identical
+    assert torch.equal(a, b) and torch.equal(a, c)
+    for rb in G.resblocks:                                   # a trained G has non-zero noise weights
+        rb.noise1.weight.data.fill_(0.05)
+    d = G(code.view(B, 8, 8, 2048), train=True)
+    assert not torch.equal(a, d) and float((a - d).abs().max()) < 1.0
+    assert torch.equal(a, G(code.view(B, 8, 8, 2048), train=False))
+
+
+def test_generator_rejects_other_architectures_and_cpu():
+    from xlxmert_b200.generator import B200Generator
+    with pytest.raises(NotImplementedError):
+        B200Generator(base_dim=64)
+    G = B200Generator()
+    with pytest.raises(RuntimeError):
+        G(torch.zeros(1, 2048, 8, 8))

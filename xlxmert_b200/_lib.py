@@ -91,6 +91,15 @@ def _sig(lib):
     lib.xlx_visual_input_fwd.argtypes = [P, P, P, P, I32, I32, P, P]
     lib.xlx_visual_input_bwd.restype = I32
     lib.xlx_visual_input_bwd.argtypes = [P, P, I32, I32, P, P, P]
+    lib.xlx_generator_num_params.restype = I64
+    lib.xlx_generator_launch_count.restype = I64
+    lib.xlx_generator_prep_bytes.restype = SZ
+    lib.xlx_generator_workspace_bytes.restype = SZ
+    lib.xlx_generator_workspace_bytes.argtypes = [I32]
+    lib.xlx_generator_prepare.restype = I32
+    lib.xlx_generator_prepare.argtypes = [P, P, P]
+    lib.xlx_generator_fwd.restype = I32
+    lib.xlx_generator_fwd.argtypes = [P, P, I32, P, P, P, P, P, P, SZ, I32, P]
     lib.xlx_matchhead_scratch_floats.restype = I64
     lib.xlx_matchhead_scratch_floats.argtypes = [I32]
     lib.xlx_matchhead_fwd.restype = I32

@@ -468,6 +468,7 @@ const char* xlx_strerror(int32_t code) {
     case -3: return "GEMM tile does not fit shared memory";
     case -4: return "unsupported hidden size for LayerNorm (128/256/512/768/1024)";
     case -5: return "attention sequence length out of range (1..64)";
+    case -6: return "unsupported convolution geometry for the implicit-GEMM path";
     case -10: return "cuTensorMapEncodeTiled unavailable (driver too old?)";
     case -11: return "cuTensorMapEncodeTiled failed";
     case -20: return "unsupported xlx_dims";
@@ -479,7 +480,7 @@ const char* xlx_strerror(int32_t code) {
   }
 }
 
-int64_t xlx_launch_count(void) { return gemm_launch_count() + aux_launch_count(); }
+int64_t xlx_launch_count(void) { return gemm_launch_count() + aux_launch_count() + xlx_generator_launch_count(); }
 int64_t xlx_gemm_launch_count(void) { return gemm_launch_count(); }
 void xlx_profile_gemm_begin(void) { gemm_timing_begin(); }
 int32_t xlx_profile_gemm_end(double* total_ms, double* total_flops, int64_t* launches) {

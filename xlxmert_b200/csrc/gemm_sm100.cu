@@ -38,6 +38,7 @@ struct KParams {
   int splits;          // split-K factor (1 = none); work item = (tile, split)
   int kb_per_split;    // k-blocks per split (last split may be shorter)
   float* part;         // [splits][M][N] fp32 partial sums when splits > 1
+  int conv, conv_H, conv_W, conv_taps, conv_kb_per_tap;   // implicit-GEMM convolution (see ConvGeometry)
   GemmEpilogue epi;
 };
 
@@ -77,6 +78,10 @@ __device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = tanhf(v[j]);
   }
+  if (E.flags & EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
   if (E.flags & EPI_GELU_GRAD) {
     const float4 u = __ldg(reinterpret_cast<const float4*>(E.u_in + static_cast<size_t>(row) * E.ld_u + n));
     v[0] *= gelu_erf_grad(u.x); v[1] *= gelu_erf_grad(u.y); v[2] *= gelu_erf_grad(u.z); v[3] *= gelu_erf_grad(u.w);
@@ -100,12 +105,11 @@ __device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, 
   }
   if (E.out_f32) {
     float4* dst = reinterpret_cast<float4*>(E.out_f32 + static_cast<size_t>(row) * E.ld_out + n);
-    float4 o = make_float4(v[0], v[1], v[2], v[3]);
     if (E.flags & EPI_ACCUM) {
       const float4 old = *dst;
-      o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      v[0] += old.x; v[1] += old.y; v[2] += old.z; v[3] += old.w;
     }
-    *dst = o;
+    *dst = make_float4(v[0], v[1], v[2], v[3]);
   }
   if (E.out_hi) {
     const size_t idx = static_cast<size_t>(row) * E.ld_split + n;
@@ -186,7 +190,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
             const CUtensorMap* mb = part ? &mapBlo : &mapBhi;
             const uint32_t dA = sA + part * P.a_part_bytes;
             const uint32_t dB = sB + part * P.b_part_bytes;
-            if (!P.a_mn) {
+            if (P.conv) {
+              // tile → (image, y, x) of its first pixel; k-block → (tap, channel offset)
+              const int hw = P.conv_H * P.conv_W;
+              const int img = m0 / hw, rem = m0 % hw;
+              const int y0 = rem / P.conv_W, x0 = rem % P.conv_W;
+              const int tap = kb / P.conv_kb_per_tap, c0 = (kb % P.conv_kb_per_tap) * BK;
+              const int dy = P.conv_taps == 9 ? tap / 3 - 1 : 0, dx = P.conv_taps == 9 ? tap % 3 - 1 : 0;
+              tma_load_4d(dA, ma, full, c0, x0 + dx, y0 + dy, img);
+            } else if (!P.a_mn) {
               tma_load_2d(dA, ma, full, k0, m0);
             } else {
               for (int j = 0; j < BM / 64; ++j) tma_load_2d(dA + j * (BK * 128), ma, full, m0 + 64 * j, k0);
@@ -420,6 +432,52 @@ int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, 
   return 0;
 }
 
+// NHWC bf16 tensor [B, H, W, C] as a rank-4 tensor map (C innermost) with box (bc, bw, bh, bb).
+struct Map4Key {
+  const void* ptr;
+  int B, H, W, C, bc, bw, bh, bb;
+  bool operator==(const Map4Key& o) const {
+    return ptr == o.ptr && B == o.B && H == o.H && W == o.W && C == o.C && bc == o.bc && bw == o.bw && bh == o.bh &&
+           bb == o.bb;
+  }
+};
+struct Map4KeyHash {
+  size_t operator()(const Map4Key& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.B); mix(k.H); mix(k.W); mix(k.C); mix(k.bc); mix(k.bw); mix(k.bh); mix(k.bb);
+    return h;
+  }
+};
+std::unordered_map<Map4Key, CUtensorMap, Map4KeyHash> g_maps4;
+
+int make_map4(CUtensorMap* out, const void* ptr, int B, int H, int W, int C, int bc, int bw, int bh, int bb,
+              CUtensorMapSwizzle swz) {
+  Map4Key key{ptr, B, H, W, C, bc, bw, bh, bb};
+  {
+    std::lock_guard<std::mutex> g(g_maps_mu);
+    auto it = g_maps4.find(key);
+    if (it != g_maps4.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -10;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t gstride[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(bc), static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh),
+                       static_cast<cuuint32_t>(bb)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return -11;
+  std::lock_guard<std::mutex> g(g_maps_mu);
+  if (g_maps4.size() > 4096) g_maps4.clear();
+  g_maps4.emplace(key, *out);
+  return 0;
+}
+
 int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
@@ -472,14 +530,36 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   };
   int rc;
   const int a_rows = p.a.rows ? p.a.rows : p.M, b_rows = p.b.rows ? p.b.rows : p.N;
-  if ((rc = mk(&mAhi, p.a, p.a.hi, a_rows, BM))) return rc;
-  if ((rc = mk(&mBhi, p.b, p.b.hi, b_rows, BN))) return rc;
-  if (P.nparts == 2) {
-    if ((rc = mk(&mAlo, p.a, p.a.lo, a_rows, BM))) return rc;
-    if ((rc = mk(&mBlo, p.b, p.b.lo, b_rows, BN))) return rc;
+  P.conv = 0;
+  if (p.conv.enabled) {
+    const ConvGeometry& g = p.conv;
+    const int hw = g.H * g.W;
+    if (g.H < 1 || g.W < 1 || (g.taps != 9 && g.taps != 1) || g.C % BK || p.K != g.taps * g.C || p.M % hw ||
+        p.a.mn_major)
+      return -6;
+    int bw, bh, bb;
+    if (hw >= BM) {
+      if (hw % BM) return -6;
+      if (g.W >= BM) { if (g.W % BM) return -6; bw = BM; bh = 1; }
+      else { if (BM % g.W) return -6; bw = g.W; bh = BM / g.W; }
+      bb = 1;
+    } else {
+      if (BM % hw) return -6;
+      bw = g.W; bh = g.H; bb = BM / hw;
+    }
+    const int nimg = p.M / hw;
+    if ((rc = make_map4(&mAhi, p.a.hi, nimg, g.H, g.W, g.C, BK, bw, bh, bb, swzK))) return rc;
+    if (P.nparts == 2) { if ((rc = make_map4(&mAlo, p.a.lo, nimg, g.H, g.W, g.C, BK, bw, bh, bb, swzK))) return rc; }
+    else mAlo = mAhi;
+    P.conv = 1; P.conv_H = g.H; P.conv_W = g.W; P.conv_taps = g.taps; P.conv_kb_per_tap = g.C / BK;
   } else {
-    mAlo = mAhi; mBlo = mBhi;
+    if ((rc = mk(&mAhi, p.a, p.a.hi, a_rows, BM))) return rc;
+    if (P.nparts == 2) { if ((rc = mk(&mAlo, p.a, p.a.lo, a_rows, BM))) return rc; }
+    else mAlo = mAhi;
   }
+  if ((rc = mk(&mBhi, p.b, p.b.hi, b_rows, BN))) return rc;
+  if (P.nparts == 2) { if ((rc = mk(&mBlo, p.b, p.b.lo, b_rows, BN))) return rc; }
+  else mBlo = mBhi;
   const int num_tiles = P.tiles_m * P.tiles_n;
   const int nkb = (p.K + BK - 1) / BK;
   // split-K: only for plain fp32-output GEMMs (weight gradients) whose tile count leaves most SMs idle
@@ -576,7 +656,7 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream) {
   if (p.passes != 1 && p.passes != 3) return -1;
   if (!p.a.hi || !p.b.hi) return -1;
   if (p.passes == 3 && (!p.a.lo || !p.b.lo)) return -1;
-  if ((p.a.ld % 8) || (p.b.ld % 8) || (p.N % 4)) return -2;  // TMA: 16-byte global strides; epilogue: 4-column vectors
+  if ((!p.conv.enabled && (p.a.ld % 8)) || (p.b.ld % 8) || (p.N % 4)) return -2;  // TMA: 16-byte global strides; epilogue: 4-column vectors
   if ((reinterpret_cast<uintptr_t>(p.a.hi) | reinterpret_cast<uintptr_t>(p.b.hi) |
        reinterpret_cast<uintptr_t>(p.a.lo) | reinterpret_cast<uintptr_t>(p.b.lo)) & 15)
     return -2;

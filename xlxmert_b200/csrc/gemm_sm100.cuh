@@ -29,6 +29,7 @@ enum EpiFlags : int {
   EPI_TANH = 8,        // v = tanh(v) after bias
   EPI_SAVE_DGELU = 16, // with EPI_GELU: out_u receives gelu'(pre-activation) instead of the pre-activation
   EPI_MUL = 32,        // v *= u_in[m,n]  (backward of an activation whose derivative was saved by the forward)
+  EPI_RELU = 64,       // v = max(v, 0) after bias
 };
 
 struct GemmEpilogue {
@@ -55,9 +56,20 @@ struct GemmOperand {
   int kext = 0;                        // extent along K that exists in memory (0 → K); zero-filled beyond
 };
 
+// Implicit-GEMM convolution: A is not a matrix but an NHWC activation tensor [B, H, W, C] (split bf16, a.hi/a.lo);
+// GEMM row m = flat pixel index (b·H + y)·W + x, GEMM column k = tap·C + c with tap = ky·3 + kx (taps = 9, zero
+// padding 1) or the pixel itself (taps = 1).  M = B·H·W, K = taps·C.  Each k-block is one TMA box of the tensor
+// shifted by the tap offset, out-of-bounds zero-filled by the TMA unit — no im2col buffer exists anywhere.
+// Constraints: C % 32 == 0, and H·W either divides 128 or is a multiple of 128 with W dividing 128 or a multiple.
+struct ConvGeometry {
+  int enabled = 0;
+  int H = 0, W = 0, C = 0, taps = 9;
+};
+
 struct GemmProblem {
   int M = 0, N = 0, K = 0;
   GemmOperand a, b;
+  ConvGeometry conv;
   int passes = 3;
   GemmEpilogue epi;
   // Optional split-K scratch (fp32).  When given, GEMMs with a plain fp32 epilogue whose output has too few

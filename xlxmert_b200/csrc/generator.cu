@@ -1,0 +1,501 @@
+// Grid-feature GAN generator forward (image_generator/src/layers.py:135-253, canonical configuration of
+// scripts/train_generator.bash + x-lxmert/src/tasks/sample_images.py:53-67: base_dim 32, emb_dim 2048,
+// codebook_dim 256, 8×8 → 256×256, SPADE + InstanceNorm, spectral norm) on sm_100a.
+//
+// Layout: every activation is NHWC ("pixel-major": [B, H, W, C], C innermost) so that a convolution is an implicit
+// GEMM whose A operand the TMA unit reads straight from the activation tensor, one shifted box per filter tap
+// (gemm_sm100.cuh, ConvGeometry) — there is no im2col buffer.  Convolution inputs are stored as split-bf16 pairs,
+// their fp32 outputs feed the normalisation kernels below.  The 128-channel SPADE hidden map never exists in fp32.
+//
+// Kernels in this file are the memory-bound glue between the tensor-core convolutions: instance-norm statistics,
+// SPADE modulation + LeakyReLU (+ fused bilinear ×2), bilinear resampling of the style map, ToRGB accumulation.
+#include <math.h>
+
+#include <atomic>
+
+#include "../../include/xlxmert_b200.h"
+#include "host_util.cuh"
+#include "xlx_ptx.cuh"
+
+using namespace xlx;
+
+namespace {
+
+constexpr int CH = 32;          // width of every block (resolution_channels = min(·, base_dim), layers.py:161-175)
+constexpr int HID = 128;        // SPADE hidden width (layers.py:23)
+constexpr int EMB = 2048, CODE = 256, NBLK = 5, R0 = 8, RGB_LD = 16;
+constexpr int N_PARAMS = 10 + NBLK * 26 + NBLK * 2;
+
+std::atomic<long long> g_gen_launches{0};
+inline int krc() {
+  g_gen_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+__device__ __forceinline__ void store_split(bf16* hi, bf16* lo, size_t idx, float4 v) {
+  bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+  split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+  *reinterpret_cast<uint2*>(hi + idx) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+  *reinterpret_cast<uint2*>(lo + idx) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+}
+
+// PyTorch upsample_bilinear2d, align_corners=False: source index and weights for output index o.
+__device__ __forceinline__ void bilinear_src(int o, float scale, int in, int& i0, int& i1, float& l0, float& l1) {
+  float src = scale * (static_cast<float>(o) + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = static_cast<int>(src);
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l1 = src - static_cast<float>(i0);
+  l0 = 1.f - l1;
+}
+
+// ---- weight preparation ---------------------------------------------------------------------------
+// 1/σ of a spectrally normalised conv in eval mode: σ = uᵀ·(W_mat·v) with the stored u, v (torch.nn.utils
+// spectral_norm, compute_weight with do_power_iteration=False).  One CTA.
+__global__ void sigma_inv_kernel(const float* __restrict__ w, const float* __restrict__ u, const float* __restrict__ v,
+                                 int rows, int cols, float* out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int r = threadIdx.x >> 5; r < rows; r += blockDim.x >> 5) {
+    float d = 0.f;
+    for (int c = threadIdx.x & 31; c < cols; c += 32) d += w[static_cast<size_t>(r) * cols + c] * v[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if ((threadIdx.x & 31) == 0) acc += u[r] * d;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) s += red[i];
+    *out = 1.0f / s;
+  }
+}
+// w [Co, Ci, kh, kw] (torch conv layout) → dst[(row0 + co) * ld + tap * ctot + col0 + ci], tap = ky * kw + kx,
+// scaled by *scale (nullable), as split bf16.  For grouped convs col0 is chosen per output channel:
+// col0 = (co / co_per_group) * Ci.
+__global__ void prep_conv_kernel(const float* __restrict__ w, const float* __restrict__ scale, int Co, int Ci, int taps,
+                                 int ctot, int co_per_group, int row0, int ld, bf16* hi, bf16* lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Co * Ci * taps) return;
+  const int tap = i % taps, ci = (i / taps) % Ci, co = i / (taps * Ci);
+  const int col0 = co_per_group ? (co / co_per_group) * Ci : 0;
+  const float v = w[i] * (scale ? *scale : 1.0f);
+  bf16 h, l;
+  split_bf16(v, h, l);
+  const size_t d = static_cast<size_t>(row0 + co) * ld + static_cast<size_t>(tap) * ctot + col0 + ci;
+  hi[d] = h; lo[d] = l;
+}
+__global__ void concat_bias_kernel(const float* a, int na, const float* b, int nb, float* dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = i < na ? a[i] : (i < na + nb ? b[i - na] : 0.f);
+}
+
+// ---- instance-norm statistics -----------------------------------------------------------------------
+// x: [B, HW, ld] fp32 (first CH channels used).  acc[b][c][0..1] += (Σx, Σx²) in fp64.  grid (chunks, B), 256 thr.
+__global__ void __launch_bounds__(256)
+in_stats_kernel(const float* __restrict__ x, int ld, int HW, double* acc) {
+  __shared__ double s1[8][CH], s2[8][CH];
+  const int c = threadIdx.x & 31, lane = threadIdx.x >> 5, b = blockIdx.y;
+  const float* xb = x + static_cast<size_t>(b) * HW * ld;
+  double a1 = 0.0, a2 = 0.0;
+  for (int p = blockIdx.x * 8 + lane; p < HW; p += gridDim.x * 8) {
+    const double v = static_cast<double>(__ldg(xb + static_cast<size_t>(p) * ld + c));
+    a1 += v; a2 += v * v;
+  }
+  s1[lane][c] = a1; s2[lane][c] = a2;
+  __syncthreads();
+  if (lane == 0) {
+    for (int i = 1; i < 8; ++i) { a1 += s1[i][c]; a2 += s2[i][c]; }
+    atomicAdd(acc + (static_cast<size_t>(b) * CH + c) * 2, a1);
+    atomicAdd(acc + (static_cast<size_t>(b) * CH + c) * 2 + 1, a2);
+  }
+}
+// InstanceNorm2d(affine=False): biased variance over H×W, eps 1e-5 (layers.py:16)
+__global__ void in_finish_kernel(const double* __restrict__ acc, int n, int HW, float* mean, float* rstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double m = acc[2 * i] / HW;
+  double var = acc[2 * i + 1] / HW - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = static_cast<float>(m);
+  rstd[i] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+}
+
+// ---- resampling / modulation --------------------------------------------------------------------------
+// Bilinear resize of a CH-channel NHWC map [B, Hi, Hi, ld] → split [B, Ho, Ho, CH].  One thread = 4 channels of a pixel.
+__global__ void resize_split_kernel(const float* __restrict__ x, int ld, int Hi, int Ho, size_t npix, bf16* hi, bf16* lo) {
+  const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (t >= npix * (CH / 4)) return;
+  const int c4 = t % (CH / 4);
+  const size_t p = t / (CH / 4);
+  const int ox = p % Ho, oy = (p / Ho) % Ho;
+  const size_t b = p / (static_cast<size_t>(Ho) * Ho);
+  const float scale = static_cast<float>(Hi) / static_cast<float>(Ho);
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  bilinear_src(oy, scale, Hi, y0, y1, ly0, ly1);
+  bilinear_src(ox, scale, Hi, x0, x1, lx0, lx1);
+  const float* xb = x + b * Hi * Hi * ld + c4 * 4;
+  const float4 v00 = __ldg(reinterpret_cast<const float4*>(xb + (static_cast<size_t>(y0) * Hi + x0) * ld));
+  const float4 v01 = __ldg(reinterpret_cast<const float4*>(xb + (static_cast<size_t>(y0) * Hi + x1) * ld));
+  const float4 v10 = __ldg(reinterpret_cast<const float4*>(xb + (static_cast<size_t>(y1) * Hi + x0) * ld));
+  const float4 v11 = __ldg(reinterpret_cast<const float4*>(xb + (static_cast<size_t>(y1) * Hi + x1) * ld));
+  float4 o;
+  o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+  o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+  o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+  o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+  store_split(hi, lo, p * CH + c4 * 4, o);
+}
+
+// SPADE modulation + noise + LeakyReLU(0.2) at one source pixel (layers.py:33-47, 56-62, 97-100):
+//   t = ((x − mean)·rstd)·(1 + γ) + β  (+ w·noise);  t = t > 0 ? t : 0.2·t
+__device__ __forceinline__ float4 spade_pixel(const float* __restrict__ x, int ldx, const float* __restrict__ gb,
+                                              size_t pix, int c4, float4 mu, float4 rs, const float* noise, float nw) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(x + pix * ldx + c4 * 4));
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gb + pix * (2 * CH) + c4 * 4));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(gb + pix * (2 * CH) + CH + c4 * 4));
+  const float nz = noise ? nw * __ldg(noise + pix) : 0.f;
+  float4 t;
+  t.x = ((v.x - mu.x) * rs.x) * (1.f + g.x) + b.x + nz;
+  t.y = ((v.y - mu.y) * rs.y) * (1.f + g.y) + b.y + nz;
+  t.z = ((v.z - mu.z) * rs.z) * (1.f + g.z) + b.z + nz;
+  t.w = ((v.w - mu.w) * rs.w) * (1.f + g.w) + b.w + nz;
+  t.x = t.x > 0.f ? t.x : 0.2f * t.x; t.y = t.y > 0.f ? t.y : 0.2f * t.y;
+  t.z = t.z > 0.f ? t.z : 0.2f * t.z; t.w = t.w > 0.f ? t.w : 0.2f * t.w;
+  return t;
+}
+// out[B, up·R, up·R, CH] (split) = bilinear_up( lrelu(spade(x)) ), up ∈ {1, 2}.  With gb == nullptr the modulation is
+// skipped and the kernel is a plain ×up bilinear resize of x (the residual branch, layers.py:88-91).
+__global__ void spade_act_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mean,
+                                 const float* __restrict__ rstd, const float* __restrict__ gb,
+                                 const float* __restrict__ noise, const float* __restrict__ noise_w, int R, int up,
+                                 size_t npix_out, bf16* hi, bf16* lo) {
+  const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (t >= npix_out * (CH / 4)) return;
+  const int c4 = t % (CH / 4);
+  const size_t p = t / (CH / 4);
+  const int Ro = R * up;
+  const int ox = p % Ro, oy = (p / Ro) % Ro;
+  const size_t b = p / (static_cast<size_t>(Ro) * Ro);
+  float4 mu = make_float4(0, 0, 0, 0), rs = make_float4(1, 1, 1, 1);
+  if (gb) {
+    mu = __ldg(reinterpret_cast<const float4*>(mean + b * CH + c4 * 4));
+    rs = __ldg(reinterpret_cast<const float4*>(rstd + b * CH + c4 * 4));
+  }
+  const float nw = (noise && noise_w) ? __ldg(noise_w) : 0.f;
+  const size_t base = b * R * R;
+  auto fetch = [&](int y, int xx) -> float4 {
+    const size_t pix = base + static_cast<size_t>(y) * R + xx;
+    if (gb) return spade_pixel(x, ldx, gb, pix, c4, mu, rs, noise, nw);
+    return __ldg(reinterpret_cast<const float4*>(x + pix * ldx + c4 * 4));
+  };
+  float4 o;
+  if (up == 1) {
+    o = fetch(oy, ox);
+  } else {
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    bilinear_src(oy, 0.5f, R, y0, y1, ly0, ly1);
+    bilinear_src(ox, 0.5f, R, x0, x1, lx0, lx1);
+    const float4 v00 = fetch(y0, x0), v01 = fetch(y0, x1), v10 = fetch(y1, x0), v11 = fetch(y1, x1);
+    o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+    o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+    o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+    o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+  }
+  store_split(hi, lo, p * CH + c4 * 4, o);
+}
+
+// ToRGB tail (layers.py:126-132, 241-251): img[b, c, :, :] (+)= bilinear(rgb[b, :, :, c] → T×T); the last block
+// applies tanh and optionally exports the pre-tanh sum.  rgb: [B, r, r, RGB_LD] fp32; img NCHW [B, 3, T, T].
+__global__ void rgb_accumulate_kernel(const float* __restrict__ rgb, int r, int T, size_t n, int first, int last,
+                                      float* acc, float* img, float* pre_tanh) {
+  const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (t >= n) return;
+  const int ox = t % T, oy = (t / T) % T, c = (t / (static_cast<size_t>(T) * T)) % 3;
+  const size_t b = t / (static_cast<size_t>(T) * T * 3);
+  const float* rb = rgb + b * r * r * RGB_LD + c;
+  float v;
+  if (r == T) {
+    v = __ldg(rb + (static_cast<size_t>(oy) * r + ox) * RGB_LD);
+  } else {
+    const float scale = static_cast<float>(r) / static_cast<float>(T);
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    bilinear_src(oy, scale, r, y0, y1, ly0, ly1);
+    bilinear_src(ox, scale, r, x0, x1, lx0, lx1);
+    const float v00 = __ldg(rb + (static_cast<size_t>(y0) * r + x0) * RGB_LD);
+    const float v01 = __ldg(rb + (static_cast<size_t>(y0) * r + x1) * RGB_LD);
+    const float v10 = __ldg(rb + (static_cast<size_t>(y1) * r + x0) * RGB_LD);
+    const float v11 = __ldg(rb + (static_cast<size_t>(y1) * r + x1) * RGB_LD);
+    v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+  }
+  const float s = first ? v : acc[t] + v;      // out = zeros + rgb_0 + rgb_1 + … in block order
+  if (last) {
+    if (pre_tanh) pre_tanh[t] = s;
+    img[t] = tanhf(s);
+  } else {
+    acc[t] = s;
+  }
+}
+
+// ---- parameter slots ----------------------------------------------------------------------------------
+// 0,1 bottleneck_emb.0.{weight,bias}; 2-5 learned_init_conv.0.{weight_orig,bias,weight_u,weight_v};
+// 6-9 style_init_conv.0.{…}; block i at 10 + 26·i: cbn1.{shared.0,gamma,beta}.{weight,bias} (6), cbn2.… (6),
+// conv1.{weight_orig,bias,weight_u,weight_v}, conv2.{…}, res_branch.1.{…} (12), noise1.weight, noise2.weight (2);
+// to_RGB_blocks.i.conv.{weight,bias} at 140 + 2·i.
+inline int blk(int i) { return 10 + 26 * i; }
+inline int rgb_slot(int i) { return 10 + 26 * NBLK + 2 * i; }
+
+struct SpadeW { Split shared, gb; float* gb_bias; };
+struct Prep {
+  Split bott, init;          // [256, 2048]; [64, 9·256] (rows 0-31 learned_init, 32-63 style_init)
+  float* init_bias;          // [64]
+  SpadeW sp[NBLK][2];
+  Split conv1[NBLK], conv2[NBLK], res[NBLK], rgb[NBLK];   // [64(pad), 288], [64, 288], [64, 32], [64, 288]
+  float* sig;                // 1/σ per spectrally normalised conv: 2 + 3·NBLK
+  float* rgb_bias[NBLK];     // [RGB_LD]
+  size_t bytes;
+};
+Prep prep_layout(void* base) {
+  Bump b; b.base = static_cast<char*>(base);
+  Prep p;
+  p.bott = b.split(static_cast<size_t>(CODE) * EMB);
+  p.init = b.split(static_cast<size_t>(64) * 9 * CODE);
+  p.init_bias = b.f32(64);
+  for (int i = 0; i < NBLK; ++i) {
+    for (int j = 0; j < 2; ++j) {
+      p.sp[i][j].shared = b.split(static_cast<size_t>(HID) * 9 * CH);
+      p.sp[i][j].gb = b.split(static_cast<size_t>(2 * CH) * 9 * HID);
+      p.sp[i][j].gb_bias = b.f32(2 * CH);
+    }
+    p.conv1[i] = b.split(static_cast<size_t>(64) * 9 * CH);
+    p.conv2[i] = b.split(static_cast<size_t>(64) * 9 * CH);
+    p.res[i] = b.split(static_cast<size_t>(64) * CH);
+    p.rgb[i] = b.split(static_cast<size_t>(64) * 9 * CH);
+    p.rgb_bias[i] = b.f32(RGB_LD);
+  }
+  p.sig = b.f32(2 + 3 * NBLK);
+  p.bytes = b.total();
+  return p;
+}
+
+struct Ws {
+  Split emb, code, yup[NBLK + 1], actv, a, xu, os;
+  float *hy, *gb, *h1, *of[2], *rgb, *acc, *mean, *rstd;
+  double* stat;
+  size_t bytes;
+};
+Ws ws_layout(int B, void* base) {
+  Bump b; b.base = static_cast<char*>(base);
+  Ws w;
+  const size_t n = B, top = static_cast<size_t>(256) * 256;
+  w.emb = b.split(n * 64 * EMB);
+  w.code = b.split(n * 64 * CODE);
+  w.hy = b.f32(n * 64 * 64);
+  for (int i = 0; i <= NBLK; ++i) w.yup[i] = b.split(n * (static_cast<size_t>(R0 << i) * (R0 << i)) * CH);
+  w.actv = b.split(n * top * HID);
+  w.gb = b.f32(n * top * 2 * CH);
+  w.a = b.split(n * top * CH);
+  w.xu = b.split(n * top * CH);
+  w.os = b.split(n * top * CH);
+  w.h1 = b.f32(n * top * CH);
+  w.of[0] = b.f32(n * top * CH);
+  w.of[1] = b.f32(n * top / 4 * CH);
+  w.rgb = b.f32(n * top * RGB_LD);
+  w.acc = b.f32(n * 3 * top);
+  w.mean = b.f32(n * CH);
+  w.rstd = b.f32(n * CH);
+  w.stat = static_cast<double*>(b.take(n * CH * 2 * sizeof(double)));
+  w.bytes = b.total();
+  return w;
+}
+
+// conv as implicit GEMM over an NHWC split tensor: out[B·R², N] = conv_{taps}(in[B,R,R,C]) · Wᵀ (+ epilogue)
+int conv(int passes, cudaStream_t st, Split in, int B, int R, int C, int taps, Split w, int w_rows, int N,
+         const GemmEpilogue& e) {
+  GemmProblem p;
+  p.M = B * R * R; p.N = N; p.K = taps * C; p.passes = passes;
+  p.a.hi = in.hi; p.a.lo = in.lo; p.a.ld = C;
+  p.conv.enabled = 1; p.conv.H = R; p.conv.W = R; p.conv.C = C; p.conv.taps = taps;
+  p.b.hi = w.hi; p.b.lo = w.lo; p.b.ld = taps * C; p.b.mn_major = 0; p.b.rows = w_rows;
+  p.epi = e;
+  return gemm_launch(p, st);
+}
+
+int instance_stats(const float* x, int ld, int B, int HW, const Ws& w, cudaStream_t st) {
+  XLX_CUDA(cudaMemsetAsync(w.stat, 0, static_cast<size_t>(B) * CH * 2 * sizeof(double), st));
+  int chunks = (HW + 255) / 256;
+  if (chunks > 64) chunks = 64;
+  in_stats_kernel<<<dim3(chunks, B), 256, 0, st>>>(x, ld, HW, w.stat);
+  XLX_TRY(krc());
+  in_finish_kernel<<<(B * CH + 255) / 256, 256, 0, st>>>(w.stat, B * CH, HW, w.mean, w.rstd);
+  return krc();
+}
+
+inline unsigned blocks_for(size_t n) { return static_cast<unsigned>((n + 255) / 256); }
+
+}  // namespace
+
+extern "C" {
+
+int64_t xlx_generator_launch_count(void) { return g_gen_launches.load(); }
+int64_t xlx_generator_num_params(void) { return N_PARAMS; }
+size_t xlx_generator_prep_bytes(void) { return prep_layout(nullptr).bytes; }
+size_t xlx_generator_workspace_bytes(int32_t B) { return B > 0 ? ws_layout(B, nullptr).bytes : 0; }
+
+int32_t xlx_generator_prepare(const float* const* P, void* prep, void* stream) {
+  if (!P || !prep) return -24;
+  XLX_TRY(ensure_device(prep));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Prep p = prep_layout(prep);
+  XLX_CUDA(cudaMemsetAsync(prep, 0, p.bytes - 256, st));     // padded rows / off-group blocks stay zero
+  auto prep_w = [&](const float* w, const float* scale, int Co, int Ci, int taps, int ctot, int cpg, int row0,
+                    Split dst) -> int {
+    const int n = Co * Ci * taps;
+    prep_conv_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, scale, Co, Ci, taps, ctot, cpg, row0, taps * ctot, dst.hi, dst.lo);
+    return krc();
+  };
+  auto sigma = [&](int slot, int rows, int cols, float* out) -> int {
+    sigma_inv_kernel<<<1, 256, 0, st>>>(P[slot], P[slot + 2], P[slot + 3], rows, cols, out);
+    return krc();
+  };
+  XLX_TRY(prep_w(P[0], nullptr, CODE, EMB, 1, EMB, 0, 0, p.bott));
+  // grouped init convs (groups = 4, layers.py:178-185): 8 output channels per group see 64 input channels
+  XLX_TRY(sigma(2, CH, (CODE / 4) * 9, p.sig + 0));
+  XLX_TRY(sigma(6, CH, (CODE / 4) * 9, p.sig + 1));
+  XLX_TRY(prep_w(P[2], p.sig + 0, CH, CODE / 4, 9, CODE, CH / 4, 0, p.init));
+  XLX_TRY(prep_w(P[6], p.sig + 1, CH, CODE / 4, 9, CODE, CH / 4, CH, p.init));
+  concat_bias_kernel<<<1, 64, 0, st>>>(P[3], CH, P[7], CH, p.init_bias, 64);
+  XLX_TRY(krc());
+  for (int i = 0; i < NBLK; ++i) {
+    const int s = blk(i);
+    for (int j = 0; j < 2; ++j) {
+      const int q = s + 6 * j;
+      XLX_TRY(prep_w(P[q], nullptr, HID, CH, 9, CH, 0, 0, p.sp[i][j].shared));
+      XLX_TRY(prep_w(P[q + 2], nullptr, CH, HID, 9, HID, 0, 0, p.sp[i][j].gb));       // γ rows 0-31
+      XLX_TRY(prep_w(P[q + 4], nullptr, CH, HID, 9, HID, 0, CH, p.sp[i][j].gb));      // β rows 32-63
+      concat_bias_kernel<<<1, 64, 0, st>>>(P[q + 3], CH, P[q + 5], CH, p.sp[i][j].gb_bias, 2 * CH);
+      XLX_TRY(krc());
+    }
+    float* sg = p.sig + 2 + 3 * i;
+    XLX_TRY(sigma(s + 12, CH, CH * 9, sg + 0));
+    XLX_TRY(sigma(s + 16, CH, CH * 9, sg + 1));
+    XLX_TRY(sigma(s + 20, CH, CH, sg + 2));
+    XLX_TRY(prep_w(P[s + 12], sg + 0, CH, CH, 9, CH, 0, 0, p.conv1[i]));
+    XLX_TRY(prep_w(P[s + 16], sg + 1, CH, CH, 9, CH, 0, 0, p.conv2[i]));
+    XLX_TRY(prep_w(P[s + 20], sg + 2, CH, CH, 1, CH, 0, 0, p.res[i]));
+    XLX_TRY(prep_w(P[rgb_slot(i)], nullptr, 3, CH, 9, CH, 0, 0, p.rgb[i]));
+    concat_bias_kernel<<<1, 64, 0, st>>>(P[rgb_slot(i) + 1], 3, nullptr, 0, p.rgb_bias[i], RGB_LD);
+    XLX_TRY(krc());
+  }
+  return 0;
+}
+
+int32_t xlx_generator_fwd(const float* const* P, const void* prep, int32_t B, const float* emb,
+                          const float* const* noise, float* img, float* pre_tanh, float* const* block_out,
+                          void* workspace, size_t workspace_bytes, int32_t passes, void* stream) {
+  if (B < 1) return -21;
+  if (!P || !prep || !emb || !img || !workspace) return -24;
+  if (passes != 1 && passes != 3) return -1;
+  XLX_TRY(ensure_device(workspace));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Prep p = prep_layout(const_cast<void*>(prep));
+  Ws w = ws_layout(B, workspace);
+  if (w.bytes > workspace_bytes) return -23;
+  const int M0 = B * R0 * R0;
+
+  // bottleneck_emb: 1×1 conv 2048 → 256 + tanh (layers.py:147-150) = GEMM over the B·64 grid cells
+  XLX_TRY(split_f32(emb, w.emb, static_cast<size_t>(M0) * EMB, st));
+  {
+    GemmEpilogue e;
+    e.bias = P[1]; e.flags = EPI_TANH; e.out_hi = w.code.hi; e.out_lo = w.code.lo; e.ld_split = CODE;
+    XLX_TRY(gemm_linear(passes, st, w.emb, M0, EMB, p.bott, CODE, e));
+  }
+  // learned_init_conv | style_init_conv in one grouped 3×3 conv: hy[:, :32] = h, hy[:, 32:] = y (layers.py:238-239)
+  {
+    GemmEpilogue e;
+    e.bias = p.init_bias; e.out_f32 = w.hy; e.ld_out = 64;
+    XLX_TRY(conv(passes, st, w.code, B, R0, CODE, 9, p.init, 64, 64, e));
+  }
+  const float* y = w.hy + CH;
+  // style map resized to every resolution once (SPADE resizes y to x's size, layers.py:40)
+  for (int i = 0; i <= NBLK; ++i) {
+    const int R = R0 << i;
+    const size_t npix = static_cast<size_t>(B) * R * R;
+    resize_split_kernel<<<blocks_for(npix * (CH / 4)), 256, 0, st>>>(y, 64, R0, R, npix, w.yup[i].hi, w.yup[i].lo);
+    XLX_TRY(krc());
+  }
+  // SPADE parameter maps at resolution index ri for SPADE instance (i, j): gb = [γ | β] fp32 [B,R,R,64]
+  auto spade_params = [&](int i, int j, int ri) -> int {
+    const int R = R0 << ri;
+    GemmEpilogue e;
+    e.bias = P[blk(i) + 6 * j + 1]; e.flags = EPI_RELU; e.out_hi = w.actv.hi; e.out_lo = w.actv.lo; e.ld_split = HID;
+    XLX_TRY(conv(passes, st, w.yup[ri], B, R, CH, 9, p.sp[i][j].shared, HID, HID, e));
+    GemmEpilogue g;
+    g.bias = p.sp[i][j].gb_bias; g.out_f32 = w.gb; g.ld_out = 2 * CH;
+    return conv(passes, st, w.actv, B, R, HID, 9, p.sp[i][j].gb, 2 * CH, 2 * CH, g);
+  };
+
+  const float* x = w.hy;     // current block input, fp32 NHWC with pixel stride ldx
+  int ldx = 64;
+  for (int i = 0; i < NBLK; ++i) {
+    const int R = R0 << i, R2 = R * 2, s = blk(i);
+    const size_t npix2 = static_cast<size_t>(B) * R2 * R2;
+    const float* n1 = noise ? noise[2 * i] : nullptr;
+    const float* n2 = noise ? noise[2 * i + 1] : nullptr;
+    // cbn1 → noise1 → LeakyReLU → ×2 bilinear (layers.py:96-101)
+    XLX_TRY(instance_stats(x, ldx, B, R * R, w, st));
+    XLX_TRY(spade_params(i, 0, i));
+    spade_act_kernel<<<blocks_for(npix2 * (CH / 4)), 256, 0, st>>>(x, ldx, w.mean, w.rstd, w.gb, n1, P[s + 24], R, 2,
+                                                                   npix2, w.a.hi, w.a.lo);
+    XLX_TRY(krc());
+    // residual branch input: ×2 bilinear of x (layers.py:88-91)
+    spade_act_kernel<<<blocks_for(npix2 * (CH / 4)), 256, 0, st>>>(x, ldx, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                   R, 2, npix2, w.xu.hi, w.xu.lo);
+    XLX_TRY(krc());
+    // conv1 (spectral norm folded into the prepared weight)
+    {
+      GemmEpilogue e;
+      e.bias = P[s + 13]; e.out_f32 = w.h1; e.ld_out = CH;
+      XLX_TRY(conv(passes, st, w.a, B, R2, CH, 9, p.conv1[i], 64, CH, e));
+    }
+    // cbn2 → noise2 → LeakyReLU (layers.py:104-107)
+    XLX_TRY(instance_stats(w.h1, CH, B, R2 * R2, w, st));
+    XLX_TRY(spade_params(i, 1, i + 1));
+    spade_act_kernel<<<blocks_for(npix2 * (CH / 4)), 256, 0, st>>>(w.h1, CH, w.mean, w.rstd, w.gb, n2, P[s + 25], R2, 1,
+                                                                   npix2, w.a.hi, w.a.lo);
+    XLX_TRY(krc());
+    // conv2, then out = h + res_branch(x): the 1×1 conv accumulates onto conv2's output (layers.py:108-112)
+    // ping-pong: blocks alternate between the two buffers; the largest (last) block uses the full-size of[0]
+    float* of = ((NBLK - 1 - i) & 1) ? w.of[1] : w.of[0];
+    {
+      GemmEpilogue e;
+      e.bias = P[s + 17]; e.out_f32 = of; e.ld_out = CH;
+      XLX_TRY(conv(passes, st, w.a, B, R2, CH, 9, p.conv2[i], 64, CH, e));
+      GemmEpilogue r;
+      r.bias = P[s + 21]; r.flags = EPI_ACCUM; r.out_f32 = of; r.ld_out = CH;
+      r.out_hi = w.os.hi; r.out_lo = w.os.lo; r.ld_split = CH;
+      XLX_TRY(conv(passes, st, w.xu, B, R2, CH, 1, p.res[i], 64, CH, r));
+    }
+    if (block_out && block_out[i])
+      XLX_CUDA(cudaMemcpyAsync(block_out[i], of, npix2 * CH * 4, cudaMemcpyDeviceToDevice, st));
+    // ToRGB (layers.py:126-132) and accumulation into the image (layers.py:241-251)
+    {
+      GemmEpilogue e;
+      e.bias = p.rgb_bias[i]; e.out_f32 = w.rgb; e.ld_out = RGB_LD;
+      XLX_TRY(conv(passes, st, w.os, B, R2, CH, 9, p.rgb[i], 64, RGB_LD, e));
+      const size_t n = static_cast<size_t>(B) * 3 * 256 * 256;
+      rgb_accumulate_kernel<<<blocks_for(n), 256, 0, st>>>(w.rgb, R2, 256, n, i == 0, i == NBLK - 1, w.acc, img, pre_tanh);
+      XLX_TRY(krc());
+    }
+    x = of; ldx = CH;
+  }
+  return 0;
+}
+
+}  // extern "C"
