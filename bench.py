@@ -251,6 +251,8 @@ def run_ours(args):
     h2d = ids_h.numel() * 8 + mask_h.numel() * 1 + cids_h.numel() * 8
     d2h = 4
 
+    from xlxmert_b200.parallel import allreduce_gradients
+
     def step_e2e():
         enc.invalidate_prepared()
         ids = ids_h.to(dev, non_blocking=True)
@@ -260,7 +262,7 @@ def run_ours(args):
         out = model(input_ids=ids, visual_feats=feats, visual_pos=pos_d, attention_mask=am)
         loss = (out[0] * g_lang).sum() + (out[1] * g_vis).sum() + out[2].mean()
         loss.backward()
-        allreduce_grads()
+        allreduce_gradients(model)                                # encoder arena + one flat buffer for the rest
         loss_h.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()                 # the step's result is read on the host
         for p in model.parameters():

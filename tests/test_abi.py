@@ -1,0 +1,89 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/xlxmert_b200.h declares,
+its size/introspection entry points answer without a GPU, and the product path refuses to run without CUDA."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "xlxmert_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(xlx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as entry
+    entry.build()
+    from xlxmert_b200 import _lib
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert b"sm_100a" in lib.xlx_version()
+    assert lib.xlx_strerror(-22).decode().startswith("sequence length")
+
+
+def test_size_queries_work_without_gpu():
+    from xlxmert_b200 import _lib, params as P
+    from xlxmert_b200.config import DEFAULT_DIMS as D
+    lib = _lib.load()
+    cd = _lib.XlxDims.from_dims(D)
+    n = lib.xlx_encoder_num_params(C.byref(cd))
+    assert n == P.num_encoder_params(D) == len(P.encoder_param_names(D))
+    total = lib.xlx_encoder_grad_elems(C.byref(cd))
+    assert total == sum(lib.xlx_encoder_param_elems(C.byref(cd), i) for i in range(n))
+    specs = P.encoder_param_specs(D)
+    for i in (0, 5, 8, 17, n - 1):
+        shape = specs[i][1]
+        assert lib.xlx_encoder_param_elems(C.byref(cd), i) == int(torch.tensor(shape).prod())
+    assert lib.xlx_encoder_workspace_bytes(C.byref(cd), 256, 20, 64, 1) > lib.xlx_encoder_workspace_bytes(C.byref(cd), 256, 20, 64, 0) > 0
+    assert lib.xlx_encoder_workspace_bytes(C.byref(cd), 2, 65, 64, 0) == 0          # unsupported length → 0, not a crash
+    assert lib.xlx_objhead_workspace_bytes(C.byref(cd), 10000, 128) > 0
+    assert lib.xlx_generator_num_params() == 150 and lib.xlx_generator_workspace_bytes(2) > 0
+    bad = _lib.XlxDims.from_dims(D)
+    bad.hidden = 100
+    assert lib.xlx_encoder_num_params(C.byref(bad)) == -20
+
+
+def test_generator_state_dict_contract():
+    """State-dict keys of the drop-in generator are exactly the reference's."""
+    from xlxmert_b200 import params as P
+    from xlxmert_b200.generator import B200Generator
+    G = B200Generator()
+    want = set(P.init_generator_state_dict(seed=0).keys())
+    assert set(G.state_dict().keys()) == want
+    assert sum(1 for k in want if k.endswith("weight_orig")) == 17      # 17 spectrally normalised convs
+
+
+def test_pretraining_state_dict_contract():
+    from xlxmert_b200.config import TINY_DIMS
+    from xlxmert_b200.pretraining import B200XLxmertForPretraining
+    m = B200XLxmertForPretraining(TINY_DIMS, num_clusters=TINY_DIMS.num_clusters)
+    m.set_visual_embedding(torch.rand(TINY_DIMS.num_clusters, TINY_DIMS.feat_dim))
+    keys = set(m.state_dict().keys())
+    for k in ("mask_feat", "bert.embeddings.word_embeddings.weight", "bert.encoder.visn_fc.visn_fc.weight",
+              "bert.encoder.layer.0.attention.self.query.weight", "bert.encoder.r_layers.0.output.LayerNorm.bias",
+              "bert.encoder.x_layers.1.visual_attention.att.key.bias", "bert.encoder.x_layers.0.lang_inter.dense.weight",
+              "bert.pooler.dense.weight", "cls.predictions.bias", "cls.predictions.transform.dense.weight",
+              "cls.predictions.decoder.weight", "cls.seq_relationship.weight", "obj_predict_head.transform.LayerNorm.weight",
+              "obj_predict_head.linear_feat.weight", "obj_predict_head.out_cluster.weight",
+              "obj_predict_head.out_cluster.bias", "vis_emb.weight"):
+        assert k in keys, k
+    assert m.cls.predictions.decoder.weight is m.bert.embeddings.word_embeddings.weight       # modeling.py:86
+    assert m.obj_predict_head.out_cluster.weight is m.vis_emb.weight                          # modeling.py:151
+    assert not m.vis_emb.weight.requires_grad
+
+
+def test_product_path_has_no_cpu_fallback():
+    from xlxmert_b200.config import TINY_DIMS
+    from xlxmert_b200.lxmert import B200LxmertModel
+    m = B200LxmertModel(TINY_DIMS)
+    ids = torch.ones(1, 4, dtype=torch.long)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(input_ids=ids, visual_feats=torch.zeros(1, 4, TINY_DIMS.feat_dim), visual_pos=torch.zeros(1, 4, 4))

@@ -1,0 +1,163 @@
+"""Text → image sampling model: drop-in for ``ImggenModel`` (``x-lxmert/src/tasks/imggen_model.py:11-257``).
+
+Same attributes (``bert``, ``obj_predict_head``, ``mask_feat``, ``vis_emb``, ``G``), same ``set_visual_embedding`` /
+``set_image_generator`` / ``denorm`` and the two samplers with the reference's keywords.  Every encoder pass, the
+cluster head with its fused ``softmax(2).max(2)`` and the generator run in ``libxlxmert_b200.so``; the loop itself
+stays host-driven exactly like the reference (SURVEY.md §8f ranks moving it on device as the next step).
+
+``sentences`` may be a list of strings (needs a tokenizer: pass one to the constructor — the reference downloads
+``unc-nlp/lxmert-base-uncased``, impossible offline) or an already tokenised ``LongTensor [B, L]``.
+"""
+from __future__ import annotations
+
+import random
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from .config import LxmertDims
+from .heads import B200LxmertVisualObjHead
+from .lxmert import B200LxmertModel
+from .synth import box_position
+
+
+class B200ImggenModel(nn.Module):
+    def __init__(self, config, args=None, num_clusters: int = 10000, passes: int = 3, tokenizer=None):
+        super().__init__()
+        from .encoder import dims_from_hf_config
+        dims = config if isinstance(config, LxmertDims) else dims_from_hf_config(config)
+        if dims.num_clusters != num_clusters:
+            dims = LxmertDims(**{**dims.asdict(), "num_clusters": num_clusters})
+        self.dims, self.args = dims, args
+        self.config = None if isinstance(config, LxmertDims) else config
+        self.bert = B200LxmertModel(dims, passes=passes)
+        self.obj_predict_head = B200LxmertVisualObjHead(dims, num_clusters, passes=passes)
+        self.mask_feat = nn.Parameter(torch.zeros(dims.feat_dim))
+        self.vis_emb: Optional[nn.Embedding] = None
+        self.tokenizer = tokenizer
+        self.G = None
+
+    def set_visual_embedding(self, centroids):                         # imggen_model.py:29-39
+        if isinstance(centroids, np.ndarray):
+            centroids = torch.from_numpy(centroids)
+        centroids = centroids.to(device=self.mask_feat.device, dtype=torch.float32).contiguous()
+        self.vis_emb = nn.Embedding.from_pretrained(centroids, freeze=True)
+        self.obj_predict_head.out_cluster.weight = self.vis_emb.weight
+
+    def set_image_generator(self, generator):                          # imggen_model.py:41-42
+        self.G = generator
+
+    def denorm(self, x):                                               # imggen_model.py:44-47
+        """(-1, 1) => (0, 1)"""
+        return ((x + 1) / 2).clamp(0, 1)
+
+    # -- helpers -------------------------------------------------------------------------------------
+    def _input_ids(self, sentences, max_text_length):
+        dev = self.mask_feat.device
+        if torch.is_tensor(sentences):
+            return sentences[:, :max_text_length].to(dev)
+        if self.tokenizer is None:
+            raise RuntimeError("no tokenizer: pass tokenizer= to B200ImggenModel or give token ids [B, L]")
+        ids = self.tokenizer(sentences, max_length=max_text_length, truncation=True, return_tensors='pt').input_ids
+        return ids.to(dev)
+
+    def _predict(self, input_ids, code, visual_pos):
+        """One full pass: LXMERT → cluster head → ``softmax(2).max(2)`` (imggen_model.py:221-235)."""
+        out = self.bert(input_ids=input_ids, visual_feats=code, visual_pos=visual_pos, attention_mask=input_ids > 0)
+        return self.obj_predict_head.predict(out[1])
+
+    def _decode(self, code, B, code_dim, grid_size):
+        return self.denorm(self.G(code.permute(0, 2, 1).view(B, code_dim, grid_size, grid_size))).cpu()
+
+    # -- samplers ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def sample_image_NAR(self, sentences, max_text_length=20, n_steps=None, return_intermediate=False,
+                         return_codes=False):
+        """Mask-predict sampling with linear decay (imggen_model.py:169-257)."""
+        self.eval()
+        input_ids = self._input_ids(sentences, max_text_length)
+        B, dev = input_ids.shape[0], input_ids.device
+        grid_size, code_dim = 8, self.dims.feat_dim
+        n_grids = grid_size ** 2
+        if n_steps is None:
+            n_steps = n_grids
+        visual_pos = torch.from_numpy(box_position(grid_size)).unsqueeze(0).expand(B, -1, -1).contiguous().to(dev)
+        intermediate_imgs = []
+        pred_prob = pred_code_id = None
+        for i in range(n_steps):
+            n_mask = int((n_steps - i) / n_steps * n_grids)
+            if i == 0:
+                vis_mask = torch.ones(B, n_grids, dtype=torch.long, device=dev)
+                code = torch.zeros(B, n_grids, code_dim, device=dev)
+            else:
+                _, lowest_arg = pred_prob.topk(n_mask, dim=1, largest=False)
+                vis_mask = torch.zeros(B, n_grids, dtype=torch.long, device=dev)
+                vis_mask.scatter_(1, lowest_arg, 1)
+            m = vis_mask.view(B, n_grids, 1).bool()
+            code = torch.where(m, self.mask_feat.view(1, 1, -1).to(code.dtype), code)
+            pred_prob, pred_code_id = self._predict(input_ids, code, visual_pos)
+            code = torch.where(m, self.vis_emb(pred_code_id), code)
+            if return_intermediate:
+                intermediate_imgs.append(self._decode(code, B, code_dim, grid_size))
+        if return_intermediate:
+            return intermediate_imgs
+        if return_codes:
+            return code, pred_prob, pred_code_id
+        return self._decode(code, B, code_dim, grid_size)
+
+    @torch.no_grad()
+    def sample_image_AR(self, sentences, max_text_length=20, position_random=False, position_TLBR=False,
+                        position_confidence=True, n_steps=None, seed=None, return_intermediate=False,
+                        return_codes=False):
+        """One grid cell per step (imggen_model.py:49-167): random, raster (TLBR) or highest-confidence order."""
+        self.eval()
+        input_ids = self._input_ids(sentences, max_text_length)
+        B, dev = input_ids.shape[0], input_ids.device
+        grid_size, code_dim = 8, self.dims.feat_dim
+        n_grids = grid_size ** 2
+        if n_steps is None:
+            n_steps = n_grids
+        visual_pos = torch.from_numpy(box_position(grid_size)).unsqueeze(0).expand(B, -1, -1).contiguous().to(dev)
+        intermediate_imgs = []
+        if position_random:
+            positions = list(range(n_grids))
+            rng = random.Random(seed) if seed is not None else random
+            rng.shuffle(positions)
+            if n_steps > n_grids:
+                extra = list(range(n_steps - n_grids))
+                (random.Random(seed) if seed is not None else random).shuffle(extra)
+                positions = extra + positions
+        if position_confidence:
+            visited = torch.zeros(B, n_grids, device=dev)
+        vis_mask = torch.ones(B, n_grids, dtype=torch.long, device=dev)
+        code = torch.zeros(B, n_grids, code_dim, device=dev)
+        current = None
+        for i in range(n_steps):
+            if position_random:
+                current = positions.pop() % n_grids
+                vis_mask[:, current] = 1
+            elif position_TLBR:
+                current = i
+            code = torch.where(vis_mask.view(B, n_grids, 1).bool(), self.mask_feat.view(1, 1, -1).to(code.dtype), code)
+            pred_prob, pred_code_id = self._predict(input_ids, code, visual_pos)
+            if position_TLBR or position_random:
+                update_mask = torch.zeros(B, n_grids, dtype=torch.bool, device=dev)
+                update_mask[:, current] = True
+                vis_mask[:, current] = 0
+            else:
+                masked = pred_prob.masked_fill(visited.bool(), -10000)
+                _, top_arg = masked.topk(1, dim=1, largest=True)
+                update_mask = torch.zeros(B, n_grids, dtype=torch.long, device=dev)
+                update_mask.scatter_(1, top_arg, 1)
+                vis_mask.scatter_(1, top_arg, 0)
+                visited.scatter_(1, top_arg, 1)
+            code = torch.where(update_mask.view(B, n_grids, 1).bool(), self.vis_emb(pred_code_id), code)
+            if return_intermediate:
+                intermediate_imgs.append(self._decode(code, B, code_dim, grid_size))
+        if return_intermediate:
+            return intermediate_imgs
+        if return_codes:
+            return code, pred_prob, pred_code_id
+        return self._decode(code, B, code_dim, grid_size)
