@@ -305,7 +305,7 @@ def run_ours(args):
         sampler.start()
     ms_step, launches = timed(step_resident, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_e2e, max(3, args.steps // 2), 3)
+    ms_e2e, _ = timed(step_e2e, max(3, args.steps), 5)
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM), events around every launch, outside the timed region
     lib.xlx_profile_gemm_begin()

@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Secondary measurements on one B200 (not the driver's bench line): BASELINE.json configs[2..4] —
+full pre-training step per task (B=256), generator forward (B=128), NAR sampling + decode (B=32).
+CUDA-event timed, 3 warm-up + N timed iterations, device-resident inputs.  Prints one JSON object."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from xlxmert_b200 import params as P, synth  # noqa: E402
+from xlxmert_b200.config import DEFAULT_DIMS as D  # noqa: E402
+
+
+def timed(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    import __graft_entry__ as entry
+    entry.build()
+    from test_pretrain_parity import build_model
+    from xlxmert_b200.generator import B200Generator
+    from xlxmert_b200.sampler import B200ImggenModel
+    out = {}
+    model, table = build_model(0)
+    model.train()
+    B = 256
+    batch = {k: v.cuda() for k, v in synth.make_batch(D, B, 20, 64, seed=0).items()}
+    labels = dict(word_labels=batch["word_labels"], obj_labels=batch["obj_labels"], matched_labels=batch["matched_labels"])
+
+    def step(task):
+        def f():
+            ids = batch["masked_input_ids"] if task == "word_mask" else batch["input_ids"]
+            for p in model.parameters():
+                p.grad = None
+            o = model(input_ids=ids, visual_pos=batch["visual_pos"], attention_mask=batch["attention_mask"],
+                      cluster_ids=batch["cluster_ids"], vis_mask=batch["vis_mask"], label_dict=labels, task=task)
+            o["total_loss"].backward()
+        return f
+    flop = {"vis_mask": 54.9, "word_mask": 49.1, "matched": 47.2}
+    for task in ("vis_mask", "word_mask", "matched"):
+        ms = timed(step(task), 5)
+        out[f"pretrain_{task}_B{B}"] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3,
+                                        "algorithmic_tflops": flop[task] * B / ms}
+    del model
+    torch.cuda.empty_cache()
+
+    G = B200Generator()
+    G.load_state_dict(P.init_generator_state_dict(seed=0), strict=True)
+    G = G.cuda().eval()
+    Bg = 128
+    ids = torch.randint(0, D.num_clusters, (Bg, 64), device="cuda")
+    code = table.cuda()[ids]
+    ms = timed(lambda: G(code.view(Bg, 8, 8, 2048), train=False), 5)
+    out[f"generator_fwd_B{Bg}"] = {"ms": ms, "images_per_s": Bg / ms * 1e3, "algorithmic_tflops": 27.755 * Bg / ms}
+
+    pre, table = build_model(0)
+    m = B200ImggenModel(D, num_clusters=D.num_clusters)
+    m.set_visual_embedding(table.clone())
+    m.load_state_dict({k: v for k, v in pre.state_dict().items() if not k.startswith("cls.")}, strict=False)
+    m.set_image_generator(G)
+    m = m.cuda()
+    Bs = 32
+    tok = synth.make_batch(D, Bs, 20, 64, seed=3)["input_ids"].cuda()
+    ms = timed(lambda: m.sample_image_NAR(tok, n_steps=4), 3, warm=2)
+    out[f"sample_NAR4_plus_decode_B{Bs}"] = {"ms": ms, "images_per_s": Bs / ms * 1e3,
+                                             "algorithmic_tflops": 100.9 * Bs / ms}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

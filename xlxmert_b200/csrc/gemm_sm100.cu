@@ -122,7 +122,9 @@ __device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, 
   }
 }
 
-template <int BK>
+// A_MN / B_MN: operand stored MN-major; NPARTS: 1 = hi only (1 pass), 2 = hi + lo (3 passes).  Compile-time so that
+// the single MMA-issuing thread's loop is a handful of integer adds per tcgen05.mma (it is the critical path).
+template <int BK, int A_MN, int B_MN, int NPARTS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
             const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
@@ -145,7 +147,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapAhi);
     tma_prefetch_desc(&mapBhi);
-    if (P.nparts == 2) {
+    if (NPARTS == 2) {
       tma_prefetch_desc(&mapAlo);
       tma_prefetch_desc(&mapBlo);
     }
@@ -178,32 +180,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
         const int m0 = (tile / P.tiles_n) * BM;
         const int n0 = (tile % P.tiles_n) * P.BN;
         const int kb0 = split * P.kb_per_split, kb1 = min(nkb, kb0 + P.kb_per_split);
+        // conv mode: tile → (image, y, x) of its first pixel
+        int img = 0, y0 = 0, x0 = 0;
+        if (P.conv) {
+          const int hw = P.conv_H * P.conv_W;
+          img = m0 / hw;
+          const int rem = m0 % hw;
+          y0 = rem / P.conv_W; x0 = rem % P.conv_W;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
           const uint32_t full = smem_u32(&bar_full[s]);
           mbar_arrive_expect_tx(full, P.stage_bytes);
           const uint32_t sA = smem_base + s * P.stage_bytes;
-          const uint32_t sB = sA + P.nparts * P.a_part_bytes;
+          const uint32_t sB = sA + NPARTS * P.a_part_bytes;
           const int k0 = kb * BK;
-          for (int part = 0; part < P.nparts; ++part) {
+#pragma unroll
+          for (int part = 0; part < NPARTS; ++part) {
             const CUtensorMap* ma = part ? &mapAlo : &mapAhi;
             const CUtensorMap* mb = part ? &mapBlo : &mapBhi;
             const uint32_t dA = sA + part * P.a_part_bytes;
             const uint32_t dB = sB + part * P.b_part_bytes;
-            if (P.conv) {
-              // tile → (image, y, x) of its first pixel; k-block → (tap, channel offset)
-              const int hw = P.conv_H * P.conv_W;
-              const int img = m0 / hw, rem = m0 % hw;
-              const int y0 = rem / P.conv_W, x0 = rem % P.conv_W;
+            if (!A_MN && P.conv) {
+              // k-block → (filter tap, channel offset); the box is the activation tensor shifted by the tap
               const int tap = kb / P.conv_kb_per_tap, c0 = (kb % P.conv_kb_per_tap) * BK;
               const int dy = P.conv_taps == 9 ? tap / 3 - 1 : 0, dx = P.conv_taps == 9 ? tap % 3 - 1 : 0;
               tma_load_4d(dA, ma, full, c0, x0 + dx, y0 + dy, img);
-            } else if (!P.a_mn) {
+            } else if (!A_MN) {
               tma_load_2d(dA, ma, full, k0, m0);
             } else {
+#pragma unroll
               for (int j = 0; j < BM / 64; ++j) tma_load_2d(dA + j * (BK * 128), ma, full, m0 + 64 * j, k0);
             }
-            if (!P.b_mn) {
+            if (!B_MN) {
               tma_load_2d(dB, mb, full, k0, n0);
             } else {
               for (int j = 0; j < P.BN / 64; ++j) tma_load_2d(dB + j * (BK * 128), mb, full, n0 + 64 * j, k0);
@@ -214,59 +223,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== UMMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, P.BN, P.a_mn, P.b_mn);
-      // K-major: rows of BK·2 bytes (64B or 128B swizzle), 8-row groups contiguous.
-      constexpr uint32_t kSwzK = (BK == 64) ? UMMA_SWZ_128B : UMMA_SWZ_64B;
-      constexpr uint32_t kSboK = 8 * BK * 2;
-      constexpr uint32_t kStepK = 32;          // 16 bf16 along K inside the swizzled row
-      // MN-major: 64-element (128B) MN atoms, one TMA box of BK rows each; 8-row K groups 1024B apart.
-      constexpr uint32_t kLboMN = BK * 128;
-      constexpr uint32_t kSboMN = 1024;
-      constexpr uint32_t kStepMN = 16 * 128;   // 16 K rows
-      int s = 0;
-      uint32_t ph = 0;
-      int local = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
-        const int split = item / num_tiles;
-        const int kb0 = split * P.kb_per_split, kb1 = min(nkb, kb0 + P.kb_per_split);
-        const int buf = local & 1;
-        const uint32_t acc_ph = (local >> 1) & 1;
-        mbar_wait(smem_u32(&bar_tmem_empty[buf]), acc_ph ^ 1);
+    // ===================== UMMA issuer (whole warp runs the loop, one elected lane issues) =====================
+    const uint32_t idesc = umma_idesc_bf16(BM, P.BN, A_MN, B_MN);
+    // Shared-memory descriptors: the high word is a per-operand constant, the low word is
+    // (LBO >> 4) << 16 | (address >> 4); stepping along K only adds to the address field.
+    //   K-major: rows of BK·2 bytes (64B swizzle for BK = 32), 8-row groups SBO apart, K step = 32 bytes.
+    //   MN-major: 64-element (128B) MN atoms = one TMA box of BK rows each (LBO apart); 8-row K groups 1024B apart.
+    constexpr uint32_t kSwzK = (BK == 64) ? UMMA_SWZ_128B : UMMA_SWZ_64B;
+    constexpr uint32_t kHiK = umma_desc_hi(8 * BK * 2, kSwzK), kHiMN = umma_desc_hi(1024, UMMA_SWZ_128B);
+    constexpr uint32_t kLoK = umma_desc_lo_lbo(16), kLoMN = umma_desc_lo_lbo(BK * 128);
+    constexpr uint32_t kStepK = 32 >> 4, kStepMN = (16 * 128) >> 4;
+    constexpr uint32_t hiA = A_MN ? kHiMN : kHiK, hiB = B_MN ? kHiMN : kHiK;
+    constexpr uint32_t loA = A_MN ? kLoMN : kLoK, loB = B_MN ? kLoMN : kLoK;
+    constexpr uint32_t stepA = A_MN ? kStepMN : kStepK, stepB = B_MN ? kStepMN : kStepK;
+    const uint32_t a_part = P.a_part_bytes >> 4, b_part = P.b_part_bytes >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    int local = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+      const int split = item / num_tiles;
+      const int kb0 = split * P.kb_per_split, kb1 = min(nkb, kb0 + P.kb_per_split);
+      const int buf = local & 1;
+      const uint32_t acc_ph = (local >> 1) & 1;
+      mbar_wait(smem_u32(&bar_tmem_empty[buf]), acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * P.BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(smem_u32(&bar_full[s]), ph);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * P.BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(smem_u32(&bar_full[s]), ph);
-          tc_fence_after();
-          const uint32_t sA = smem_base + s * P.stage_bytes;
-          const uint32_t sB = sA + P.nparts * P.a_part_bytes;
+        const uint32_t sA = smem_base + s * P.stage_bytes;
+        const uint32_t a0 = loA | (sA >> 4);
+        const uint32_t b0 = loB | ((sA + NPARTS * P.a_part_bytes) >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint32_t offA = P.a_mn ? kk * kStepMN : kk * kStepK;
-            const uint32_t offB = P.b_mn ? kk * kStepMN : kk * kStepK;
-            const uint64_t dAhi = P.a_mn ? umma_smem_desc(sA + offA, kLboMN, kSboMN, UMMA_SWZ_128B)
-                                         : umma_smem_desc(sA + offA, 16, kSboK, kSwzK);
-            const uint64_t dBhi = P.b_mn ? umma_smem_desc(sB + offB, kLboMN, kSboMN, UMMA_SWZ_128B)
-                                         : umma_smem_desc(sB + offB, 16, kSboK, kSwzK);
-            const uint32_t first = ((kb - kb0) | kk) ? 1u : 0u;
-            if (P.nparts == 2) {
-              const uint64_t dAlo = P.a_mn ? umma_smem_desc(sA + P.a_part_bytes + offA, kLboMN, kSboMN, UMMA_SWZ_128B)
-                                           : umma_smem_desc(sA + P.a_part_bytes + offA, 16, kSboK, kSwzK);
-              const uint64_t dBlo = P.b_mn ? umma_smem_desc(sB + P.b_part_bytes + offB, kLboMN, kSboMN, UMMA_SWZ_128B)
-                                           : umma_smem_desc(sB + P.b_part_bytes + offB, 16, kSboK, kSwzK);
+            const uint32_t acc = (kb > kb0 || kk > 0) ? 1u : 0u;
+            const uint32_t ah = a0 + kk * stepA, bh = b0 + kk * stepB;
+            if (NPARTS == 2) {
               // small cross terms first, leading term last
-              umma_bf16(tmem_d, dAlo, dBhi, idesc, first);
-              umma_bf16(tmem_d, dAhi, dBlo, idesc, 1u);
-              umma_bf16(tmem_d, dAhi, dBhi, idesc, 1u);
+              umma_bf16(tmem_d, umma_desc(hiA, ah + a_part), umma_desc(hiB, bh), idesc, acc);
+              umma_bf16(tmem_d, umma_desc(hiA, ah), umma_desc(hiB, bh + b_part), idesc, 1u);
+              umma_bf16(tmem_d, umma_desc(hiA, ah), umma_desc(hiB, bh), idesc, 1u);
             } else {
-              umma_bf16(tmem_d, dAhi, dBhi, idesc, first);
+              umma_bf16(tmem_d, umma_desc(hiA, ah), umma_desc(hiB, bh), idesc, acc);
             }
           }
           umma_commit(smem_u32(&bar_empty[s]));              // smem slot reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(smem_u32(&bar_tmem_full[buf]));
-          if (++s == P.num_stages) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == P.num_stages) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -483,19 +489,27 @@ int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
+template <int BK, int A_MN, int B_MN, int NPARTS>
+int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& mAhi, const CUtensorMap& mAlo,
+                   const CUtensorMap& mBhi, const CUtensorMap& mBlo, const KParams& P) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BK, A_MN, B_MN, NPARTS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  gemm_kernel<BK, A_MN, B_MN, NPARTS><<<grid, GEMM_THREADS, smem, stream>>>(mAhi, mAlo, mBhi, mBlo, P);
+  return 0;
+}
+
 template <int BK>
 int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   static int num_sms = 0;
-  static bool attr_set = false;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
   }
   KParams P;
   memset(&P, 0, sizeof(P));
@@ -600,7 +614,21 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     tl.grid = grid;
     cudaEventRecord(tl.e0, stream);
   }
-  gemm_kernel<BK><<<grid, GEMM_THREADS, smem, stream>>>(mAhi, mAlo, mBhi, mBlo, P);
+  {
+    const int v = (P.a_mn ? 4 : 0) | (P.b_mn ? 2 : 0) | (P.nparts == 2 ? 1 : 0);
+    int lrc = 0;
+    switch (v) {
+      case 0: lrc = launch_variant<BK, 0, 0, 1>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
+      case 1: lrc = launch_variant<BK, 0, 0, 2>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
+      case 2: lrc = launch_variant<BK, 0, 1, 1>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
+      case 3: lrc = launch_variant<BK, 0, 1, 2>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
+      case 4: lrc = launch_variant<BK, 1, 0, 1>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
+      case 5: lrc = launch_variant<BK, 1, 0, 2>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
+      case 6: lrc = launch_variant<BK, 1, 1, 1>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
+      default: lrc = launch_variant<BK, 1, 1, 2>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
+    }
+    if (lrc) return lrc;
+  }
   if (P.splits > 1) {
     const size_t mn4 = static_cast<size_t>(p.M) * p.N / 4;
     size_t blocks = (mn4 + 255) / 256;
@@ -666,8 +694,7 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream) {
     return -2;
   if ((E.flags & (EPI_GELU_GRAD | EPI_MUL)) && !E.u_in) return -1;
   if (E.addend_hi && !E.addend_lo) return -1;
-  static const int bk = env_int("XLX_GEMM_BK", 32);
-  return bk == 64 ? launch_bk<64>(p, stream) : launch_bk<32>(p, stream);
+  return launch_bk<32>(p, stream);
 }
 
 }  // namespace xlx

@@ -128,6 +128,15 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 constexpr uint32_t UMMA_SWZ_NONE = 0, UMMA_SWZ_128B = 2, UMMA_SWZ_64B = 4, UMMA_SWZ_32B = 6;
+// The same descriptor split into its two 32-bit words, so that an issue loop keeps the constant high word
+// (SBO, version, swizzle) in an immediate and only adds to the address field of the low word.
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((layout_type & 7) << 29);
+}
+__host__ __device__ constexpr uint32_t umma_desc_lo_lbo(uint32_t lbo_bytes) { return ((lbo_bytes >> 4) & 0x3FFF) << 16; }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t hi, uint32_t lo) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 
 // Instruction descriptor for kind::f16, bf16 × bf16 → fp32:
 //   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
