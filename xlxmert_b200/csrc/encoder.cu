@@ -87,7 +87,7 @@ Prep prep_layout(const xlx_dims* d, void* base) {
 
 // ---- activation plan -----------------------------------------------------------------------------
 struct AttSave {
-  float* qkv = nullptr;    // [M, 3H]
+  Split qkv;               // [M, 3H] fused Q | K | V projections, split bf16 (the attention kernels TMA-load it)
   float* probs = nullptr;  // self: [B,heads,S,S]; cross: lang-query probs [B,heads,L,V]
   float* probs2 = nullptr; // cross only: vis-query probs [B,heads,V,L]
   Split ctx;               // [M, H]
@@ -117,8 +117,8 @@ struct Plan {
   size_t part_elems = 0;
   float* splitk = nullptr;   // split-K partial sums of the weight-gradient GEMMs
   // backward scratch
-  float *dA = nullptr, *dB = nullptr, *dy = nullptr, *dctx = nullptr, *dy2 = nullptr;
-  Split dy_s, dqkv, du;
+  float *dA = nullptr, *dB = nullptr, *dy = nullptr, *dy2 = nullptr;
+  Split dy_s, dqkv, du, dctx;
   size_t bytes = 0;
 };
 
@@ -152,11 +152,11 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
   Split xin0 = b.split(Mt * H);  // input of the first cross-modality layer: [lang rows | vis rows]
 
   // inference: every block shares one set of temporaries and layer outputs rotate through a small ring
-  float *sh_qkv = nullptr, *sh_y = nullptr;
-  Split sh_ctx, sh_h, ring[4];
+  float* sh_y = nullptr;
+  Split sh_qkv, sh_ctx, sh_h, ring[4];
   int ring_i = 0;
   if (!training) {
-    sh_qkv = b.f32(Mt * 3 * H);
+    sh_qkv = b.split(Mt * 3 * H);
     sh_ctx = b.split(Mt * H);
     sh_y = b.f32(Mt * H);
     sh_h = b.split(Mmax * I);
@@ -171,7 +171,7 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
   auto fill_att = [&](AttSave& a, size_t M, size_t probs_elems, size_t probs2_elems) {
     a.M = static_cast<int>(M);
     if (training) {
-      a.qkv = b.f32(M * 3 * H);
+      a.qkv = b.split(M * 3 * H);
       a.probs = b.f32(probs_elems);
       if (probs2_elems) a.probs2 = b.f32(probs2_elems);
       a.ctx = b.split(M * H);
@@ -232,7 +232,7 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
     } else {  // shared temporaries: give the two streams disjoint row ranges
       fill_att(sl, Ml, 0, 0);
       fill_att(sv, Mv, 0, 0);
-      sv.qkv = sh_qkv + Ml * 3 * H; sv.ctx = rows(sh_ctx, Ml, H); sv.y = sh_y + Ml * H;
+      sv.qkv = rows(sh_qkv, Ml, 3 * H); sv.ctx = rows(sh_ctx, Ml, H); sv.y = sh_y + Ml * H;
     }
     sl.in = rows(c.out, 0, H); sl.out = rows(S2, 0, H);
     sv.in = rows(c.out, Ml, H); sv.out = rows(S2, Ml, H);
@@ -248,7 +248,7 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
     p.dA = b.f32(Mt * H);
     p.dB = b.f32(Mt * H);
     p.dy = b.f32(Mt * H);
-    p.dctx = b.f32(Mt * H);
+    p.dctx = b.split(Mt * H);
     p.dy2 = b.f32(Mv * H);
     p.dy_s = b.split(Mt * H);
     p.dqkv = b.split(Mt * 3 * H);
@@ -283,6 +283,18 @@ int wgrad(const Run& r, Split dy, int M, int N, Split x, int K, float* dw) {
 
 const float* P(const Run& r, int slot) { return r.params[slot]; }
 
+// attention operands: part 0/1/2 = Q/K/V columns of a fused [M, 3H] projection; or a plain [M, H] matrix
+AttnOperand qkv_op(Split qkv, int M, int H, int part) {
+  AttnOperand o;
+  o.base = qkv; o.ld = 3 * H; o.rows = M; o.col = part * H;
+  return o;
+}
+AttnOperand mat_op(Split m, int M, int H) {
+  AttnOperand o;
+  o.base = m; o.ld = H; o.rows = M; o.col = 0;
+  return o;
+}
+
 // ---- forward blocks ------------------------------------------------------------------------------
 // residual + LayerNorm tail shared by the attention-output and FFN-output sub-blocks (HF:277-288, 339-350)
 int ln_tail(const Run& r, float* y, int M, const float* g, const float* b, Split out, float* out_f32, float* mean,
@@ -296,10 +308,10 @@ int att_self_fwd(const Run& r, int blk, int S, const float* mask, float* out_f32
   const AttW& w = r.prep.att[blk];
   const int s0 = att_slot(r.d, blk), H = p.H, M = a.M;
   GemmEpilogue e;
-  e.bias = w.bqkv; e.out_f32 = a.qkv; e.ld_out = 3 * H;
+  e.bias = w.bqkv; e.out_hi = a.qkv.hi; e.out_lo = a.qkv.lo; e.ld_split = 3 * H;
   XLX_TRY(linear(r, a.in, M, H, w.wqkv, 3 * H, e));
-  XLX_TRY(attention_fwd(a.qkv, a.qkv + H, a.qkv + 2 * H, 3 * H, mask, p.B, p.heads, S, S, a.ctx, nullptr, H, a.probs,
-                        r.st));
+  XLX_TRY(attention_fwd(qkv_op(a.qkv, M, H, 0), qkv_op(a.qkv, M, H, 1), qkv_op(a.qkv, M, H, 2), mask, p.B, p.heads, S, S,
+                        a.ctx, nullptr, H, a.probs, r.st));
   GemmEpilogue o;
   o.bias = P(r, s0 + 7); o.addend_hi = a.in.hi; o.addend_lo = a.in.lo; o.ld_addend = H;
   o.out_f32 = a.y; o.ld_out = H;
@@ -315,16 +327,15 @@ int att_cross_fwd(const Run& r, int blk) {
   const int s0 = att_slot(r.d, blk), H = p.H;
   const size_t H3 = 3 * static_cast<size_t>(H);
   GemmEpilogue e;
-  e.bias = w.bqkv; e.out_f32 = a.qkv; e.ld_out = 3 * H;
+  e.bias = w.bqkv; e.out_hi = a.qkv.hi; e.out_lo = a.qkv.lo; e.ld_split = 3 * H;
   XLX_TRY(linear(r, a.in, p.Mt, H, w.wqkv, 3 * H, e));   // Q, K, V of all B·(L+V) tokens in one GEMM
-  const float* ql = a.qkv;                  // language rows
-  const float* qv = a.qkv + p.Ml * H3;      // vision rows
+  const Split ql = a.qkv, qv = rows(a.qkv, p.Ml, H3);     // language rows / vision rows
   // language queries over vision keys/values (mask = visual attention mask, normally none)
-  XLX_TRY(attention_fwd(ql, qv + H, qv + 2 * H, 3 * H, r.vmask, p.B, p.heads, p.L, p.V, a.ctx, nullptr, H, a.probs,
-                        r.st));
+  XLX_TRY(attention_fwd(qkv_op(ql, p.Ml, H, 0), qkv_op(qv, p.Mv, H, 1), qkv_op(qv, p.Mv, H, 2), r.vmask, p.B, p.heads,
+                        p.L, p.V, a.ctx, nullptr, H, a.probs, r.st));
   // vision queries over language keys/values (mask = language attention mask)
-  XLX_TRY(attention_fwd(qv, ql + H, ql + 2 * H, 3 * H, r.lmask, p.B, p.heads, p.V, p.L, rows(a.ctx, p.Ml, H), nullptr,
-                        H, a.probs2, r.st));
+  XLX_TRY(attention_fwd(qkv_op(qv, p.Mv, H, 0), qkv_op(ql, p.Ml, H, 1), qkv_op(ql, p.Ml, H, 2), r.lmask, p.B, p.heads,
+                        p.V, p.L, rows(a.ctx, p.Ml, H), nullptr, H, a.probs2, r.st));
   GemmEpilogue o;
   o.bias = P(r, s0 + 7); o.addend_hi = a.in.hi; o.addend_lo = a.in.lo; o.ld_addend = H;
   o.out_f32 = a.y; o.ld_out = H;
@@ -397,7 +408,7 @@ int att_bwd_head(const Bwd& bw, int blk, const float* dout) {
   XLX_TRY(colsum(p.dy, Split(), M, H, H, p.part, bw.G(s0 + 7), r.st));
   XLX_TRY(wgrad(r, p.dy_s, M, H, a.ctx, H, bw.G(s0 + 6)));
   GemmEpilogue e;
-  e.out_f32 = p.dctx; e.ld_out = H;
+  e.out_hi = p.dctx.hi; e.out_lo = p.dctx.lo; e.ld_split = H;
   return dgrad(r, p.dy_s, M, H, w.wo, H, e);
 }
 int att_bwd_tail(const Bwd& bw, int blk, float* din) {
@@ -420,8 +431,8 @@ int att_self_bwd(const Bwd& bw, int blk, int S, const float* dout, float* din) {
   XLX_TRY(att_bwd_head(bw, blk, dout));
   Split dq = p.dqkv, dk = p.dqkv, dv = p.dqkv;
   dk.hi += H; dk.lo += H; dv.hi += 2 * H; dv.lo += 2 * H;
-  XLX_TRY(attention_bwd(p.dctx, H, a.qkv, a.qkv + H, a.qkv + 2 * H, 3 * H, a.probs, p.B, p.heads, S, S, dq, dk, dv,
-                        3 * H, r.st));
+  XLX_TRY(attention_bwd(mat_op(p.dctx, a.M, H), qkv_op(a.qkv, a.M, H, 0), qkv_op(a.qkv, a.M, H, 1),
+                        qkv_op(a.qkv, a.M, H, 2), a.probs, p.B, p.heads, S, S, dq, dk, dv, 3 * H, r.st));
   return att_bwd_tail(bw, blk, din);
 }
 int att_cross_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
@@ -431,16 +442,16 @@ int att_cross_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
   const int H = p.H;
   const size_t H3 = 3 * static_cast<size_t>(H);
   XLX_TRY(att_bwd_head(bw, blk, dout));
-  const float* ql = a.qkv;
-  const float* qv = a.qkv + p.Ml * H3;
+  const Split ql = a.qkv, qv = rows(a.qkv, p.Ml, H3);
   Split dl = p.dqkv, dvv = rows(p.dqkv, p.Ml, H3);   // language rows / vision rows of dqkv
   auto col = [](Split s, int c) { s.hi += c; s.lo += c; return s; };
   // language queries: dQ → language rows, dK/dV → vision rows
-  XLX_TRY(attention_bwd(p.dctx, H, ql, qv + H, qv + 2 * H, 3 * H, a.probs, p.B, p.heads, p.L, p.V, col(dl, 0),
-                        col(dvv, H), col(dvv, 2 * H), 3 * H, r.st));
+  XLX_TRY(attention_bwd(mat_op(p.dctx, p.Ml, H), qkv_op(ql, p.Ml, H, 0), qkv_op(qv, p.Mv, H, 1), qkv_op(qv, p.Mv, H, 2),
+                        a.probs, p.B, p.heads, p.L, p.V, col(dl, 0), col(dvv, H), col(dvv, 2 * H), 3 * H, r.st));
   // vision queries: dQ → vision rows, dK/dV → language rows
-  XLX_TRY(attention_bwd(p.dctx + static_cast<size_t>(p.Ml) * H, H, qv, ql + H, ql + 2 * H, 3 * H, a.probs2, p.B,
-                        p.heads, p.V, p.L, col(dvv, 0), col(dl, H), col(dl, 2 * H), 3 * H, r.st));
+  XLX_TRY(attention_bwd(mat_op(rows(p.dctx, p.Ml, H), p.Mv, H), qkv_op(qv, p.Mv, H, 0), qkv_op(ql, p.Ml, H, 1),
+                        qkv_op(ql, p.Ml, H, 2), a.probs2, p.B, p.heads, p.V, p.L, col(dvv, 0), col(dl, H),
+                        col(dl, 2 * H), 3 * H, r.st));
   return att_bwd_tail(bw, blk, din);
 }
 

@@ -650,6 +650,14 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
 }  // namespace
 
 long long gemm_launch_count() { return g_launches.load(); }
+
+int tma_map_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                    uint32_t box_outer, int swizzle_bytes) {
+  const CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  return make_map(out, ptr, inner, outer, ld, box_inner, box_outer, swz);
+}
 // splits · tiles ≤ 2 · #SMs and every tile is ≤ 128 × 256 outputs
 size_t gemm_splitk_ws_floats() { return static_cast<size_t>(2 * 148) * BM * 256; }
 

@@ -79,6 +79,10 @@ struct GemmProblem {
   size_t splitk_ws_floats = 0;
 };
 size_t gemm_splitk_ws_floats();
+// Cached 2-D TMA descriptor of a row-major bf16 matrix [outer, inner] with leading dimension ld (elements) and a
+// box of box_inner × box_outer elements; swizzle_bytes ∈ {0, 32, 64, 128}.  0 on success.
+int tma_map_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                    uint32_t box_outer, int swizzle_bytes);
 
 // Returns 0 on success, negative on invalid arguments, positive CUDA error otherwise.
 int gemm_launch(const GemmProblem& p, cudaStream_t stream);

@@ -2,6 +2,7 @@
 #include "kernels.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 #include "xlx_ptx.cuh"
 
@@ -528,289 +529,6 @@ __global__ void box_pack_kernel(const float* t, int H, float* dWp) {
   if (i < 4 * H) dWp[i] = t[(i & 3) * H + (i >> 2)];
 }
 
-// ---- attention core -----------------------------------------------------------------------------
-// CTA (128 threads) per (head, sample).  Thread (ti = tid/8, tj = tid%8) owns rows {ti + 16·ii} and, for
-// score-shaped tiles, columns {tj + 8·jj}; for [rows, 64]-shaped outputs, feature columns 4·tj.. and 32+4·tj..
-// All shared tiles are row-major with a 68-float pitch (float4 aligned, conflict-free for these patterns).
-constexpr int AT = 128;
-constexpr int LDS = 68;
-
-__device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ src, int ld, int rows, int rows_pad) {
-  // rows × 64 fp32 → dst[rows_pad][LDS], zero padded
-  for (int idx = threadIdx.x; idx < rows_pad * 16; idx += AT) {
-    const int r = idx >> 4, c4 = idx & 15;
-    float4 v = make_float4(0, 0, 0, 0);
-    if (r < rows) v = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(r) * ld) + c4);
-    *reinterpret_cast<float4*>(dst + r * LDS + c4 * 4) = v;
-  }
-}
-
-// acc[ii][jj] = Σ_d A[ti+16ii][d] · Bm[tj+8jj][d]   (A, Bm row-major tiles, contraction over 64 features)
-template <int NI, int NJ>
-__device__ __forceinline__ void tile_abt(const float* A, const float* Bm, int ti, int tj, float (&acc)[NI][NJ]) {
-#pragma unroll
-  for (int ii = 0; ii < NI; ++ii)
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) acc[ii][jj] = 0.f;
-#pragma unroll 4
-  for (int d = 0; d < 64; d += 4) {
-    float4 a[NI], b[NJ];
-#pragma unroll
-    for (int ii = 0; ii < NI; ++ii) a[ii] = *reinterpret_cast<const float4*>(A + (ti + 16 * ii) * LDS + d);
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) b[jj] = *reinterpret_cast<const float4*>(Bm + (tj + 8 * jj) * LDS + d);
-#pragma unroll
-    for (int ii = 0; ii < NI; ++ii)
-#pragma unroll
-      for (int jj = 0; jj < NJ; ++jj)
-        acc[ii][jj] += (a[ii].x * b[jj].x + a[ii].y * b[jj].y) + (a[ii].z * b[jj].z + a[ii].w * b[jj].w);
-  }
-}
-
-// out[r][c] (r = ti + 16·rr, 8 feature columns per thread) = Σ_{t < T} W[r][t] · X[t][c]
-template <int NR>
-__device__ __forceinline__ void tile_ab(const float* W, const float* X, int T, int ti, int tj, float4 (&o0)[NR],
-                                        float4 (&o1)[NR]) {
-#pragma unroll
-  for (int rr = 0; rr < NR; ++rr) { o0[rr] = make_float4(0, 0, 0, 0); o1[rr] = make_float4(0, 0, 0, 0); }
-  for (int t = 0; t < T; t += 4) {
-    float4 w[NR];
-#pragma unroll
-    for (int rr = 0; rr < NR; ++rr) w[rr] = *reinterpret_cast<const float4*>(W + (ti + 16 * rr) * LDS + t);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float4 x0 = *reinterpret_cast<const float4*>(X + (t + u) * LDS + 4 * tj);
-      const float4 x1 = *reinterpret_cast<const float4*>(X + (t + u) * LDS + 32 + 4 * tj);
-#pragma unroll
-      for (int rr = 0; rr < NR; ++rr) {
-        const float wv = u == 0 ? w[rr].x : u == 1 ? w[rr].y : u == 2 ? w[rr].z : w[rr].w;
-        o0[rr].x += wv * x0.x; o0[rr].y += wv * x0.y; o0[rr].z += wv * x0.z; o0[rr].w += wv * x0.w;
-        o1[rr].x += wv * x1.x; o1[rr].y += wv * x1.y; o1[rr].z += wv * x1.z; o1[rr].w += wv * x1.w;
-      }
-    }
-  }
-}
-
-template <int NI, int NJ>
-__global__ void __launch_bounds__(AT)
-attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int ld,
-                const float* __restrict__ mask, int heads, int Sq, int Sk, bf16* ctx_hi, bf16* ctx_lo, float* ctx_f32,
-                int ld_ctx, float* probs) {
-  extern __shared__ float sm[];
-  constexpr int RI = NI * 16, RJ = NJ * 8;
-  float* Qs = sm;                 // [RI][LDS]
-  float* Ks = Qs + RI * LDS;      // [RJ][LDS]
-  float* Vs = Ks + RJ * LDS;      // [RJ][LDS]
-  float* Ps = Vs + RJ * LDS;      // [RI][LDS]
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int ti = threadIdx.x >> 3, tj = threadIdx.x & 7;
-  const size_t qrow0 = static_cast<size_t>(b) * Sq, krow0 = static_cast<size_t>(b) * Sk;
-  load_tile(Qs, q + qrow0 * ld + h * 64, ld, Sq, RI);
-  load_tile(Ks, k + krow0 * ld + h * 64, ld, Sk, RJ);
-  load_tile(Vs, v + krow0 * ld + h * 64, ld, Sk, RJ);
-  __syncthreads();
-
-  float s[NI][NJ];
-  tile_abt<NI, NJ>(Qs, Ks, ti, tj, s);
-  float mk[NJ];
-#pragma unroll
-  for (int jj = 0; jj < NJ; ++jj) {
-    const int j = tj + 8 * jj;
-    mk[jj] = (j < Sk) ? (mask ? __ldg(mask + static_cast<size_t>(b) * Sk + j) : 0.f) : -INFINITY;
-  }
-#pragma unroll
-  for (int ii = 0; ii < NI; ++ii) {
-    float mx = -INFINITY;
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      s[ii][jj] = s[ii][jj] * 0.125f + mk[jj];   // scores / sqrt(64) then + mask (HF:255-259)
-      mx = fmaxf(mx, s[ii][jj]);
-    }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-    float sum = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) { s[ii][jj] = expf(s[ii][jj] - mx); sum += s[ii][jj]; }
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-    const float inv = 1.0f / sum;
-    const int i = ti + 16 * ii;
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      const float p = s[ii][jj] * inv;
-      const int j = tj + 8 * jj;
-      Ps[i * LDS + j] = p;
-      if (probs && i < Sq && j < Sk) probs[((static_cast<size_t>(b) * heads + h) * Sq + i) * Sk + j] = p;
-    }
-  }
-  __syncthreads();
-  float4 o0[NI], o1[NI];
-  tile_ab<NI>(Ps, Vs, RJ, ti, tj, o0, o1);
-#pragma unroll
-  for (int ii = 0; ii < NI; ++ii) {
-    const int i = ti + 16 * ii;
-    if (i < Sq) {
-      const size_t idx = (qrow0 + i) * ld_ctx + h * 64 + 4 * tj;
-      if (ctx_hi) { store_split4(ctx_hi, ctx_lo, idx, o0[ii]); store_split4(ctx_hi, ctx_lo, idx + 32, o1[ii]); }
-      if (ctx_f32) {
-        *reinterpret_cast<float4*>(ctx_f32 + idx) = o0[ii];
-        *reinterpret_cast<float4*>(ctx_f32 + idx + 32) = o1[ii];
-      }
-    }
-  }
-}
-
-// Backward of the attention core.  dP = dO·Vᵀ; dS = P ∘ (dP − rowsum(P ∘ dP)) / 8;
-// dV = Pᵀ·dO, dK = dSᵀ·Q, dQ = dS·K.
-template <int NI, int NJ>
-__global__ void __launch_bounds__(AT)
-attn_bwd_kernel(const float* __restrict__ dctx, int ld_dctx, const float* __restrict__ q, const float* __restrict__ k,
-                const float* __restrict__ v, int ld, const float* __restrict__ probs, int heads, int Sq, int Sk,
-                bf16* dq_hi, bf16* dq_lo, bf16* dk_hi, bf16* dk_lo, bf16* dv_hi, bf16* dv_lo, int ld_d) {
-  extern __shared__ float sm[];
-  constexpr int RI = NI * 16, RJ = NJ * 8;
-  constexpr int RJ16 = ((RJ + 15) / 16) * 16;   // dK/dV rows are produced with the 16-row thread pattern
-  constexpr int NRJ = RJ16 / 16;
-  float* Qs = sm;                    // [RI][LDS]
-  float* Ks = Qs + RI * LDS;         // [RJ][LDS]
-  float* VPt = Ks + RJ * LDS;        // V [RJ][LDS], later Pᵀ [RJ16][LDS]
-  float* dOs = VPt + RJ16 * LDS;     // [RI][LDS]
-  float* dSs = dOs + RI * LDS;       // [RI][LDS]
-  float* dSt = dSs + RI * LDS;       // [RJ16][LDS]
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int ti = threadIdx.x >> 3, tj = threadIdx.x & 7;
-  const size_t qrow0 = static_cast<size_t>(b) * Sq, krow0 = static_cast<size_t>(b) * Sk;
-  load_tile(Qs, q + qrow0 * ld + h * 64, ld, Sq, RI);
-  load_tile(Ks, k + krow0 * ld + h * 64, ld, Sk, RJ);
-  load_tile(VPt, v + krow0 * ld + h * 64, ld, Sk, RJ);
-  load_tile(dOs, dctx + qrow0 * ld_dctx + h * 64, ld_dctx, Sq, RI);
-  __syncthreads();
-
-  float dp[NI][NJ];
-  tile_abt<NI, NJ>(dOs, VPt, ti, tj, dp);
-  float p[NI][NJ];
-#pragma unroll
-  for (int ii = 0; ii < NI; ++ii) {
-    const int i = ti + 16 * ii;
-    float dot = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      const int j = tj + 8 * jj;
-      p[ii][jj] = (i < Sq && j < Sk) ? __ldg(probs + ((static_cast<size_t>(b) * heads + h) * Sq + i) * Sk + j) : 0.f;
-      dot += p[ii][jj] * dp[ii][jj];
-    }
-    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) dp[ii][jj] = p[ii][jj] * (dp[ii][jj] - dot) * 0.125f;   // now dS
-  }
-  __syncthreads();   // everyone is done reading V
-  for (int idx = threadIdx.x; idx < (RJ16 - RJ) * LDS; idx += AT) {   // zero the padding rows of the transposed tiles
-    VPt[RJ * LDS + idx] = 0.f;
-    dSt[RJ * LDS + idx] = 0.f;
-  }
-#pragma unroll
-  for (int ii = 0; ii < NI; ++ii) {
-    const int i = ti + 16 * ii;
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      const int j = tj + 8 * jj;
-      dSs[i * LDS + j] = dp[ii][jj];
-      dSt[j * LDS + i] = dp[ii][jj];
-      VPt[j * LDS + i] = p[ii][jj];
-    }
-  }
-  __syncthreads();
-  {
-    float4 o0[NRJ], o1[NRJ];
-    tile_ab<NRJ>(VPt, dOs, RI, ti, tj, o0, o1);     // dV = Pᵀ · dO
-#pragma unroll
-    for (int rr = 0; rr < NRJ; ++rr) {
-      const int j = ti + 16 * rr;
-      if (j < Sk) {
-        const size_t idx = (krow0 + j) * ld_d + h * 64 + 4 * tj;
-        store_split4(dv_hi, dv_lo, idx, o0[rr]); store_split4(dv_hi, dv_lo, idx + 32, o1[rr]);
-      }
-    }
-    tile_ab<NRJ>(dSt, Qs, RI, ti, tj, o0, o1);      // dK = dSᵀ · Q
-#pragma unroll
-    for (int rr = 0; rr < NRJ; ++rr) {
-      const int j = ti + 16 * rr;
-      if (j < Sk) {
-        const size_t idx = (krow0 + j) * ld_d + h * 64 + 4 * tj;
-        store_split4(dk_hi, dk_lo, idx, o0[rr]); store_split4(dk_hi, dk_lo, idx + 32, o1[rr]);
-      }
-    }
-  }
-  {
-    float4 o0[NI], o1[NI];
-    tile_ab<NI>(dSs, Ks, RJ, ti, tj, o0, o1);       // dQ = dS · K
-#pragma unroll
-    for (int ii = 0; ii < NI; ++ii) {
-      const int i = ti + 16 * ii;
-      if (i < Sq) {
-        const size_t idx = (qrow0 + i) * ld_d + h * 64 + 4 * tj;
-        store_split4(dq_hi, dq_lo, idx, o0[ii]); store_split4(dq_hi, dq_lo, idx + 32, o1[ii]);
-      }
-    }
-  }
-}
-
-template <int NI, int NJ>
-int attn_fwd_launch(const float* q, const float* k, const float* v, int ld, const float* mask, int B, int heads, int Sq,
-                    int Sk, Split ctx, float* ctx_f32, int ld_ctx, float* probs, cudaStream_t s) {
-  constexpr size_t smem = static_cast<size_t>(2 * NI * 16 + 2 * NJ * 8) * LDS * sizeof(float);
-  static bool set = false;
-  if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<NI, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    set = true;
-  }
-  attn_fwd_kernel<NI, NJ><<<dim3(heads, B), AT, smem, s>>>(q, k, v, ld, mask, heads, Sq, Sk, ctx.hi, ctx.lo, ctx_f32,
-                                                           ld_ctx, probs);
-  return launch_rc();
-}
-template <int NI, int NJ>
-int attn_bwd_launch(const float* dctx, int ld_dctx, const float* q, const float* k, const float* v, int ld,
-                    const float* probs, int B, int heads, int Sq, int Sk, Split dq, Split dk, Split dv, int ld_d,
-                    cudaStream_t s) {
-  constexpr int RI = NI * 16, RJ = NJ * 8, RJ16 = ((RJ + 15) / 16) * 16;
-  constexpr size_t smem = static_cast<size_t>(3 * RI + RJ + 2 * RJ16) * LDS * sizeof(float);
-  static bool set = false;
-  if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<NI, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    set = true;
-  }
-  attn_bwd_kernel<NI, NJ><<<dim3(heads, B), AT, smem, s>>>(dctx, ld_dctx, q, k, v, ld, probs, heads, Sq, Sk, dq.hi,
-                                                           dq.lo, dk.hi, dk.lo, dv.hi, dv.lo, ld_d);
-  return launch_rc();
-}
-
-// pick the smallest instantiated (NI, NJ) ∈ {2,3,4} × {3,5,8} covering (Sq, Sk)
-#define XLX_ATTN_DISPATCH(FN, ...)                                             \
-  do {                                                                         \
-    const int ni = (Sq + 15) / 16, nj = (Sk + 7) / 8;                          \
-    if (ni <= 2) {                                                             \
-      if (nj <= 3) return FN<2, 3>(__VA_ARGS__);                               \
-      if (nj <= 5) return FN<2, 5>(__VA_ARGS__);                               \
-      return FN<2, 8>(__VA_ARGS__);                                            \
-    } else if (ni <= 3) {                                                      \
-      if (nj <= 3) return FN<3, 3>(__VA_ARGS__);                               \
-      if (nj <= 5) return FN<3, 5>(__VA_ARGS__);                               \
-      return FN<3, 8>(__VA_ARGS__);                                            \
-    } else {                                                                   \
-      if (nj <= 3) return FN<4, 3>(__VA_ARGS__);                               \
-      if (nj <= 5) return FN<4, 5>(__VA_ARGS__);                               \
-      return FN<4, 8>(__VA_ARGS__);                                            \
-    }                                                                          \
-  } while (0)
-
 }  // namespace
 
 long long aux_launch_count() { return g_aux_launches.load(); }
@@ -1009,20 +727,6 @@ int box_linear_bwd(const float* dy2, const float* pos, int M, int H, float* scra
   return launch_rc();
 }
 
-int attention_fwd(const float* q, const float* k, const float* v, int ld, const float* mask, int B, int heads,
-                  int Sq, int Sk, Split ctx, float* ctx_f32, int ld_ctx, float* probs, cudaStream_t s) {
-  if (Sq < 1 || Sk < 1 || Sq > 64 || Sk > 64) return -5;
-  if ((ld % 4) || (ld_ctx % 4)) return -2;
-  if (!B) return 0;
-  XLX_ATTN_DISPATCH(attn_fwd_launch, q, k, v, ld, mask, B, heads, Sq, Sk, ctx, ctx_f32, ld_ctx, probs, s);
-}
-int attention_bwd(const float* dctx, int ld_dctx, const float* q, const float* k, const float* v, int ld,
-                  const float* probs, int B, int heads, int Sq, int Sk, Split dq, Split dk, Split dv, int ld_d,
-                  cudaStream_t s) {
-  if (Sq < 1 || Sk < 1 || Sq > 64 || Sk > 64) return -5;
-  if ((ld % 4) || (ld_d % 4) || (ld_dctx % 4)) return -2;
-  if (!B) return 0;
-  XLX_ATTN_DISPATCH(attn_bwd_launch, dctx, ld_dctx, q, k, v, ld, probs, B, heads, Sq, Sk, dq, dk, dv, ld_d, s);
-}
+void count_aux_launch() { g_aux_launches.fetch_add(1, std::memory_order_relaxed); }
 
 }  // namespace xlx

@@ -98,17 +98,21 @@ int box_linear_fwd(const float* pos, const float* Wp, const float* bp, int M, in
 int box_linear_bwd(const float* dy2, const float* pos, int M, int H, float* scratch, float* dWp, float* dbp,
                    cudaStream_t s);
 
-// Attention core, LxmertAttention.forward (HF:238-274) after the projections, head_dim 64:
+// Attention core, LxmertAttention.forward (HF:238-274) after the projections, head_dim 64 (attention.cu):
 //   P = softmax(Q·Kᵀ/8 + mask), ctx = P·V per (sample, head).
-// q/k/v: fp32 matrices with row stride ld (elements); sample b's query rows are b*Sq.., key/value rows b*Sk..;
-// head h occupies columns [h*64, h*64+64).  mask: additive fp32 [B, Sk] or null.  Sq, Sk ≤ 64.
-// ctx: split and/or fp32 rows [b*Sq + i, h*64 + d] with leading dimension ld_ctx.  probs (optional) [B,heads,Sq,Sk].
-int attention_fwd(const float* q, const float* k, const float* v, int ld, const float* mask, int B, int heads,
-                  int Sq, int Sk, Split ctx, float* ctx_f32, int ld_ctx, float* probs, cudaStream_t s);
-// Backward: dctx fp32 [B*Sq, ld_dctx]; writes dq (rows b*Sq+i), dk/dv (rows b*Sk+j), columns h*64+d, as split
-// matrices with leading dimension ld_d.
-int attention_bwd(const float* dctx, int ld_dctx, const float* q, const float* k, const float* v, int ld,
-                  const float* probs, int B, int heads, int Sq, int Sk, Split dq, Split dk, Split dv, int ld_d,
-                  cudaStream_t s);
+// An operand is a split-bf16 matrix [rows, ld]; sample b uses rows b·S.. and head h the columns col + h·64 ..
+struct AttnOperand {
+  Split base;
+  int ld = 0, rows = 0, col = 0;
+};
+// mask: additive fp32 [B, Sk] or null.  Sq, Sk ≤ 64.  ctx: split and/or fp32 rows [b·Sq + i, h·64 + d] with leading
+// dimension ld_ctx.  probs (optional) [B, heads, Sq, Sk] fp32.
+int attention_fwd(AttnOperand q, AttnOperand k, AttnOperand v, const float* mask, int B, int heads, int Sq, int Sk,
+                  Split ctx, float* ctx_f32, int ld_ctx, float* probs, cudaStream_t s);
+// Backward: dctx = gradient wrt ctx (an operand like q); writes dq (rows b·Sq + i), dk / dv (rows b·Sk + j), columns
+// h·64 + d, as split matrices with leading dimension ld_d.
+int attention_bwd(AttnOperand dctx, AttnOperand q, AttnOperand k, AttnOperand v, const float* probs, int B, int heads,
+                  int Sq, int Sk, Split dq, Split dk, Split dv, int ld_d, cudaStream_t s);
+void count_aux_launch();
 
 }  // namespace xlx
