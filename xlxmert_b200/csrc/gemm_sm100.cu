@@ -21,8 +21,10 @@ constexpr int BM = 128;            // UMMA M (one TMEM lane per output row)
 #endif
 constexpr int EPI_WARPS = XLX_EPI_WARPS;  // EPI_WARPS/4 warps per TMEM lane quadrant, alternating 32-column chunks
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;  // warp 0: TMA, warp 1: MMA, then the epilogue warps
-constexpr int STAGE_PITCH = 36;    // floats per staged row: 16-byte aligned, conflict-free for both phases
-constexpr int STAGE_BYTES = EPI_WARPS * 32 * STAGE_PITCH * 4;
+constexpr int EPI_COLS = 16;       // accumulator columns per epilogue step (one tcgen05.ld.32x32b.x16)
+// Per-warp transpose buffer: 32 rows × 16 fp32, no padding; the 16-byte chunk index is XOR-ed with (row >> 1) & 3,
+// which makes both the row-wise writes and the 4-lanes-per-row reads bank-conflict free.
+constexpr int STAGE_BYTES = EPI_WARPS * 32 * EPI_COLS * 4;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA on sm_100
 
@@ -39,6 +41,7 @@ struct KParams {
   int kb_per_split;    // k-blocks per split (last split may be shorter)
   float* part;         // [splits][M][N] fp32 partial sums when splits > 1
   int conv, conv_H, conv_W, conv_taps, conv_kb_per_tap;   // implicit-GEMM convolution (see ConvGeometry)
+  int debug;           // XLX_GEMM_DEBUG bit 0: skip the epilogue's global traffic (mainloop-only timing experiments)
   GemmEpilogue epi;
 };
 
@@ -49,9 +52,10 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// Epilogue on 4 consecutive columns of one output row.  Called in the "coalesced domain": the 8 lanes of a
-// quarter warp hold 32 consecutive columns of the same row, so every global access below is a full 128-byte
-// (fp32) or 64-byte (bf16) segment.
+// Epilogue on 4 consecutive columns of one output row.  Called in the "coalesced domain": 4 adjacent lanes hold 16
+// consecutive columns of the same row, so every global access below covers whole 32-byte sectors (64-byte fp32 /
+// 32-byte bf16 segments per row).
+template <bool ACT>
 __device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, float4 acc) {
   const GemmEpilogue& E = P.epi;
   float v[4] = {acc.x * E.alpha, acc.y * E.alpha, acc.z * E.alpha, acc.w * E.alpha};
@@ -59,7 +63,7 @@ __device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, 
     const float4 b = __ldg(reinterpret_cast<const float4*>(E.bias + n));
     v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
   }
-  if (E.flags & EPI_GELU) {
+  if (ACT && (E.flags & EPI_GELU)) {
     float dg[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -74,15 +78,15 @@ __device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, 
   } else if (E.out_u) {
     *reinterpret_cast<float4*>(E.out_u + static_cast<size_t>(row) * E.ld_u + n) = make_float4(v[0], v[1], v[2], v[3]);
   }
-  if (E.flags & EPI_TANH) {
+  if (ACT && (E.flags & EPI_TANH)) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = tanhf(v[j]);
   }
-  if (E.flags & EPI_RELU) {
+  if (ACT && (E.flags & EPI_RELU)) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
   }
-  if (E.flags & EPI_GELU_GRAD) {
+  if (ACT && (E.flags & EPI_GELU_GRAD)) {
     const float4 u = __ldg(reinterpret_cast<const float4*>(E.u_in + static_cast<size_t>(row) * E.ld_u + n));
     v[0] *= gelu_erf_grad(u.x); v[1] *= gelu_erf_grad(u.y); v[2] *= gelu_erf_grad(u.z); v[3] *= gelu_erf_grad(u.w);
   }
@@ -124,7 +128,9 @@ __device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, 
 
 // A_MN / B_MN: operand stored MN-major; NPARTS: 1 = hi only (1 pass), 2 = hi + lo (3 passes).  Compile-time so that
 // the single MMA-issuing thread's loop is a handful of integer adds per tcgen05.mma (it is the critical path).
-template <int BK, int A_MN, int B_MN, int NPARTS>
+// ACT: the epilogue may contain an activation (GeLU / tanh / ReLU / gelu-grad); kept out of the other instantiations so
+// that their code stays small — the epilogue warps share the instruction cache with the MMA-issuing warp.
+template <int BK, int A_MN, int B_MN, int NPARTS, bool ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
             const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
@@ -191,7 +197,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
           const uint32_t full = smem_u32(&bar_full[s]);
-          mbar_arrive_expect_tx(full, P.stage_bytes);
+          mbar_arrive_expect_tx(full, (P.debug & 64) ? P.stage_bytes - P.b_part_bytes : P.stage_bytes);
           const uint32_t sA = smem_base + s * P.stage_bytes;
           const uint32_t sB = sA + NPARTS * P.a_part_bytes;
           const int k0 = kb * BK;
@@ -212,7 +218,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j) tma_load_2d(dA + j * (BK * 128), ma, full, m0 + 64 * j, k0);
             }
-            if (!B_MN) {
+            if ((P.debug & 64) && part == 1) {
+              // experiment: skip the B_lo load (results are wrong; measures sensitivity to operand traffic)
+            } else if (!B_MN) {
               tma_load_2d(dB, mb, full, k0, n0);
             } else {
               for (int j = 0; j < P.BN / 64; ++j) tma_load_2d(dB + j * (BK * 128), mb, full, n0 + 64 * j, k0);
@@ -277,14 +285,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue warps =====================
-    // TMEM → registers (thread = row) → shared-memory transpose → coalesced global traffic (quarter warp = 128 B
-    // of one row).  Warps e and e + 4 share TMEM lane quadrant q = warp % 4 and alternate 32-column chunks.
+    // TMEM → registers (thread = row) → shared-memory transpose → coalesced global traffic (4 lanes = 64 B of one
+    // row, 8 rows per instruction).  The EPI_WARPS/4 warps sharing TMEM lane quadrant q = warp % 4 alternate
+    // EPI_COLS-column chunks.
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int e = warp - 2;                 // epilogue warp index 0 … EPI_WARPS-1
     const int half = e >> 2;                // which of the EPI_WARPS/4 warps of the quadrant
     float* stage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + P.num_stages * P.stage_bytes) +
-                   e * 32 * STAGE_PITCH;
-    const int sub = lane >> 3, cq = lane & 7;
+                   e * 32 * EPI_COLS;
+    const int sub = lane >> 2, cq = lane & 3;
     int local = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int tile = item % num_tiles, split = item / num_tiles;
@@ -295,42 +304,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
       mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * P.BN;
-      const int nchunks = P.BN / 32;
-      // last chunk this warp will read (chunks beyond N are skipped by both warps alike)
+      const int nchunks = P.BN / EPI_COLS;
+      // last chunk this warp will read (chunks beyond N are skipped)
       int last_c = -1;
       for (int c = half; c < nchunks; c += EPI_WARPS / 4)
-        if (n0 + c * 32 < P.N) last_c = c;
+        if (n0 + c * EPI_COLS < P.N) last_c = c;
       if (last_c < 0) {   // nothing to read from this accumulator: hand it back right away
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
       }
       for (int c = half; c <= last_c; c += EPI_WARPS / 4) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
+        uint32_t r[EPI_COLS];
+        tmem_ld_32x16(taddr + c * EPI_COLS, r);
         tmem_ld_wait();
         if (c == last_c) {  // accumulator fully read by this warp: release before the global traffic
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
         }
+        if (P.debug & 1) continue;
+        const int wsw = (lane >> 1) & 3;
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<float4*>(stage + lane * STAGE_PITCH + g * 4) =
+        for (int g = 0; g < EPI_COLS / 4; ++g)
+          *reinterpret_cast<float4*>(stage + lane * EPI_COLS + ((g ^ wsw) << 2)) =
               make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]),
                           __uint_as_float(r[g * 4 + 3]));
         __syncwarp();
-        const int n = n0 + c * 32 + cq * 4;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + sub;
+        const int n = n0 + c * EPI_COLS + cq * 4;
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + sub;
           const int row = m0 + q * 32 + rr;
-          const float4 acc = *reinterpret_cast<const float4*>(stage + rr * STAGE_PITCH + cq * 4);
+          const float4 acc = *reinterpret_cast<const float4*>(stage + rr * EPI_COLS + ((cq ^ ((rr >> 1) & 3)) << 2));
           if (row < P.M && n < P.N) {
             if (P.splits > 1)   // raw partial sums; the reduce kernel finishes the job
               *reinterpret_cast<float4*>(P.part + (static_cast<size_t>(split) * P.M + row) * P.N + n) = acc;
             else
-              epilogue_vec4(P, row, n, acc);
+              epilogue_vec4<ACT>(P, row, n, acc);
           }
         }
         __syncwarp();
@@ -489,17 +500,17 @@ int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
-template <int BK, int A_MN, int B_MN, int NPARTS>
+template <int BK, int A_MN, int B_MN, int NPARTS, bool ACT>
 int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& mAhi, const CUtensorMap& mAlo,
                    const CUtensorMap& mBhi, const CUtensorMap& mBlo, const KParams& P) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BK, A_MN, B_MN, NPARTS>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BK, A_MN, B_MN, NPARTS, ACT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  gemm_kernel<BK, A_MN, B_MN, NPARTS><<<grid, GEMM_THREADS, smem, stream>>>(mAhi, mAlo, mBhi, mBlo, P);
+  gemm_kernel<BK, A_MN, B_MN, NPARTS, ACT><<<grid, GEMM_THREADS, smem, stream>>>(mAhi, mAlo, mBhi, mBlo, P);
   return 0;
 }
 
@@ -534,6 +545,8 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   while (cols < static_cast<uint32_t>(2 * BN)) cols <<= 1;
   P.tmem_cols = cols;
   P.epi = p.epi;
+  static const int debug = env_int("XLX_GEMM_DEBUG", 0);
+  P.debug = debug;
 
   CUtensorMap mAhi, mAlo, mBhi, mBlo;
   const CUtensorMapSwizzle swzK = (BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -615,18 +628,23 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     cudaEventRecord(tl.e0, stream);
   }
   {
+    const bool act = (p.epi.flags & (EPI_GELU | EPI_TANH | EPI_RELU | EPI_GELU_GRAD)) != 0;
     const int v = (P.a_mn ? 4 : 0) | (P.b_mn ? 2 : 0) | (P.nparts == 2 ? 1 : 0);
     int lrc = 0;
+#define XLX_LAUNCH(A, B, N)                                                                                   \
+  lrc = act ? launch_variant<BK, A, B, N, true>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P)                \
+            : launch_variant<BK, A, B, N, false>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P)
     switch (v) {
-      case 0: lrc = launch_variant<BK, 0, 0, 1>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
-      case 1: lrc = launch_variant<BK, 0, 0, 2>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
-      case 2: lrc = launch_variant<BK, 0, 1, 1>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
-      case 3: lrc = launch_variant<BK, 0, 1, 2>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
-      case 4: lrc = launch_variant<BK, 1, 0, 1>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
-      case 5: lrc = launch_variant<BK, 1, 0, 2>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
-      case 6: lrc = launch_variant<BK, 1, 1, 1>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
-      default: lrc = launch_variant<BK, 1, 1, 2>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P); break;
+      case 0: XLX_LAUNCH(0, 0, 1); break;
+      case 1: XLX_LAUNCH(0, 0, 2); break;
+      case 2: XLX_LAUNCH(0, 1, 1); break;
+      case 3: XLX_LAUNCH(0, 1, 2); break;
+      case 4: XLX_LAUNCH(1, 0, 1); break;
+      case 5: XLX_LAUNCH(1, 0, 2); break;
+      case 6: XLX_LAUNCH(1, 1, 1); break;
+      default: XLX_LAUNCH(1, 1, 2); break;
     }
+#undef XLX_LAUNCH
     if (lrc) return lrc;
   }
   if (P.splits > 1) {
