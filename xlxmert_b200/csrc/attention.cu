@@ -20,8 +20,6 @@ namespace xlx {
 namespace {
 
 constexpr int AT = 128;      // threads per CTA
-constexpr int PITCH = 72;    // bf16 elements per row of the kernel-written tiles (P, dS): 144 B, conflict-free fragments
-constexpr int TILE = 64 * PITCH;
 constexpr int TT = 64 * 64;  // elements of a TMA-written tile: 64 rows × 128 B, 128-byte swizzle, 1024-byte aligned
 
 // element (row r, column k) of a TMA tile: the 16-byte chunk index is XOR-ed with the row index modulo 8
@@ -59,10 +57,10 @@ __device__ __forceinline__ void load_b(uint32_t& b0, uint32_t& b1, const bf16* Y
   b0 = lds32(Y + swz(n0 + g, k0 + 2 * t));
   b1 = lds32(Y + swz(n0 + g, k0 + 2 * t + 8));
 }
-// A fragment of the TRANSPOSE of a pitch-PITCH tile S[k][m] (written by this kernel): rows m0.., columns k0..
+// A fragment of the TRANSPOSE of a swizzled tile S[k][m]: rows m0.., columns k0..
 __device__ __forceinline__ void load_a_trans(uint32_t (&a)[4], const bf16* S, int m0, int k0, int lane) {
   const int mat = lane >> 3, i = lane & 7;
-  const bf16* p = S + (k0 + (mat >> 1) * 8 + i) * PITCH + m0 + (mat & 1) * 8;
+  const bf16* p = S + swz(k0 + (mat >> 1) * 8 + i, m0 + (mat & 1) * 8);
   ldsm_x4_trans(a, smem_u32(p));
 }
 // B fragments of two adjacent n-tiles (n0, n0 + 8) from a swizzled tile Z[k][n] (k0..k0+15): r[0..1] → n0, r[2..3] → n0+8
@@ -263,10 +261,11 @@ attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, in
   bf16* Vl = Vh + TT;
   bf16* Oh = Vl + TT;        // dO
   bf16* Ol = Oh + TT;
-  bf16* Ph = Ol + TT;        // P  [query][key], pitch PITCH (written here)
-  bf16* Pl = Ph + TILE;
-  bf16* Sh = Pl + TILE;      // dS [query][key]
-  bf16* Sl = Sh + TILE;
+  // P and dS ([query][key], same swizzled layout) overlay the V and K tiles once phase 1 no longer needs them
+  bf16* Ph = Vh;
+  bf16* Pl = Vl;
+  bf16* Sh = Kh;
+  bf16* Sl = Kl;
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const size_t qrow0 = static_cast<size_t>(b) * Sq, krow0 = static_cast<size_t>(b) * Sk;
@@ -282,11 +281,15 @@ attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, in
   const int nk16 = (Sk + 15) >> 4, nq16 = (Sq + 15) >> 4;
   const int i0 = r0 + g, i1 = r0 + g + 8;
 
-  // phase 1 (warp = 16 query rows): dP, dS, dQ; P and dS go to shared memory for the transposed products
-  float dp[8][4];
+  // phase 1 (warp = 16 query rows): dP = dO·Vᵀ, dS, dQ = dS·K, all in registers
+  float dp[8][4], p[8][4];
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) { dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f; }
-  if (r0 < 16 * nq16) {
+  for (int nt = 0; nt < 8; ++nt) {
+    dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+    p[nt][0] = p[nt][1] = p[nt][2] = p[nt][3] = 0.f;
+  }
+  const bool rows_live = r0 < 16 * nq16;
+  if (rows_live) {
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       uint32_t ah[4], al[4];
@@ -302,7 +305,6 @@ attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, in
         }
       }
     }
-    float p[8][4];
     float dot0 = 0.f, dot1 = 0.f;
     const float* pr = probs + (static_cast<size_t>(b) * heads + h) * Sq * Sk;
 #pragma unroll
@@ -326,16 +328,6 @@ attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, in
         dp[nt][1] = p[nt][1] * (dp[nt][1] - dot0) * 0.125f;
         dp[nt][2] = p[nt][2] * (dp[nt][2] - dot1) * 0.125f;
         dp[nt][3] = p[nt][3] * (dp[nt][3] - dot1) * 0.125f;
-        const int j = nt * 8 + 2 * t;
-        uint32_t hi, lo;
-        split2(p[nt][0], p[nt][1], hi, lo);
-        *reinterpret_cast<uint32_t*>(Ph + i0 * PITCH + j) = hi; *reinterpret_cast<uint32_t*>(Pl + i0 * PITCH + j) = lo;
-        split2(p[nt][2], p[nt][3], hi, lo);
-        *reinterpret_cast<uint32_t*>(Ph + i1 * PITCH + j) = hi; *reinterpret_cast<uint32_t*>(Pl + i1 * PITCH + j) = lo;
-        split2(dp[nt][0], dp[nt][1], hi, lo);
-        *reinterpret_cast<uint32_t*>(Sh + i0 * PITCH + j) = hi; *reinterpret_cast<uint32_t*>(Sl + i0 * PITCH + j) = lo;
-        split2(dp[nt][2], dp[nt][3], hi, lo);
-        *reinterpret_cast<uint32_t*>(Sh + i1 * PITCH + j) = hi; *reinterpret_cast<uint32_t*>(Sl + i1 * PITCH + j) = lo;
       }
     }
     // dQ = dS·K
@@ -375,10 +367,23 @@ attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, in
         *reinterpret_cast<uint32_t*>(dq_lo + (qrow0 + i1) * ld_d + c) = lo;
       }
     }
-  } else {
-    // rows of P / dS beyond the staged queries must read as zero in phase 2
-    for (int idx = lane; idx < 16 * PITCH; idx += 32) {
-      Ph[r0 * PITCH + idx] = Pl[r0 * PITCH + idx] = Sh[r0 * PITCH + idx] = Sl[r0 * PITCH + idx] = __float2bfloat16(0.f);
+  }
+  __syncthreads();     // every warp is done with the V and K tiles: P and dS may overwrite them
+  if (rows_live) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      if (nt < 2 * nk16) {
+        const int j = nt * 8 + 2 * t;
+        uint32_t hi, lo;
+        split2(p[nt][0], p[nt][1], hi, lo);
+        *reinterpret_cast<uint32_t*>(Ph + swz(i0, j)) = hi; *reinterpret_cast<uint32_t*>(Pl + swz(i0, j)) = lo;
+        split2(p[nt][2], p[nt][3], hi, lo);
+        *reinterpret_cast<uint32_t*>(Ph + swz(i1, j)) = hi; *reinterpret_cast<uint32_t*>(Pl + swz(i1, j)) = lo;
+        split2(dp[nt][0], dp[nt][1], hi, lo);
+        *reinterpret_cast<uint32_t*>(Sh + swz(i0, j)) = hi; *reinterpret_cast<uint32_t*>(Sl + swz(i0, j)) = lo;
+        split2(dp[nt][2], dp[nt][3], hi, lo);
+        *reinterpret_cast<uint32_t*>(Sh + swz(i1, j)) = hi; *reinterpret_cast<uint32_t*>(Sl + swz(i1, j)) = lo;
+      }
     }
   }
   __syncthreads();
@@ -476,7 +481,7 @@ int attention_bwd(AttnOperand dctx, AttnOperand q, AttnOperand k, AttnOperand v,
   if (Sq < 1 || Sk < 1 || Sq > 64 || Sk > 64) return -5;
   if (!operand_ok(q) || !operand_ok(k) || !operand_ok(v) || !operand_ok(dctx) || (ld_d % 2)) return -2;
   if (!B) return 0;
-  constexpr size_t smem = (8 * TT + 4 * TILE) * sizeof(bf16) + 1024;
+  constexpr size_t smem = 8 * TT * sizeof(bf16) + 1024;
   static bool set = false;
   if (!set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

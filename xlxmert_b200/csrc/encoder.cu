@@ -134,7 +134,7 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
   p.att.resize(nl + nr + 3 * nx);
   p.ffn.resize(nl + nr + 2 * nx);
 
-  size_t pe = 2 * static_cast<size_t>(reduce_max_blocks()) * H;
+  size_t pe = 3 * static_cast<size_t>(reduce_max_blocks()) * H;
   size_t widest = 3 * H > I ? 3 * H : I;
   if (F > widest) widest = F;
   if (128 * widest > pe) pe = 128 * widest;
@@ -369,13 +369,15 @@ struct Bwd {
   float* G(int slot) const { return grads + slots.offset[slot]; }
 };
 
+// LayerNorm backward of a "dense → +residual → LayerNorm" tail; also yields the dense bias gradient (slot_g − 1),
+// which is the column sum of the LayerNorm-input gradient.
 int ln_tail_bwd(const Bwd& bw, const float* dout, const float* y, int slot_g, const float* mean, const float* rstd,
                 int M, float* dy, Split dy_s) {
   const Run& r = *bw.r;
   int nblk = 0;
   XLX_TRY(layernorm_bwd(dout, 1.0f, y, P(r, slot_g), mean, rstd, M, r.plan.H, dy, dy_s, r.plan.part, &nblk, r.st));
-  float* outs[2] = {bw.G(slot_g), bw.G(slot_g + 1)};
-  return colsum_finish(r.plan.part, 2, nblk, r.plan.H, outs, 0, r.st);
+  float* outs[3] = {bw.G(slot_g), bw.G(slot_g + 1), bw.G(slot_g - 1)};
+  return colsum_finish(r.plan.part, 3, nblk, r.plan.H, outs, 0, r.st);
 }
 
 int ffn_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
@@ -384,8 +386,7 @@ int ffn_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
   const FfnSave& f = p.ffn[blk];
   const FfnW& w = r.prep.ffn[blk];
   const int s0 = ffn_slot(r.d, blk), H = p.H, I = p.I, M = f.M;
-  XLX_TRY(ln_tail_bwd(bw, dout, f.y, s0 + 4, f.mean, f.rstd, M, p.dy, p.dy_s));
-  XLX_TRY(colsum(p.dy, Split(), M, H, H, p.part, bw.G(s0 + 3), r.st));
+  XLX_TRY(ln_tail_bwd(bw, dout, f.y, s0 + 4, f.mean, f.rstd, M, p.dy, p.dy_s));    // also dense bias grad (s0 + 3)
   XLX_TRY(wgrad(r, p.dy_s, M, H, f.h, I, bw.G(s0 + 2)));
   GemmEpilogue e;   // du = (dy · W2) ∘ gelu'(u), the derivative was saved by the forward
   e.flags = EPI_MUL; e.u_in = f.u; e.ld_u = I; e.out_hi = p.du.hi; e.out_lo = p.du.lo; e.ld_split = I;
@@ -404,8 +405,7 @@ int att_bwd_head(const Bwd& bw, int blk, const float* dout) {
   const AttSave& a = p.att[blk];
   const AttW& w = r.prep.att[blk];
   const int s0 = att_slot(r.d, blk), H = p.H, M = a.M;
-  XLX_TRY(ln_tail_bwd(bw, dout, a.y, s0 + 8, a.mean, a.rstd, M, p.dy, p.dy_s));
-  XLX_TRY(colsum(p.dy, Split(), M, H, H, p.part, bw.G(s0 + 7), r.st));
+  XLX_TRY(ln_tail_bwd(bw, dout, a.y, s0 + 8, a.mean, a.rstd, M, p.dy, p.dy_s));    // also dense bias grad (s0 + 7)
   XLX_TRY(wgrad(r, p.dy_s, M, H, a.ctx, H, bw.G(s0 + 6)));
   GemmEpilogue e;
   e.out_hi = p.dctx.hi; e.out_lo = p.dctx.lo; e.ld_split = H;
@@ -684,9 +684,8 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
     XLX_TRY(box_linear_bwd(p.dy2, visual_pos, Mv, H, p.part, bw.G(4), bw.G(5), r.st));
     // feature branch: d(0.5·LN_v(y1))
     XLX_TRY(layernorm_bwd(dvis, 0.5f, p.y1, P(r, 2), p.vstats, p.vstats + Mv, Mv, H, p.dy, p.dy_s, p.part, &nblk, r.st));
-    float* o1[2] = {bw.G(2), bw.G(3)};
-    XLX_TRY(colsum_finish(p.part, 2, nblk, H, o1, 0, r.st));
-    XLX_TRY(colsum(p.dy, Split(), Mv, H, H, p.part, bw.G(1), r.st));
+    float* o1[3] = {bw.G(2), bw.G(3), bw.G(1)};      // LN affine grads + visn_fc bias grad (Σ_rows of the LN-input grad)
+    XLX_TRY(colsum_finish(p.part, 3, nblk, H, o1, 0, r.st));
     XLX_TRY(wgrad(r, p.dy_s, Mv, H, p.feats, F, bw.G(0)));
     if (d_visual_feats) {
       GemmEpilogue e;

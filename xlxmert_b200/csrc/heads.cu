@@ -80,7 +80,7 @@ HeadWs head_ws_layout(const HeadDims& h, int M, void* base) {
   w.dt = b.f32(m * H);
   w.dg = b.f32(m * H);
   w.du = b.split(m * H);
-  size_t pe = 2 * static_cast<size_t>(reduce_max_blocks()) * H;
+  size_t pe = 3 * static_cast<size_t>(reduce_max_blocks()) * H;
   const size_t widest = Cp > F ? Cp : F;
   if (128 * widest > pe) pe = 128 * widest;
   w.part = b.f32(pe);
@@ -219,7 +219,7 @@ size_t xlx_embeddings_save_bytes(const xlx_dims* d, int32_t B, int32_t L) {
 }
 size_t xlx_embeddings_scratch_bytes(const xlx_dims* d, int32_t B, int32_t L) {
   if (!hidden_ok(d) || B < 1 || L < 1) return 0;
-  return (static_cast<size_t>(B) * L * d->hidden + 2 * static_cast<size_t>(reduce_max_blocks()) * d->hidden) * 4 + 512;
+  return (static_cast<size_t>(B) * L * d->hidden + 3 * static_cast<size_t>(reduce_max_blocks()) * d->hidden) * 4 + 512;
 }
 
 int32_t xlx_embeddings_fwd(const xlx_dims* d, int32_t B, int32_t L, const int64_t* input_ids,
@@ -253,7 +253,7 @@ int32_t xlx_embeddings_bwd(const xlx_dims* d, int32_t B, int32_t L, int32_t voca
   EmbSave s = emb_layout(d, M, const_cast<void*>(save));
   Bump b; b.base = static_cast<char*>(scratch);
   float* dy = b.f32(static_cast<size_t>(M) * H);
-  float* part = b.f32(2 * static_cast<size_t>(reduce_max_blocks()) * H);
+  float* part = b.f32(3 * static_cast<size_t>(reduce_max_blocks()) * H);
   int nblk = 0;
   XLX_TRY(layernorm_bwd(d_out, 1.0f, s.y, params[3], s.mean, s.rstd, M, H, dy, Split(), part, &nblk, st));
   float* o[2] = {grads[3], grads[4]};

@@ -386,9 +386,11 @@ ln_bwd_kernel(const float* __restrict__ dy, float dy_scale, const float* __restr
   constexpr int H = NV * 128;
   __shared__ float4 red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  float4 dg[NV], db[NV];
+  float4 dg[NV], db[NV], ds[NV];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) { dg[k] = make_float4(0, 0, 0, 0); db[k] = make_float4(0, 0, 0, 0); }
+  for (int k = 0; k < NV; ++k) {
+    dg[k] = make_float4(0, 0, 0, 0); db[k] = make_float4(0, 0, 0, 0); ds[k] = make_float4(0, 0, 0, 0);
+  }
   for (int row = blockIdx.x * nwarp + warp; row < M; row += gridDim.x * nwarp) {
     const float mu = mean[row], r = rstd[row];
     const float4* py = reinterpret_cast<const float4*>(y + static_cast<size_t>(row) * H);
@@ -419,15 +421,17 @@ ln_bwd_kernel(const float* __restrict__ dy, float dy_scale, const float* __restr
       const size_t idx = static_cast<size_t>(row) * H + (lane + 32 * k) * 4;
       if (dx) *reinterpret_cast<float4*>(dx + idx) = o;
       if (dx_hi) store_split4(dx_hi, dx_lo, idx, o);
+      ds[k].x += o.x; ds[k].y += o.y; ds[k].z += o.z; ds[k].w += o.w;
     }
   }
-  // cross-warp reduction of the column partials
+  // cross-warp reduction of the column partials: dgamma, dbeta and Σ_rows dx (the bias gradient of the Linear that
+  // produced the LayerNorm input)
 #pragma unroll
-  for (int v = 0; v < 2; ++v) {
+  for (int v = 0; v < 3; ++v) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       __syncthreads();
-      red[warp][lane] = v ? db[k] : dg[k];
+      red[warp][lane] = v == 0 ? dg[k] : (v == 1 ? db[k] : ds[k]);
       __syncthreads();
       if (warp == 0) {
         float4 a = red[0][lane];

@@ -79,7 +79,7 @@ int small_linear_bwd(const float* dy, const float* x, const float* W, int M, int
 int layernorm_fwd(const float* y, const float* gamma, const float* beta, float eps, int M, int H, float out_scale,
                   const float* addend, Split out, float* out_f32, float* mean, float* rstd, cudaStream_t s);
 // dy [M,H]: upstream grad wrt the LN output (scaled by dy_scale); y: saved LN input; → dx fp32 and/or split,
-// plus partial column sums part[2, nblk, H] (dgamma, dbeta); finish with colsum_finish.  dx may alias dy.
+// plus partial column sums part[3, nblk, H] (dgamma, dbeta, Σ_rows dx); finish with colsum_finish.  dx may alias dy.
 int layernorm_bwd(const float* dy, float dy_scale, const float* y, const float* gamma, const float* mean,
                   const float* rstd, int M, int H, float* dx, Split dx_split, float* part, int* nblk_out,
                   cudaStream_t s);
