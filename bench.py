@@ -193,9 +193,11 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    import contextlib
     import __graft_entry__ as entry
     if rank == 0:
-        entry.build()
+        with contextlib.redirect_stdout(sys.stderr):      # stdout carries exactly one line: the JSON result
+            entry.build()
     if world > 1:
         dist.barrier()
     from xlxmert_b200 import _lib, params as P, synth

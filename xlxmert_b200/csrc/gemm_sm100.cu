@@ -41,6 +41,10 @@ struct KParams {
   int kb_per_split;    // k-blocks per split (last split may be shorter)
   float* part;         // [splits][M][N] fp32 partial sums when splits > 1
   int conv, conv_H, conv_W, conv_taps, conv_kb_per_tap;   // implicit-GEMM convolution (see ConvGeometry)
+  int cluster;         // 1, or 2 = CTA pairs on adjacent m-tiles sharing the B tile by TMA multicast
+  int tiles_per_split; // tiles (cluster = 1) or tile pairs (cluster = 2) per split
+  int num_items;       // work items of the launch: tiles_per_split · splits
+  int tma_out;         // 1: the epilogue is a plain fp32 store and goes out through TMA (mapOut) instead of st.global
   int debug;           // XLX_GEMM_DEBUG bit 0: skip the epilogue's global traffic (mainloop-only timing experiments)
   GemmEpilogue epi;
 };
@@ -134,7 +138,7 @@ template <int BK, int A_MN, int B_MN, int NPARTS, bool ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
             const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
-            const KParams P) {
+            const __grid_constant__ CUtensorMap mapOut, const KParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
@@ -146,9 +150,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024B alignment
 
-  const int num_tiles = P.tiles_m * P.tiles_n;
-  const int num_items = num_tiles * P.splits;
   const int nkb = (P.K + BK - 1) / BK;
+  // Work decomposition.  cluster = 1: item → (tile, split).  cluster = 2: the two CTAs of a cluster take the m-tiles
+  // 2p and 2p + 1 of the same n-tile, so that each loads half of the shared B tile and multicasts it to both.
+  const int crank = (P.cluster == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int item0 = (P.cluster == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int istride = (P.cluster == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int num_items = P.num_items;
+  auto decode = [&](int item, int& m0, int& n0, int& split) {
+    const int t = item % P.tiles_per_split;
+    split = item / P.tiles_per_split;
+    const int mt = (P.cluster == 2) ? 2 * (t / P.tiles_n) + crank : t / P.tiles_n;
+    m0 = mt * BM;
+    n0 = (t % P.tiles_n) * P.BN;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapAhi);
@@ -159,7 +174,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
     }
     for (int s = 0; s < P.num_stages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), P.cluster);     // one tcgen05.commit per CTA of the cluster
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_tmem_full[b]), 1);
@@ -173,6 +188,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (P.cluster == 2) cluster_sync_all();     // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -181,10 +197,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int tile = item % num_tiles, split = item / num_tiles;
-        const int m0 = (tile / P.tiles_n) * BM;
-        const int n0 = (tile % P.tiles_n) * P.BN;
+      for (int item = item0; item < num_items; item += istride) {
+        int m0, n0, split;
+        decode(item, m0, n0, split);
         const int kb0 = split * P.kb_per_split, kb1 = min(nkb, kb0 + P.kb_per_split);
         // conv mode: tile → (image, y, x) of its first pixel
         int img = 0, y0 = 0, x0 = 0;
@@ -197,7 +212,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
           const uint32_t full = smem_u32(&bar_full[s]);
-          mbar_arrive_expect_tx(full, (P.debug & 64) ? P.stage_bytes - P.b_part_bytes : P.stage_bytes);
+          mbar_arrive_expect_tx(full, P.stage_bytes);
           const uint32_t sA = smem_base + s * P.stage_bytes;
           const uint32_t sB = sA + NPARTS * P.a_part_bytes;
           const int k0 = kb * BK;
@@ -218,8 +233,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j) tma_load_2d(dA + j * (BK * 128), ma, full, m0 + 64 * j, k0);
             }
-            if ((P.debug & 64) && part == 1) {
-              // experiment: skip the B_lo load (results are wrong; measures sensitivity to operand traffic)
+            if (P.cluster == 2) {
+              // this CTA fetches its half of the B tile and multicasts it into both CTAs' stage s
+              if (!B_MN) {
+                const int half_rows = P.BN / 2;
+                tma_load_2d_mcast(dB + crank * half_rows * (BK * 2), mb, full, k0, n0 + crank * half_rows, 3);
+              } else {
+                const int nbox = P.BN / 128;
+                for (int j = crank * nbox; j < (crank + 1) * nbox; ++j)
+                  tma_load_2d_mcast(dB + j * (BK * 128), mb, full, n0 + 64 * j, k0, 3);
+              }
             } else if (!B_MN) {
               tma_load_2d(dB, mb, full, k0, n0);
             } else {
@@ -248,8 +271,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
     int s = 0;
     uint32_t ph = 0;
     int local = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
-      const int split = item / num_tiles;
+    for (int item = item0; item < num_items; item += istride, ++local) {
+      const int split = item / P.tiles_per_split;
       const int kb0 = split * P.kb_per_split, kb1 = min(nkb, kb0 + P.kb_per_split);
       const int buf = local & 1;
       const uint32_t acc_ph = (local >> 1) & 1;
@@ -259,7 +282,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(smem_u32(&bar_full[s]), ph);
         tc_fence_after();
-        const uint32_t sA = smem_base + s * P.stage_bytes;
+        // CTA-local byte offset of the stage: in a cluster launch shared-window addresses carry the CTA rank in
+        // their upper bits, which must not leak into the descriptor's LBO field
+        const uint32_t sA = (smem_base + s * P.stage_bytes) & 0x3FFFFu;
         const uint32_t a0 = loA | (sA >> 4);
         const uint32_t b0 = loB | ((sA + NPARTS * P.a_part_bytes) >> 4);
         if (elect_one()) {
@@ -276,7 +301,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
               umma_bf16(tmem_d, umma_desc(hiA, ah), umma_desc(hiB, bh), idesc, acc);
             }
           }
-          umma_commit(smem_u32(&bar_empty[s]));              // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire (in a cluster: once BOTH CTAs' MMAs on it retired)
+          if (P.cluster == 2) umma_commit_mcast(smem_u32(&bar_empty[s]), 3);
+          else umma_commit(smem_u32(&bar_empty[s]));
           if (kb == kb1 - 1) umma_commit(smem_u32(&bar_tmem_full[buf]));
         }
         __syncwarp();
@@ -295,12 +322,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
                    e * 32 * EPI_COLS;
     const int sub = lane >> 2, cq = lane & 3;
     int local = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
-      const int tile = item % num_tiles, split = item / num_tiles;
+    for (int item = item0; item < num_items; item += istride, ++local) {
+      int m0, n0, split;
+      decode(item, m0, n0, split);
       const int buf = local & 1;
       const uint32_t acc_ph = (local >> 1) & 1;
-      const int m0 = (tile / P.tiles_n) * BM;
-      const int n0 = (tile % P.tiles_n) * P.BN;
       mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * P.BN;
@@ -330,6 +356,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
           *reinterpret_cast<float4*>(stage + lane * EPI_COLS + ((g ^ wsw) << 2)) =
               make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]),
                           __uint_as_float(r[g * 4 + 3]));
+        if (P.tma_out) {
+          // plain fp32 output: the staged 32 × 16 block (64-byte-swizzle layout) leaves as one bulk tensor store
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&mapOut, smem_u32(stage), n0 + c * EPI_COLS, m0 + q * 32);
+            tma_store_commit();
+            tma_store_wait_read();
+          }
+          __syncwarp();
+          continue;
+        }
         __syncwarp();
         const int n = n0 + c * EPI_COLS + cq * 4;
 #pragma unroll 1
@@ -351,6 +389,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (P.cluster == 2) cluster_sync_all();     // nobody exits while the peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, P.tmem_cols);
@@ -495,6 +534,21 @@ int make_map4(CUtensorMap* out, const void* ptr, int B, int H, int W, int C, int
   return 0;
 }
 
+// fp32 row-major [outer, inner] output matrix, box = box0 × box1, 64-byte swizzle (the epilogue staging layout)
+int make_map_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box0,
+                 uint32_t box1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -10;
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {ld * 4};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -11;
+}
+
 int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
@@ -502,7 +556,7 @@ int env_int(const char* name, int dflt) {
 
 template <int BK, int A_MN, int B_MN, int NPARTS, bool ACT>
 int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& mAhi, const CUtensorMap& mAlo,
-                   const CUtensorMap& mBhi, const CUtensorMap& mBlo, const KParams& P) {
+                   const CUtensorMap& mBhi, const CUtensorMap& mBlo, const CUtensorMap& mOut, const KParams& P) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BK, A_MN, B_MN, NPARTS, ACT>,
@@ -510,8 +564,21 @@ int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUtensorMap
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  gemm_kernel<BK, A_MN, B_MN, NPARTS, ACT><<<grid, GEMM_THREADS, smem, stream>>>(mAhi, mAlo, mBhi, mBlo, P);
-  return 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  static const int force_cl = env_int("XLX_GEMM_FORCE_CLUSTER_LAUNCH", 0);    // experiment: cluster launch, independent CTAs
+  attr[0].val.clusterDim.x = (force_cl && grid % 2 == 0) ? 2 : P.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BK, A_MN, B_MN, NPARTS, ACT>, mAhi, mAlo, mBhi, mBlo, mOut, P);
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
 }
 
 template <int BK>
@@ -584,17 +651,23 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     if (P.nparts == 2) { if ((rc = mk(&mAlo, p.a, p.a.lo, a_rows, BM))) return rc; }
     else mAlo = mAhi;
   }
-  if ((rc = mk(&mBhi, p.b, p.b.hi, b_rows, BN))) return rc;
-  if (P.nparts == 2) { if ((rc = mk(&mBlo, p.b, p.b.lo, b_rows, BN))) return rc; }
+  // CTA pairs (cluster of 2 along M) share the B tile through TMA multicast: a third less operand traffic per CTA.
+  static const int cluster_on = env_int("XLX_GEMM_CLUSTER", 1);
+  P.cluster = (cluster_on && !P.conv && BN >= 128 && P.tiles_m >= 2 && num_sms >= 2) ? 2 : 1;
+  const int b_box_rows = P.cluster == 2 ? BN / 2 : BN;
+  if ((rc = mk(&mBhi, p.b, p.b.hi, b_rows, b_box_rows))) return rc;
+  if (P.nparts == 2) { if ((rc = mk(&mBlo, p.b, p.b.lo, b_rows, b_box_rows))) return rc; }
   else mBlo = mBhi;
-  const int num_tiles = P.tiles_m * P.tiles_n;
+  // tiles per split: single tiles, or pairs of m-tiles (an odd last m-tile gets an idle partner)
+  const int num_tiles = P.cluster == 2 ? ((P.tiles_m + 1) / 2) * P.tiles_n : P.tiles_m * P.tiles_n;
+  const int cta_per_item = P.cluster;
   const int nkb = (p.K + BK - 1) / BK;
   // split-K: only for plain fp32-output GEMMs (weight gradients) whose tile count leaves most SMs idle
   P.splits = 1; P.kb_per_split = nkb; P.part = nullptr;
   const bool plain = p.epi.out_f32 && !p.epi.bias && !p.epi.addend && !p.epi.addend_hi && !p.epi.out_hi &&
                      !p.epi.out_u && !(p.epi.flags & ~EPI_ACCUM) && p.epi.alpha == 1.0f;
   static const int splitk_on = env_int("XLX_GEMM_SPLITK", 1);
-  if (splitk_on && plain && p.splitk_ws && num_tiles < num_sms) {
+  if (splitk_on && plain && p.splitk_ws && num_tiles * cta_per_item < num_sms) {
     // pick the split count whose work items fill whole waves of SMs best (ties → fewer splits)
     const size_t need = static_cast<size_t>(p.M) * p.N;
     int maxS = nkb / 8;                                         // ≥ 8 k-blocks per split
@@ -602,7 +675,7 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     int best = 1;
     double best_eff = 0.0;
     for (int S = 1; S <= maxS && need * S <= p.splitk_ws_floats; ++S) {
-      const int items = num_tiles * S;
+      const int items = num_tiles * S * cta_per_item;
       const int waves = (items + num_sms - 1) / num_sms;
       const double eff = static_cast<double>(items) / (static_cast<double>(waves) * num_sms);
       if (eff > best_eff + 0.03) { best_eff = eff; best = S; }
@@ -613,8 +686,20 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
       P.part = p.splitk_ws;
     }
   }
+  // plain fp32 output (no split-K partials): TMA store from the staging buffers
+  CUtensorMap mOut = mAhi;
+  P.tma_out = 0;
+  static const int tma_out_on = env_int("XLX_GEMM_TMA_OUT", 1);
+  if (tma_out_on && plain && P.splits == 1 && !(p.epi.flags & EPI_ACCUM) &&
+      !(reinterpret_cast<uintptr_t>(p.epi.out_f32) & 15)) {
+    if ((rc = make_map_f32(&mOut, p.epi.out_f32, p.N, p.M, p.epi.ld_out, EPI_COLS, 32))) return rc;
+    P.tma_out = 1;
+  }
   const int num_items = num_tiles * P.splits;
-  const int grid = num_items < num_sms ? num_items : num_sms;
+  P.tiles_per_split = num_tiles;
+  P.num_items = num_items;
+  int grid = num_items * cta_per_item < num_sms ? num_items * cta_per_item : num_sms;
+  if (P.cluster == 2) grid &= ~1;
   const size_t smem = static_cast<size_t>(stages) * P.stage_bytes + 1024 + STAGE_BYTES;
   TimedLaunch tl{};
   if (g_timing) {
@@ -632,8 +717,8 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     const int v = (P.a_mn ? 4 : 0) | (P.b_mn ? 2 : 0) | (P.nparts == 2 ? 1 : 0);
     int lrc = 0;
 #define XLX_LAUNCH(A, B, N)                                                                                   \
-  lrc = act ? launch_variant<BK, A, B, N, true>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P)                \
-            : launch_variant<BK, A, B, N, false>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, P)
+  lrc = act ? launch_variant<BK, A, B, N, true>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)          \
+            : launch_variant<BK, A, B, N, false>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)
     switch (v) {
       case 0: XLX_LAUNCH(0, 0, 1); break;
       case 1: XLX_LAUNCH(0, 0, 2); break;

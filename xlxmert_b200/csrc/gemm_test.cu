@@ -89,9 +89,26 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(ohi.data(), dOhi, nmn * 2, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(olo.data(), dOlo, nmn * 2, cudaMemcpyDeviceToHost));
 
+  if (getenv("XLX_TEST_MAP")) {   // per (m-tile, 64-column block): count of wrong entries (exhaustive, small problems only)
+    for (int mt = 0; mt < (M + 127) / 128; ++mt) {
+      printf("  mtile %2d:", mt);
+      for (int nb = 0; nb < (N + 63) / 64; ++nb) {
+        int bad = 0;
+        for (int r = mt * 128; r < M && r < mt * 128 + 128; ++r)
+          for (int c = nb * 64; c < N && c < nb * 64 + 64; ++c) {
+            double acc = 0;
+            for (int k = 0; k < K; ++k) acc += static_cast<double>(A[static_cast<size_t>(r) * K + k]) * B[static_cast<size_t>(c) * K + k];
+            if (!(fabs(out[static_cast<size_t>(r) * N + c] - acc) < 1e-3 * (1 + fabs(acc)))) ++bad;
+          }
+        printf(" %4d", bad);
+      }
+      printf("\n");
+    }
+  }
   // sampled reference
   size_t nsamp = nmn < 200000 ? nmn : 200000;
   double max_err = 0, max_ref = 0, max_split_err = 0, max_u_err = 0;
+  int nbad = 0;
   uint64_t s2 = 99;
   for (size_t t = 0; t < nsamp; ++t) {
     size_t idx;
@@ -115,6 +132,8 @@ int main(int argc, char** argv) {
     if (epi & 16) { double x = uin[idx]; v *= 0.5 * (1.0 + erf(x / sqrt(2.0))) + x * exp(-0.5 * x * x) / sqrt(2.0 * M_PI); }
     if (epi & 4) v += addend[idx];
     if (epi & 32) v += out0[idx];
+    if (getenv("XLX_TEST_VERBOSE") && !(fabs(out[idx] - v) < 1e-3 * (1 + fabs(v))) && nbad++ < 24)
+      printf("  bad r=%d (mtile %d, r%%128=%d) c=%d (ntile %d, c%%256=%d) got %.5g want %.5g\n", r, r / 128, r % 128, c, c / 256, c % 256, out[idx], v);
     max_err = fmax(max_err, fabs(out[idx] - v));
     max_ref = fmax(max_ref, fabs(v));
     if (epi & 8) max_split_err = fmax(max_split_err, fabs(static_cast<double>(__bfloat162float(ohi[idx])) + __bfloat162float(olo[idx]) - out[idx]));
