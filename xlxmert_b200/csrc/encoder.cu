@@ -61,12 +61,16 @@ int ffn_slot(const xlx_dims* d, int blk) {
 }
 
 // ---- prepared weights ----------------------------------------------------------------------------
-struct AttW { Split wqkv; float* bqkv; Split wo; };
-struct FfnW { Split w1, w2; };
+// Every Linear weight W [N, K] is kept twice as split bf16: as is (forward: Y = X·Wᵀ reads it K-major) and
+// transposed Wᵀ [K, N] (dgrad: dX = dY·W reads Wᵀ K-major too) — K-major B operands are ≈ 20 % faster than
+// MN-major ones on this kernel, and one batched launch per step builds both.
+struct AttW { Split wqkv, wqkv_t; float* bqkv; Split wo, wo_t; };
+struct FfnW { Split w1, w1_t, w2, w2_t; };
 struct Prep {
-  Split visn_w;
+  Split visn_w, visn_w_t;
   std::vector<AttW> att;
   std::vector<FfnW> ffn;
+  int max_jobs = 0;
   size_t bytes = 0;
 };
 Prep prep_layout(const xlx_dims* d, void* base) {
@@ -75,12 +79,17 @@ Prep prep_layout(const xlx_dims* d, void* base) {
   b.base = static_cast<char*>(base);
   const size_t H = d->hidden, I = d->intermediate, F = d->feat_dim;
   p.visn_w = b.split(H * F);
+  p.visn_w_t = b.split(F * H);
   const int natt = d->l_layers + d->r_layers + 3 * d->x_layers;
   const int nffn = d->l_layers + d->r_layers + 2 * d->x_layers;
   p.att.resize(natt);
   p.ffn.resize(nffn);
-  for (auto& a : p.att) { a.wqkv = b.split(3 * H * H); a.bqkv = b.f32(3 * H); a.wo = b.split(H * H); }
-  for (auto& f : p.ffn) { f.w1 = b.split(I * H); f.w2 = b.split(H * I); }
+  for (auto& a : p.att) {
+    a.wqkv = b.split(3 * H * H); a.wqkv_t = b.split(3 * H * H); a.bqkv = b.f32(3 * H);
+    a.wo = b.split(H * H); a.wo_t = b.split(H * H);
+  }
+  for (auto& f : p.ffn) { f.w1 = b.split(I * H); f.w1_t = b.split(H * I); f.w2 = b.split(H * I); f.w2_t = b.split(I * H); }
+  p.max_jobs = 1 + 4 * natt + 2 * nffn;
   p.bytes = b.off + 256;
   return p;
 }
@@ -274,8 +283,9 @@ struct Run {
 int linear(const Run& r, Split x, int M, int K, Split w, int N, const GemmEpilogue& e) {
   return gemm_linear(r.passes, r.st, x, M, K, w, N, e);
 }
-int dgrad(const Run& r, Split dy, int M, int N, Split w, int K, const GemmEpilogue& e) {
-  return gemm_dgrad(r.passes, r.st, dy, M, N, w, K, e);
+// dX[M,K] = dY[M,N] · W[N,K], with the transposed copy Wᵀ [K, N] as a K-major B operand
+int dgrad(const Run& r, Split dy, int M, int N, Split w_t, int K, const GemmEpilogue& e) {
+  return gemm_linear(r.passes, r.st, dy, M, N, w_t, K, e);
 }
 int wgrad(const Run& r, Split dy, int M, int N, Split x, int K, float* dw) {
   return gemm_wgrad(r.passes, r.st, dy, M, N, x, K, dw, false, 0, r.plan.splitk);
@@ -390,12 +400,12 @@ int ffn_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
   XLX_TRY(wgrad(r, p.dy_s, M, H, f.h, I, bw.G(s0 + 2)));
   GemmEpilogue e;   // du = (dy · W2) ∘ gelu'(u), the derivative was saved by the forward
   e.flags = EPI_MUL; e.u_in = f.u; e.ld_u = I; e.out_hi = p.du.hi; e.out_lo = p.du.lo; e.ld_split = I;
-  XLX_TRY(dgrad(r, p.dy_s, M, H, w.w2, I, e));
+  XLX_TRY(dgrad(r, p.dy_s, M, H, w.w2_t, I, e));
   XLX_TRY(colsum(nullptr, p.du, M, I, I, p.part, bw.G(s0 + 1), r.st));
   XLX_TRY(wgrad(r, p.du, M, I, f.in, H, bw.G(s0)));
   GemmEpilogue o;   // din = du · W1 + dy (residual path)
   o.addend = p.dy; o.ld_addend = H; o.out_f32 = din; o.ld_out = H;
-  return dgrad(r, p.du, M, I, w.w1, H, o);
+  return dgrad(r, p.du, M, I, w.w1_t, H, o);
 }
 
 // common tail/head of the attention backward: everything except the attention-core call(s)
@@ -409,7 +419,7 @@ int att_bwd_head(const Bwd& bw, int blk, const float* dout) {
   XLX_TRY(wgrad(r, p.dy_s, M, H, a.ctx, H, bw.G(s0 + 6)));
   GemmEpilogue e;
   e.out_hi = p.dctx.hi; e.out_lo = p.dctx.lo; e.ld_split = H;
-  return dgrad(r, p.dy_s, M, H, w.wo, H, e);
+  return dgrad(r, p.dy_s, M, H, w.wo_t, H, e);
 }
 int att_bwd_tail(const Bwd& bw, int blk, float* din) {
   const Run& r = *bw.r;
@@ -421,7 +431,7 @@ int att_bwd_tail(const Bwd& bw, int blk, float* din) {
   XLX_TRY(wgrad(r, p.dqkv, M, 3 * H, a.in, H, bw.G(s0)));                          // q.w | k.w | v.w
   GemmEpilogue o;
   o.addend = p.dy; o.ld_addend = H; o.out_f32 = din; o.ld_out = H;
-  return dgrad(r, p.dqkv, M, 3 * H, w.wqkv, H, o);
+  return dgrad(r, p.dqkv, M, 3 * H, w.wqkv_t, H, o);
 }
 int att_self_bwd(const Bwd& bw, int blk, int S, const float* dout, float* din) {
   const Run& r = *bw.r;
@@ -524,20 +534,30 @@ int32_t xlx_encoder_prepare(const xlx_dims* d, const float* const* params, void*
   XLX_TRY(ensure_device(prep));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Prep p = prep_layout(d, prep);
-  const size_t H = d->hidden, I = d->intermediate, F = d->feat_dim;
-  XLX_TRY(split_f32(params[0], p.visn_w, H * F, st));
+  const int H = d->hidden, I = d->intermediate, F = d->feat_dim;
+  std::vector<SplitJob> jobs;
+  jobs.reserve(p.max_jobs);
+  auto add = [&](const float* src, int R, int C, Split dst, int row0, Split dst_t, int ld_t, int col0_t) {
+    SplitJob j;
+    j.src = src; j.hi = dst.hi; j.lo = dst.lo; j.t_hi = dst_t.hi; j.t_lo = dst_t.lo;
+    j.R = R; j.C = C; j.row0 = row0; j.ld_t = ld_t; j.col0_t = col0_t; j.tile0 = 0;
+    jobs.push_back(j);
+  };
+  add(params[0], H, F, p.visn_w, 0, p.visn_w_t, H, 0);
   for (size_t blk = 0; blk < p.att.size(); ++blk) {
     const int s0 = att_slot(d, static_cast<int>(blk));
     const AttW& a = p.att[blk];
-    for (int j = 0; j < 3; ++j) XLX_TRY(split_f32(params[s0 + j], rows(a.wqkv, j * H, H), H * H, st));
-    XLX_TRY(concat3_f32(params[s0 + 3], params[s0 + 4], params[s0 + 5], a.bqkv, static_cast<int>(H), st));
-    XLX_TRY(split_f32(params[s0 + 6], a.wo, H * H, st));
+    // fused [3H, H] weight and its transpose [H, 3H]: q | k | v stacked along rows / columns
+    for (int j = 0; j < 3; ++j) add(params[s0 + j], H, H, a.wqkv, j * H, a.wqkv_t, 3 * H, j * H);
+    XLX_TRY(concat3_f32(params[s0 + 3], params[s0 + 4], params[s0 + 5], a.bqkv, H, st));
+    add(params[s0 + 6], H, H, a.wo, 0, a.wo_t, H, 0);
   }
   for (size_t blk = 0; blk < p.ffn.size(); ++blk) {
     const int s0 = ffn_slot(d, static_cast<int>(blk));
-    XLX_TRY(split_f32(params[s0], p.ffn[blk].w1, I * H, st));
-    XLX_TRY(split_f32(params[s0 + 2], p.ffn[blk].w2, H * I, st));
+    add(params[s0], I, H, p.ffn[blk].w1, 0, p.ffn[blk].w1_t, I, 0);
+    add(params[s0 + 2], H, I, p.ffn[blk].w2, 0, p.ffn[blk].w2_t, H, 0);
   }
+  XLX_TRY(split_batch(jobs.data(), static_cast<int>(jobs.size()), st));
   return 0;
 }
 
@@ -690,7 +710,7 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
     if (d_visual_feats) {
       GemmEpilogue e;
       e.out_f32 = d_visual_feats; e.ld_out = F;
-      XLX_TRY(dgrad(r, p.dy_s, Mv, H, r.prep.visn_w, F, e));
+      XLX_TRY(dgrad(r, p.dy_s, Mv, H, r.prep.visn_w_t, F, e));
     }
   }
   return 0;

@@ -321,6 +321,45 @@ __global__ void small_linear_dw_kernel(const float* __restrict__ dy, const float
   }
 }
 
+// One CTA (256 threads) per 64×64 tile of one job: coalesced fp32 reads, row-major split written directly, the
+// transposed split through a padded shared-memory tile.
+constexpr int kMaxSplitJobs = 192;
+struct SplitJobTable { SplitJob j[kMaxSplitJobs]; int n; };
+__global__ void __launch_bounds__(256)
+split_batch_kernel(const __grid_constant__ SplitJobTable T) {
+  __shared__ float tile[64][65];
+  int lo = 0, hi = T.n - 1;                   // job owning this tile: last job with tile0 ≤ blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (T.j[mid].tile0 <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+  }
+  const SplitJob J = T.j[lo];
+  const int t = blockIdx.x - J.tile0;
+  const int tiles_c = (J.C + 63) >> 6;
+  const int r0 = (t / tiles_c) * 64, c0 = (t % tiles_c) * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // 16 column quads × 16 rows per pass
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int r = r0 + pass * 16 + ty, c = c0 + tx * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < J.R && c < J.C) v = __ldg(reinterpret_cast<const float4*>(J.src + static_cast<size_t>(r) * J.C + c));
+    if (J.hi && r < J.R && c < J.C) store_split4(J.hi, J.lo, (static_cast<size_t>(J.row0) + r) * J.C + c, v);
+    tile[pass * 16 + ty][tx * 4 + 0] = v.x; tile[pass * 16 + ty][tx * 4 + 1] = v.y;
+    tile[pass * 16 + ty][tx * 4 + 2] = v.z; tile[pass * 16 + ty][tx * 4 + 3] = v.w;
+  }
+  if (!J.t_hi) return;
+  __syncthreads();
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int c = c0 + pass * 16 + ty, r = r0 + tx * 4;       // output row = source column
+    if (c < J.C && r < J.R) {
+      const float4 v = make_float4(tile[tx * 4 + 0][pass * 16 + ty], tile[tx * 4 + 1][pass * 16 + ty],
+                                   tile[tx * 4 + 2][pass * 16 + ty], tile[tx * 4 + 3][pass * 16 + ty]);
+      store_split4(J.t_hi, J.t_lo, static_cast<size_t>(c) * J.ld_t + J.col0_t + r, v);
+    }
+  }
+}
+
 inline int grid_for(size_t n, int threads) {
   size_t b = (n + threads - 1) / threads;
   return static_cast<int>(b < 148 * 16 ? (b ? b : 1) : 148 * 16);
@@ -567,6 +606,24 @@ int gather_rows(const float* table, const int64_t* ids, const uint8_t* mask, con
   return launch_rc();
 }
 
+int split_batch(SplitJob* jobs, int njobs, cudaStream_t s) {
+  for (int first = 0; first < njobs; first += kMaxSplitJobs) {
+    SplitJobTable T;
+    T.n = njobs - first < kMaxSplitJobs ? njobs - first : kMaxSplitJobs;
+    int tiles = 0;
+    for (int i = 0; i < T.n; ++i) {
+      SplitJob j = jobs[first + i];
+      if ((j.C % 4) || (j.R % 4) || (j.ld_t % 4) || (j.col0_t % 4)) return -2;
+      j.tile0 = tiles;
+      tiles += ((j.R + 63) / 64) * ((j.C + 63) / 64);
+      T.j[i] = j;
+    }
+    split_batch_kernel<<<tiles, 256, 0, s>>>(T);
+    int rc = launch_rc();
+    if (rc) return rc;
+  }
+  return 0;
+}
 int split_rows_f32(const float* x, size_t ld_in, int rows, int cols, Split out, cudaStream_t s) {
   if ((cols % 4) || (ld_in % 4)) return -2;
   if (!rows) return 0;

@@ -32,6 +32,17 @@ int gather_rows(const float* table, const int64_t* ids, const uint8_t* mask, con
 int concat3_f32(const float* a, const float* b, const float* c, float* dst, int n, cudaStream_t s);
 int fill_f32(float* dst, float v, size_t n, cudaStream_t s);
 
+// Batched weight preparation: for every job, src [R, C] fp32 → dst rows [row0 .., row0 + R) of a split matrix with
+// leading dimension C (dst may be null), and → its transpose dst_t [C, ld_t] at column offset col0_t (dst_t may be
+// null); up to 192 jobs per launch, the job table travels as a kernel parameter (no device-side table, no copies).
+struct SplitJob {
+  const float* src;
+  bf16 *hi, *lo;        // row-major copy: element (r, c) at (row0 + r) * C + c
+  bf16 *t_hi, *t_lo;    // transposed copy: element (r, c) at c * ld_t + col0_t + r
+  int R, C, row0, ld_t, col0_t, tile0;   // tile0: first 64×64 tile index of this job (prefix sum, filled by the callee)
+};
+int split_batch(SplitJob* jobs, int njobs, cudaStream_t s);
+
 // x rows with stride ld_in (fp32) → contiguous split matrix [rows, cols]; cols % 4 == 0.
 int split_rows_f32(const float* x, size_t ld_in, int rows, int cols, Split out, cudaStream_t s);
 // dpre = d · (1 − y²) (tanh backward) → split; n % 4 == 0.
