@@ -56,11 +56,49 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// GeLU (erf form) and its derivative from one exponential:
+//   Φ(x) = ½·erfc(−x/√2),  erfc(z) = e^{−z²}·(a₁t + … + a₅t⁵), t = 1/(1 + p·z), z ≥ 0   (Abramowitz–Stegun 7.1.26,
+//   |error| ≤ 1.5e-7 on erf, i.e. fp32-epsilon class on Φ), and e^{−z²} = e^{−x²/2} is exactly what φ(x) needs.
+//   gelu(x) = x·Φ(x),  gelu'(x) = Φ(x) + x·φ(x).   ≈ 20 instructions instead of erff + expf.
+__device__ __forceinline__ void gelu_and_grad(float x, float& y, float& dy) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float e = __expf(-0.5f * x * x);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float half_erfc = 0.5f * poly * t * e;              // ½·erfc(|x|/√2) = Φ(−|x|)
+  const float cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+  y = x * cdf;
+  dy = fmaf(x, 0.39894228040143267794f * e, cdf);
+}
+
+// Global inputs of the epilogue for 4 consecutive columns of one row, fetched ahead of the arithmetic so that the loads
+// of a whole 32×16 chunk are in flight together.
+// `a` holds the first fp32 input the epilogue needs (u_in, else addend, else the old output for EPI_ACCUM); the rare
+// epilogues needing more than one of them load the others late.  `h`/`l`: split-bf16 addend.
+struct EpiIn { float4 a; uint2 h, l; };
+__device__ __forceinline__ void epilogue_fetch(const KParams& P, int row, int n, EpiIn& in) {
+  const GemmEpilogue& E = P.epi;
+  if (E.flags & (EPI_MUL | EPI_GELU_GRAD))
+    in.a = __ldg(reinterpret_cast<const float4*>(E.u_in + static_cast<size_t>(row) * E.ld_u + n));
+  else if (E.addend)
+    in.a = __ldg(reinterpret_cast<const float4*>(E.addend + static_cast<size_t>(row) * E.ld_addend + n));
+  else if (E.out_f32 && (E.flags & EPI_ACCUM))
+    in.a = *reinterpret_cast<const float4*>(E.out_f32 + static_cast<size_t>(row) * E.ld_out + n);
+  if (E.addend_hi) {
+    const size_t idx = static_cast<size_t>(row) * E.ld_addend + n;
+    in.h = __ldg(reinterpret_cast<const uint2*>(E.addend_hi + idx));
+    in.l = __ldg(reinterpret_cast<const uint2*>(E.addend_lo + idx));
+  }
+}
+
 // Epilogue on 4 consecutive columns of one output row.  Called in the "coalesced domain": 4 adjacent lanes hold 16
 // consecutive columns of the same row, so every global access below covers whole 32-byte sectors (64-byte fp32 /
 // 32-byte bf16 segments per row).
 template <bool ACT>
-__device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, float4 acc) {
+__device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, float4 acc, const EpiIn& in) {
   const GemmEpilogue& E = P.epi;
   float v[4] = {acc.x * E.alpha, acc.y * E.alpha, acc.z * E.alpha, acc.w * E.alpha};
   if (E.bias) {
@@ -71,11 +109,9 @@ __device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, 
     float dg[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      // gelu(x) = x·Φ(x), gelu'(x) = Φ(x) + x·φ(x): one erf serves both
       const float x = v[j];
-      const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-      dg[j] = (E.flags & EPI_SAVE_DGELU) ? cdf + x * (0.39894228040143267794f * __expf(-0.5f * x * x)) : x;
-      v[j] = x * cdf;
+      gelu_and_grad(x, v[j], dg[j]);
+      if (!(E.flags & EPI_SAVE_DGELU)) dg[j] = x;
     }
     if (E.out_u)
       *reinterpret_cast<float4*>(E.out_u + static_cast<size_t>(row) * E.ld_u + n) = make_float4(dg[0], dg[1], dg[2], dg[3]);
@@ -90,34 +126,30 @@ __device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
   }
+  const bool has_u = (E.flags & (EPI_MUL | EPI_GELU_GRAD)) != 0;
   if (ACT && (E.flags & EPI_GELU_GRAD)) {
-    const float4 u = __ldg(reinterpret_cast<const float4*>(E.u_in + static_cast<size_t>(row) * E.ld_u + n));
-    v[0] *= gelu_erf_grad(u.x); v[1] *= gelu_erf_grad(u.y); v[2] *= gelu_erf_grad(u.z); v[3] *= gelu_erf_grad(u.w);
+    v[0] *= gelu_erf_grad(in.a.x); v[1] *= gelu_erf_grad(in.a.y); v[2] *= gelu_erf_grad(in.a.z); v[3] *= gelu_erf_grad(in.a.w);
   }
-  if (E.flags & EPI_MUL) {
-    const float4 u = __ldg(reinterpret_cast<const float4*>(E.u_in + static_cast<size_t>(row) * E.ld_u + n));
-    v[0] *= u.x; v[1] *= u.y; v[2] *= u.z; v[3] *= u.w;
-  }
+  if (E.flags & EPI_MUL) { v[0] *= in.a.x; v[1] *= in.a.y; v[2] *= in.a.z; v[3] *= in.a.w; }
   if (E.addend) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(E.addend + static_cast<size_t>(row) * E.ld_addend + n));
-    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+    const float4 add = has_u ? __ldg(reinterpret_cast<const float4*>(E.addend + static_cast<size_t>(row) * E.ld_addend + n))
+                             : in.a;
+    v[0] += add.x; v[1] += add.y; v[2] += add.z; v[3] += add.w;
   }
   if (E.addend_hi) {
-    const size_t idx = static_cast<size_t>(row) * E.ld_addend + n;
-    const uint2 h = __ldg(reinterpret_cast<const uint2*>(E.addend_hi + idx));
-    const uint2 l = __ldg(reinterpret_cast<const uint2*>(E.addend_lo + idx));
-    v[0] += __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
-    v[1] += __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
-    v[2] += __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
-    v[3] += __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+    v[0] += __uint_as_float(in.h.x << 16) + __uint_as_float(in.l.x << 16);
+    v[1] += __uint_as_float(in.h.x & 0xffff0000u) + __uint_as_float(in.l.x & 0xffff0000u);
+    v[2] += __uint_as_float(in.h.y << 16) + __uint_as_float(in.l.y << 16);
+    v[3] += __uint_as_float(in.h.y & 0xffff0000u) + __uint_as_float(in.l.y & 0xffff0000u);
   }
   if (E.out_f32) {
-    float4* dst = reinterpret_cast<float4*>(E.out_f32 + static_cast<size_t>(row) * E.ld_out + n);
     if (E.flags & EPI_ACCUM) {
-      const float4 old = *dst;
+      const float4 old = (has_u || E.addend)
+                             ? *reinterpret_cast<const float4*>(E.out_f32 + static_cast<size_t>(row) * E.ld_out + n)
+                             : in.a;
       v[0] += old.x; v[1] += old.y; v[2] += old.z; v[3] += old.w;
     }
-    *dst = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(E.out_f32 + static_cast<size_t>(row) * E.ld_out + n) = make_float4(v[0], v[1], v[2], v[3]);
   }
   if (E.out_hi) {
     const size_t idx = static_cast<size_t>(row) * E.ld_split + n;
@@ -370,16 +402,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
         }
         __syncwarp();
         const int n = n0 + c * EPI_COLS + cq * 4;
-#pragma unroll 1
-        for (int it = 0; it < 4; ++it) {
-          const int rr = it * 8 + sub;
-          const int row = m0 + q * 32 + rr;
-          const float4 acc = *reinterpret_cast<const float4*>(stage + rr * EPI_COLS + ((cq ^ ((rr >> 1) & 3)) << 2));
-          if (row < P.M && n < P.N) {
-            if (P.splits > 1)   // raw partial sums; the reduce kernel finishes the job
+        const bool col_ok = n < P.N;
+        if (P.splits > 1) {   // raw partial sums; the reduce kernel finishes the job
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + sub, row = m0 + q * 32 + rr;
+            const float4 acc = *reinterpret_cast<const float4*>(stage + rr * EPI_COLS + ((cq ^ ((rr >> 1) & 3)) << 2));
+            if (row < P.M && col_ok)
               *reinterpret_cast<float4*>(P.part + (static_cast<size_t>(split) * P.M + row) * P.N + n) = acc;
-            else
-              epilogue_vec4<ACT>(P, row, n, acc);
+          }
+        } else if (ACT) {     // activation epilogues: arithmetic-bound, kept rolled (small code)
+#pragma unroll 1
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + sub, row = m0 + q * 32 + rr;
+            const float4 acc = *reinterpret_cast<const float4*>(stage + rr * EPI_COLS + ((cq ^ ((rr >> 1) & 3)) << 2));
+            if (row < P.M && col_ok) {
+              EpiIn in;
+              epilogue_fetch(P, row, n, in);
+              epilogue_vec4<true>(P, row, n, acc, in);
+            }
+          }
+        } else {              // load-bound epilogues: all global inputs of the chunk in flight before any arithmetic
+          EpiIn in[4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int row = m0 + q * 32 + it * 8 + sub;
+            if (row < P.M && col_ok) epilogue_fetch(P, row, n, in[it]);
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + sub, row = m0 + q * 32 + rr;
+            const float4 acc = *reinterpret_cast<const float4*>(stage + rr * EPI_COLS + ((cq ^ ((rr >> 1) & 3)) << 2));
+            if (row < P.M && col_ok) epilogue_vec4<false>(P, row, n, acc, in[it]);
           }
         }
         __syncwarp();
