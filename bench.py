@@ -30,6 +30,8 @@ ENC_GFLOP_FWD = 15.389          # per sample, SURVEY.md §8(a) a11 (algorithmic,
 ENC_GFLOP_FWD_BWD = 46.17
 # measured on this pool's B200s by the driver (BASELINE.md §2 keeps a copy of MEASURED_PEAKS.json)
 PEAKS_COPY = {"hbm_gbs": 6532.9, "bf16_tflops": 1627.7, "bf16_tflops_sustained": 1358.9}
+# mean DRAM bytes per tcgen05 GEMM launch of this workload (ncu, profiles/r01_gemm_dram_traffic_step.csv)
+GEMM_DRAM_BYTES_PER_LAUNCH = 145.4e6
 PEAKS_FALLBACK = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -318,8 +320,11 @@ def run_ours(args):
     peaks, peak_src = measured_peaks()
     achieved = tot_fl.value / (tot_ms.value * 1e-3) / 1e12 if tot_ms.value > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "xlx::gemm_kernel<32> (tcgen05 bf16x3 GEMM, all Linear fwd/dgrad/wgrad)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "tensor", "kernel": "xlx::gemm_kernel<32,…> (tcgen05 bf16x3 GEMM, all Linear fwd/dgrad/wgrad)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": GEMM_DRAM_BYTES_PER_LAUNCH if (passes == 3 and B == BATCH) else None,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the 319 GEMM launches of "
+                                  "one step (profiles/r01_gemm_dram_traffic_step.csv)",
                 "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
                 "launches_per_step": n.value // 2, "avg_launch_us": tot_ms.value * 1e3 / max(n.value, 1),
                 "gemm_share_of_step": (tot_ms.value / 2) / ms_step,
