@@ -73,3 +73,19 @@ def test_ar_orders(sampler):
     a, _, _ = m.sample_image_AR(ids, n_steps=2, position_random=True, position_confidence=False, seed=7, return_codes=True)
     b, _, _ = m.sample_image_AR(ids, n_steps=2, position_random=True, position_confidence=False, seed=7, return_codes=True)
     assert torch.equal(a, b)
+
+
+def test_language_stack_cache_is_bit_identical(sampler):
+    """Reusing the language-only layers across sampling steps changes nothing: same kernels, same per-row arithmetic."""
+    g, m, ids = sampler
+    a = m.sample_image_NAR(ids, n_steps=3, return_codes=True, cache_language=True)
+    b = m.sample_image_NAR(ids, n_steps=3, return_codes=True, cache_language=False)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    with torch.no_grad():
+        vpos = torch.from_numpy(synth.box_position(8)).unsqueeze(0).expand(ids.shape[0], -1, -1).contiguous().cuda()
+        code = torch.rand(ids.shape[0], 64, D.feat_dim, device="cuda") * 0.1
+        full = m.bert(input_ids=ids, visual_feats=code, visual_pos=vpos, attention_mask=ids > 0)
+        lang = m.bert.language_stack(ids, ids > 0)
+        part = m.bert(input_ids=ids, visual_feats=code, visual_pos=vpos, attention_mask=ids > 0, language_stack=lang)
+    for x, y in zip(full, part):
+        assert torch.equal(x, y)

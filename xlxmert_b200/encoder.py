@@ -275,8 +275,36 @@ class B200LxmertEncoder(nn.Module):
         # a fresh arena per backward: the returned gradients are views into it
         return torch.empty(total, dtype=torch.float32, device=dev)
 
+    # -- partial passes (inference): the language layers never see the visual stream (HF:524-529), so a caller that
+    #    re-runs the encoder with the same text (the sampler, tasks/imggen_model.py:199-243) can compute them once
+    def _subpass(self, which: str) -> "B200LxmertEncoder":
+        subs = self.__dict__.setdefault("_subs", {})         # plain dict: not registered as sub-modules
+        if which not in subs:
+            from dataclasses import replace
+            d = replace(self.dims, r_layers=0, x_layers=0) if which == "lang" else replace(self.dims, l_layers=0)
+            subs[which] = B200LxmertEncoder(self, dims=d, passes=self.passes)
+        sub = subs[which]
+        sub.passes = self.passes
+        return sub
+
+    @torch.no_grad()
+    def language_stack(self, lang_feats, lang_attention_mask):
+        """Output of the ``layer`` (language-only) stack, ``[B, L, H]`` — feed it back through ``forward(...,
+        language_stack=...)``.  Inference only."""
+        B = lang_feats.shape[0]
+        dev = lang_feats.device
+        feats = torch.zeros(B, 1, self.dims.feat_dim, device=dev)
+        pos = torch.zeros(B, 1, self.dims.pos_dim, device=dev)
+        (_, _), (ls, _), _ = self._subpass("lang")(lang_feats, lang_attention_mask, feats, pos)
+        return ls[-1]
+
     def forward(self, lang_feats, lang_attention_mask, visual_feats, visual_pos, visual_attention_mask=None,
-                output_attentions=None):
+                output_attentions=None, language_stack=None):
+        if language_stack is not None:
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                raise RuntimeError("language_stack= is an inference-only shortcut; wrap the call in torch.no_grad()")
+            return self._subpass("rest")(language_stack, lang_attention_mask, visual_feats, visual_pos,
+                                         visual_attention_mask)
         if output_attentions:
             raise NotImplementedError("attention probabilities are not exported by the fused path")
         if not lang_feats.is_cuda:

@@ -44,9 +44,26 @@ class B200LxmertModel(nn.Module):
             self.pooler = B200LxmertPooler(dims, passes=passes)
         self.config = getattr(source, "config", None)
 
+    @staticmethod
+    def _additive(mask, B, S):
+        """``(1 − mask)·finfo.min`` as ``[B,1,1,S]`` (HF:766-782)."""
+        fmin = torch.finfo(torch.float32).min
+        return ((1.0 - mask.to(torch.float32)) * fmin).view(B, 1, 1, S)
+
+    @torch.no_grad()
+    def language_stack(self, input_ids, attention_mask=None, token_type_ids=None):
+        """Embeddings + the language-only layers: everything of the forward that depends on the text alone.  Pass the
+        result as ``forward(..., language_stack=...)`` when the same sentences are encoded repeatedly against
+        changing visual inputs (the sampling loops)."""
+        B, L = input_ids.shape
+        if attention_mask is None:
+            attention_mask = torch.ones(B, L, dtype=torch.bool, device=input_ids.device)
+        emb = self.embeddings(input_ids, token_type_ids)
+        return self.encoder.language_stack(emb, self._additive(attention_mask, B, L))
+
     def forward(self, input_ids=None, visual_feats=None, visual_pos=None, attention_mask=None,
                 visual_attention_mask=None, token_type_ids=None, inputs_embeds=None, output_attentions=None,
-                output_hidden_states=None, return_dict=None, **kw):
+                output_hidden_states=None, return_dict=None, language_stack=None, **kw):
         if output_attentions:
             raise NotImplementedError("attention probabilities are not exported by the fused path")
         if visual_feats is None or visual_pos is None:
@@ -64,14 +81,20 @@ class B200LxmertModel(nn.Module):
         if visual_attention_mask is not None:
             V = visual_feats.shape[1]
             vmask = ((1.0 - visual_attention_mask.to(torch.float32)) * fmin).view(B, 1, 1, V)
-        emb = self.embeddings(input_ids, token_type_ids, inputs_embeds)
         want_hidden = bool(output_hidden_states)
-        prev = self.encoder.output_hidden_states
-        self.encoder.output_hidden_states = want_hidden
-        try:
-            (vis_states, _), (lang_states, _), _ = self.encoder(emb, lmask, visual_feats, visual_pos, vmask)
-        finally:
-            self.encoder.output_hidden_states = prev
+        if language_stack is not None:
+            if want_hidden:
+                raise NotImplementedError("output_hidden_states with a cached language stack")
+            (vis_states, _), (lang_states, _), _ = self.encoder(None, lmask, visual_feats, visual_pos, vmask,
+                                                                 language_stack=language_stack)
+        else:
+            emb = self.embeddings(input_ids, token_type_ids, inputs_embeds)
+            prev = self.encoder.output_hidden_states
+            self.encoder.output_hidden_states = want_hidden
+            try:
+                (vis_states, _), (lang_states, _), _ = self.encoder(emb, lmask, visual_feats, visual_pos, vmask)
+            finally:
+                self.encoder.output_hidden_states = prev
         lang, vis = lang_states[-1], vis_states[-1]
         pooled = self.pooler(lang)
         return LxmertOutput(lang, vis, pooled, lang_states if want_hidden else None,

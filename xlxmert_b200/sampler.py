@@ -63,9 +63,12 @@ class B200ImggenModel(nn.Module):
         ids = self.tokenizer(sentences, max_length=max_text_length, truncation=True, return_tensors='pt').input_ids
         return ids.to(dev)
 
-    def _predict(self, input_ids, code, visual_pos):
-        """One full pass: LXMERT → cluster head → ``softmax(2).max(2)`` (imggen_model.py:221-235)."""
-        out = self.bert(input_ids=input_ids, visual_feats=code, visual_pos=visual_pos, attention_mask=input_ids > 0)
+    def _predict(self, input_ids, code, visual_pos, language_stack=None):
+        """One pass: LXMERT → cluster head → ``softmax(2).max(2)`` (imggen_model.py:221-235).  The reference re-runs
+        the nine language-only layers on the unchanged text at every step; with ``language_stack`` they are reused
+        (bit-identical result, tests/test_sampler.py)."""
+        out = self.bert(input_ids=input_ids, visual_feats=code, visual_pos=visual_pos, attention_mask=input_ids > 0,
+                        language_stack=language_stack)
         return self.obj_predict_head.predict(out[1])
 
     def _decode(self, code, B, code_dim, grid_size):
@@ -74,7 +77,7 @@ class B200ImggenModel(nn.Module):
     # -- samplers ------------------------------------------------------------------------------------
     @torch.no_grad()
     def sample_image_NAR(self, sentences, max_text_length=20, n_steps=None, return_intermediate=False,
-                         return_codes=False):
+                         return_codes=False, cache_language=True):
         """Mask-predict sampling with linear decay (imggen_model.py:169-257)."""
         self.eval()
         input_ids = self._input_ids(sentences, max_text_length)
@@ -86,6 +89,7 @@ class B200ImggenModel(nn.Module):
         visual_pos = torch.from_numpy(box_position(grid_size)).unsqueeze(0).expand(B, -1, -1).contiguous().to(dev)
         intermediate_imgs = []
         pred_prob = pred_code_id = None
+        lang = self.bert.language_stack(input_ids, input_ids > 0) if cache_language else None
         for i in range(n_steps):
             n_mask = int((n_steps - i) / n_steps * n_grids)
             if i == 0:
@@ -97,7 +101,7 @@ class B200ImggenModel(nn.Module):
                 vis_mask.scatter_(1, lowest_arg, 1)
             m = vis_mask.view(B, n_grids, 1).bool()
             code = torch.where(m, self.mask_feat.view(1, 1, -1).to(code.dtype), code)
-            pred_prob, pred_code_id = self._predict(input_ids, code, visual_pos)
+            pred_prob, pred_code_id = self._predict(input_ids, code, visual_pos, lang)
             code = torch.where(m, self.vis_emb(pred_code_id), code)
             if return_intermediate:
                 intermediate_imgs.append(self._decode(code, B, code_dim, grid_size))
@@ -110,7 +114,7 @@ class B200ImggenModel(nn.Module):
     @torch.no_grad()
     def sample_image_AR(self, sentences, max_text_length=20, position_random=False, position_TLBR=False,
                         position_confidence=True, n_steps=None, seed=None, return_intermediate=False,
-                        return_codes=False):
+                        return_codes=False, cache_language=True):
         """One grid cell per step (imggen_model.py:49-167): random, raster (TLBR) or highest-confidence order."""
         self.eval()
         input_ids = self._input_ids(sentences, max_text_length)
@@ -134,6 +138,7 @@ class B200ImggenModel(nn.Module):
         vis_mask = torch.ones(B, n_grids, dtype=torch.long, device=dev)
         code = torch.zeros(B, n_grids, code_dim, device=dev)
         current = None
+        lang = self.bert.language_stack(input_ids, input_ids > 0) if cache_language else None
         for i in range(n_steps):
             if position_random:
                 current = positions.pop() % n_grids
@@ -141,7 +146,7 @@ class B200ImggenModel(nn.Module):
             elif position_TLBR:
                 current = i
             code = torch.where(vis_mask.view(B, n_grids, 1).bool(), self.mask_feat.view(1, 1, -1).to(code.dtype), code)
-            pred_prob, pred_code_id = self._predict(input_ids, code, visual_pos)
+            pred_prob, pred_code_id = self._predict(input_ids, code, visual_pos, lang)
             if position_TLBR or position_random:
                 update_mask = torch.zeros(B, n_grids, dtype=torch.bool, device=dev)
                 update_mask[:, current] = True
