@@ -107,7 +107,7 @@ def time_cpu(B: int, steps: int, warmup: int):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     Bs = 8
     cb, dt = time_cpu(Bs, max(1, args.steps), max(1, min(args.warmup, 2)))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -117,7 +117,7 @@ def run_reference(args):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    return line
 
 
 def workload_config(n_gpus, extra=None):
@@ -195,11 +195,9 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    import contextlib
     import __graft_entry__ as entry
     if rank == 0:
-        with contextlib.redirect_stdout(sys.stderr):      # stdout carries exactly one line: the JSON result
-            entry.build()
+        entry.build()
     if world > 1:
         dist.barrier()
     from xlxmert_b200 import _lib, params as P, synth
@@ -231,8 +229,12 @@ def run_ours(args):
     g_lang = (torch.randn(B, L_TOK, D.hidden, generator=g) / (B * L_TOK)).to(dev)
     g_vis = (torch.randn(B, V_GRID, D.hidden, generator=g) / (B * V_GRID)).to(dev)
 
+    from xlxmert_b200.parallel import allreduce_gradients, enable_overlapped_gradient_sync
+    if world > 1 and not args.no_overlap:
+        enable_overlapped_gradient_sync(model)      # stage-wise all-reduce inside the backward
+
     def allreduce_grads():
-        if world > 1:
+        if world > 1 and not enc.arena_reduced:
             arena = enc.last_grad_arena
             dist.all_reduce(arena)
             arena.mul_(1.0 / world)
@@ -254,8 +256,6 @@ def run_ours(args):
     loss_h = torch.empty((), dtype=torch.float32).pin_memory()
     h2d = ids_h.numel() * 8 + mask_h.numel() * 1 + cids_h.numel() * 8
     d2h = 4
-
-    from xlxmert_b200.parallel import allreduce_gradients
 
     def step_e2e():
         enc.invalidate_prepared()
@@ -301,8 +301,7 @@ def run_ours(args):
         for _ in range(args.warmup + args.steps):
             step_resident()
         torch.cuda.synchronize()
-        print(json.dumps({"ncu_mode": True, "launches_per_step": int(lib.xlx_launch_count()) // (args.warmup + args.steps)}))
-        return
+        return {"ncu_mode": True, "launches_per_step": int(lib.xlx_launch_count()) // (args.warmup + args.steps)}
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -351,10 +350,12 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             cb, _ = time_cpu(8, 2, 1)
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+    else:
+        line = None
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -366,12 +367,22 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--passes", type=int, default=3, choices=[1, 3])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce after the backward instead of stage-wise")
     ap.add_argument("--ncu", action="store_true", help="profiler mode: run warmup+steps resident steps and exit")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE line, the JSON result: everything libraries print while we run (build messages, NCCL's
+    # version banner, …) is routed to stderr at the file-descriptor level
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -94,11 +94,24 @@ int32_t xlx_encoder_fwd(const xlx_dims* d, const float* const* params, const voi
 /* Backward of the above (the reference gets it from torch autograd: lxmert_pretrain.py:338).
  * d_lang_out / d_vis_out: gradients wrt the two outputs (NULL = zero).  Writes d_lang_in [B,L,H],
  * d_visual_feats [B,V,F] (NULL to skip) and every parameter gradient into `grads` (overwritten, not
- * accumulated). */
+ * accumulated).
+ * `stages` is a mask of XLX_BWD_* (XLX_BWD_ALL for the whole backward).  The stages must be issued in the order
+ * CROSS, VISION, LANGUAGE, VISN_FC, in one call or several (the state between stages lives in the workspace): a
+ * data-parallel caller enqueues the all-reduce of the gradient-arena range a stage completed
+ * (xlx_encoder_grad_stage_range) while the next stage computes — the overlap DistributedDataParallel gets from its
+ * bucket hooks (lxmert_pretrain.py:102-106), with four static buckets instead of an autograd-graph walk. */
+enum {
+  XLX_BWD_CROSS = 1,    /* x_layers (last in the forward, first in the backward) */
+  XLX_BWD_VISION = 2,   /* r_layers */
+  XLX_BWD_LANGUAGE = 4, /* layer.* and d_lang_in */
+  XLX_BWD_VISN_FC = 8,  /* visn_fc and d_visual_feats */
+  XLX_BWD_ALL = 15
+};
 int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const void* prep, int32_t B, int32_t L,
                         int32_t V, const float* visual_pos, const float* d_lang_out, const float* d_vis_out,
                         float* d_lang_in, float* d_visual_feats, float* grads, void* workspace,
-                        size_t workspace_bytes, int32_t passes, void* stream);
+                        size_t workspace_bytes, int32_t passes, int32_t stages, void* stream);
+int32_t xlx_encoder_grad_stage_range(const xlx_dims* d, int32_t stage, int64_t* offset, int64_t* elems);
 
 /* ---- visual input of XLxmertForPretraining.forward (x-lxmert/src/lxrt/modeling.py:185-193) ----------------------
  * out[r,:] = vis_mask[r] ? mask_feat[:] : table[cluster_ids[r],:]   (vis_emb gather + torch.where), r < rows.

@@ -87,3 +87,25 @@ def test_product_path_has_no_cpu_fallback():
     ids = torch.ones(1, 4, dtype=torch.long)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(input_ids=ids, visual_feats=torch.zeros(1, 4, TINY_DIMS.feat_dim), visual_pos=torch.zeros(1, 4, 4))
+
+
+def test_backward_stage_ranges_tile_the_gradient_arena():
+    """The four backward stages complete disjoint arena ranges that together cover it (what the overlapped
+    data-parallel exchange relies on)."""
+    from xlxmert_b200 import _lib
+    from xlxmert_b200.config import DEFAULT_DIMS as D, TINY_DIMS
+    lib = _lib.load()
+    for dims in (D, TINY_DIMS):
+        cd = _lib.XlxDims.from_dims(dims)
+        total = lib.xlx_encoder_grad_elems(C.byref(cd))
+        spans = []
+        for stage in (1, 2, 4, 8):
+            off, n = C.c_int64(), C.c_int64()
+            assert lib.xlx_encoder_grad_stage_range(C.byref(cd), stage, C.byref(off), C.byref(n)) == 0
+            spans.append((off.value, n.value))
+        spans.sort()
+        assert spans[0][0] == 0 and sum(n for _, n in spans) == total
+        for (o0, n0), (o1, _) in zip(spans, spans[1:]):
+            assert o0 + n0 == o1
+        off, n = C.c_int64(), C.c_int64()
+        assert lib.xlx_encoder_grad_stage_range(C.byref(cd), 3, C.byref(off), C.byref(n)) == -25

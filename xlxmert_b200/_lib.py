@@ -61,7 +61,9 @@ def _sig(lib):
     lib.xlx_encoder_fwd.restype = I32
     lib.xlx_encoder_fwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, SZ, I32, I32, P]
     lib.xlx_encoder_bwd.restype = I32
-    lib.xlx_encoder_bwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, SZ, I32, P]
+    lib.xlx_encoder_bwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, SZ, I32, I32, P]
+    lib.xlx_encoder_grad_stage_range.restype = I32
+    lib.xlx_encoder_grad_stage_range.argtypes = [D, I32, C.POINTER(I64), C.POINTER(I64)]
     PP = P
     lib.xlx_embeddings_save_bytes.restype = SZ
     lib.xlx_embeddings_save_bytes.argtypes = [D, I32, I32]

@@ -497,6 +497,7 @@ const char* xlx_strerror(int32_t code) {
     case -22: return "sequence length > 64 is not supported by the attention kernel";
     case -23: return "workspace too small";
     case -24: return "null pointer argument";
+    case -25: return "invalid backward stage mask";
     default: return code > 0 ? "CUDA error (see cudaGetErrorString)" : "unknown error";
   }
 }
@@ -641,10 +642,11 @@ int32_t xlx_encoder_fwd(const xlx_dims* d, const float* const* params, const voi
 int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const void* prep, int32_t B, int32_t L,
                         int32_t V, const float* visual_pos, const float* d_lang_out, const float* d_vis_out,
                         float* d_lang_in, float* d_visual_feats, float* grads, void* workspace,
-                        size_t workspace_bytes, int32_t passes, void* stream) {
+                        size_t workspace_bytes, int32_t passes, int32_t stages, void* stream) {
   XLX_TRY(check_common(d, B, L, V));
   if (!params || !prep || !visual_pos || !d_lang_in || !grads || !workspace) return -24;
   if (passes != 1 && passes != 3) return -1;
+  if (stages <= 0 || stages > XLX_BWD_ALL) return -25;
   XLX_TRY(ensure_device(workspace));
   Run r;
   r.d = d; r.params = params; r.passes = passes; r.st = static_cast<cudaStream_t>(stream);
@@ -659,41 +661,47 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
   const int nl = d->l_layers, nr = d->r_layers, nx = d->x_layers;
   const size_t lh = static_cast<size_t>(Ml) * H, vh = static_cast<size_t>(Mv) * H;
 
-  // gradient state: [language rows | vision rows], ping-pong between dA and dB
+  // gradient state: [language rows | vision rows], ping-pong between dA and dB (it lives in the workspace, so the
+  // stages of one backward may be issued by separate calls; after the cross-modality stage the roles have swapped
+  // x_layers times)
   float* cur = p.dA;
   float* nxt = p.dB;
-  auto load_grad = [&](float* dst, const float* src, size_t n) -> int {
-    cudaError_t e = src ? cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, r.st)
-                        : cudaMemsetAsync(dst, 0, n * 4, r.st);
-    return e == cudaSuccess ? 0 : static_cast<int>(e);
-  };
-  XLX_TRY(load_grad(cur, d_lang_out, lh));
-  XLX_TRY(load_grad(cur + lh, d_vis_out, vh));
-
-  for (int k = nx - 1; k >= 0; --k) {
-    const int a0 = nl + nr + 3 * k, f0 = nl + nr + 2 * k;
-    XLX_TRY(ffn_bwd(bw, f0, cur, nxt));
-    XLX_TRY(ffn_bwd(bw, f0 + 1, cur + lh, nxt + lh));
-    XLX_TRY(att_self_bwd(bw, a0 + 1, L, nxt, cur));
-    XLX_TRY(att_self_bwd(bw, a0 + 2, V, nxt + lh, cur + lh));
-    XLX_TRY(att_cross_bwd(bw, a0, cur, nxt));
-    float* t = cur; cur = nxt; nxt = t;
+  if (stages & XLX_BWD_CROSS) {
+    auto load_grad = [&](float* dst, const float* src, size_t n) -> int {
+      cudaError_t e = src ? cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, r.st)
+                          : cudaMemsetAsync(dst, 0, n * 4, r.st);
+      return e == cudaSuccess ? 0 : static_cast<int>(e);
+    };
+    XLX_TRY(load_grad(cur, d_lang_out, lh));
+    XLX_TRY(load_grad(cur + lh, d_vis_out, vh));
+    for (int k = nx - 1; k >= 0; --k) {
+      const int a0 = nl + nr + 3 * k, f0 = nl + nr + 2 * k;
+      XLX_TRY(ffn_bwd(bw, f0, cur, nxt));
+      XLX_TRY(ffn_bwd(bw, f0 + 1, cur + lh, nxt + lh));
+      XLX_TRY(att_self_bwd(bw, a0 + 1, L, nxt, cur));
+      XLX_TRY(att_self_bwd(bw, a0 + 2, V, nxt + lh, cur + lh));
+      XLX_TRY(att_cross_bwd(bw, a0, cur, nxt));
+      float* t = cur; cur = nxt; nxt = t;
+    }
+  } else if (nx & 1) {
+    cur = p.dB; nxt = p.dA;
   }
-  for (int i = nr - 1; i >= 0; --i) {
-    XLX_TRY(ffn_bwd(bw, nl + i, cur + lh, nxt + lh));
-    XLX_TRY(att_self_bwd(bw, nl + i, V, nxt + lh, cur + lh));
+  if (stages & XLX_BWD_VISION) {
+    for (int i = nr - 1; i >= 0; --i) {
+      XLX_TRY(ffn_bwd(bw, nl + i, cur + lh, nxt + lh));
+      XLX_TRY(att_self_bwd(bw, nl + i, V, nxt + lh, cur + lh));
+    }
   }
-  for (int i = nl - 1; i >= 0; --i) {
-    XLX_TRY(ffn_bwd(bw, i, cur, nxt));
-    XLX_TRY(att_self_bwd(bw, i, L, nxt, cur));
+  if (stages & XLX_BWD_LANGUAGE) {
+    for (int i = nl - 1; i >= 0; --i) {
+      XLX_TRY(ffn_bwd(bw, i, cur, nxt));
+      XLX_TRY(att_self_bwd(bw, i, L, nxt, cur));
+    }
+    // language embedding gradient
+    XLX_CUDA(cudaMemcpyAsync(d_lang_in, cur, lh * 4, cudaMemcpyDeviceToDevice, r.st));
   }
-  // language embedding gradient
-  {
-    cudaError_t e = cudaMemcpyAsync(d_lang_in, cur, lh * 4, cudaMemcpyDeviceToDevice, r.st);
-    if (e != cudaSuccess) return static_cast<int>(e);
-  }
-  // visual feature encoder backward
-  {
+  if (stages & XLX_BWD_VISN_FC) {
+    // visual feature encoder backward
     const float* dvis = cur + lh;
     int nblk = 0;
     // box branch: d(0.5·LN_b(y2))
@@ -713,6 +721,27 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
       XLX_TRY(dgrad(r, p.dy_s, Mv, H, r.prep.visn_w_t, F, e));
     }
   }
+  return 0;
+}
+
+// Element range [*offset, *offset + *elems) of the gradient arena completed by one backward stage.
+int32_t xlx_encoder_grad_stage_range(const xlx_dims* d, int32_t stage, int64_t* offset, int64_t* elems) {
+  if (!dims_ok(d)) return -20;
+  if (!offset || !elems) return -24;
+  SlotTable t = slot_table(d);
+  const int nlr_slots = (N_ATT + N_FFN);
+  const int s_l0 = N_VISN, s_r0 = N_VISN + d->l_layers * nlr_slots, s_x0 = s_r0 + d->r_layers * nlr_slots;
+  const int s_end = static_cast<int>(t.elems.size());
+  int a, b;
+  switch (stage) {
+    case XLX_BWD_CROSS: a = s_x0; b = s_end; break;
+    case XLX_BWD_VISION: a = s_r0; b = s_x0; break;
+    case XLX_BWD_LANGUAGE: a = s_l0; b = s_r0; break;
+    case XLX_BWD_VISN_FC: a = 0; b = s_l0; break;
+    default: return -25;
+  }
+  *offset = a < s_end ? t.offset[a] : t.total;
+  *elems = (b < s_end ? t.offset[b] : t.total) - *offset;
   return 0;
 }
 

@@ -100,6 +100,16 @@ class _EncoderSkeleton(nn.Module):
 
 
 # ---- autograd bridge -------------------------------------------------------------------------------
+_BWD_STAGES = (1, 2, 4, 8)      # XLX_BWD_CROSS, _VISION, _LANGUAGE, _VISN_FC (include/xlxmert_b200.h), in issue order
+_BWD_ALL = 15
+
+
+def _dist_active(group) -> bool:
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return False
+    return dist.get_world_size(None if group is True else group) > 1
+
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
@@ -167,11 +177,36 @@ class _EncoderFn(torch.autograd.Function):
         d_feats = torch.empty(B, V, d.feat_dim, device=dev, dtype=torch.float32) if ctx.need_dfeats else None
         grads = enc._grad_arena(dev)
         enc.last_grad_arena = grads
-        rc = lib.xlx_encoder_bwd(C.byref(enc._cdims), ctx.parr, ctx.prep.data_ptr(), B, L, V,
-                                 ctx.visual_pos.data_ptr(), _ptr(d_lang_out), _ptr(d_vis_out),
-                                 d_lang_in.data_ptr(), _ptr(d_feats), grads.data_ptr(), ctx.ws.data_ptr(),
-                                 ctx.ws_bytes, enc.passes, _stream_ptr())
-        _lib.check("xlx_encoder_bwd", rc)
+        enc.arena_reduced = False
+
+        def run(stages):
+            rc = lib.xlx_encoder_bwd(C.byref(enc._cdims), ctx.parr, ctx.prep.data_ptr(), B, L, V,
+                                     ctx.visual_pos.data_ptr(), _ptr(d_lang_out), _ptr(d_vis_out),
+                                     d_lang_in.data_ptr(), _ptr(d_feats), grads.data_ptr(), ctx.ws.data_ptr(),
+                                     ctx.ws_bytes, enc.passes, stages, _stream_ptr())
+            _lib.check("xlx_encoder_bwd", rc)
+
+        group = enc.grad_sync_group
+        if group is None or not _dist_active(group):
+            run(_BWD_ALL)
+        else:
+            # data parallel: all-reduce each stage's slice of the arena while the next stage computes
+            import torch.distributed as dist
+            world = dist.get_world_size(None if group is True else group)
+            pg = None if group is True else group
+            avg = dist.get_backend(pg) == "nccl"
+            works = []
+            for stage in _BWD_STAGES:
+                run(stage)
+                off, n = enc._stage_range(stage)
+                if n:
+                    works.append(dist.all_reduce(grads[off:off + n], op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM,
+                                                 group=pg, async_op=True))
+            for w in works:
+                w.wait()
+            if not avg:
+                grads.mul_(1.0 / world)
+            enc.arena_reduced = True
         enc._release_workspace(ctx.ws)
         pgrads = []
         for p, (off, n) in zip(ctx.params, enc._grad_slices):
@@ -217,6 +252,12 @@ class B200LxmertEncoder(nn.Module):
         #: flat fp32 arena holding every parameter gradient of the most recent backward (the ``.grad`` tensors
         #: are views into it) — one contiguous buffer for the data-parallel all-reduce (lxmert_pretrain.py:104-106)
         self.last_grad_arena: Optional[torch.Tensor] = None
+        #: set to ``True`` (default process group) or a ``ProcessGroup`` to have the backward all-reduce (mean) its
+        #: gradient arena stage by stage, overlapped with the remaining backward; ``arena_reduced`` then tells
+        #: ``parallel.allreduce_gradients`` that nothing is left to do for this module
+        self.grad_sync_group = None
+        self.arena_reduced = False
+        self._stage_ranges = {}
 
     # -- parameters in C-ABI slot order
     def _param_list(self) -> List[torch.Tensor]:
@@ -264,6 +305,14 @@ class B200LxmertEncoder(nn.Module):
         self._ws_busy = [b for b in self._ws_busy if b is not t]
         if len(self._ws_pool) < 2:
             self._ws_pool.append(t)
+
+    def _stage_range(self, stage: int):
+        if stage not in self._stage_ranges:
+            off, n = C.c_int64(), C.c_int64()
+            _lib.check("xlx_encoder_grad_stage_range",
+                       _lib.load().xlx_encoder_grad_stage_range(C.byref(self._cdims), stage, C.byref(off), C.byref(n)))
+            self._stage_ranges[stage] = (off.value, n.value)
+        return self._stage_ranges[stage]
 
     def _grad_arena(self, dev) -> torch.Tensor:
         lib = _lib.load()

@@ -40,10 +40,12 @@ def allreduce_gradients(model: torch.nn.Module, group: Optional[dist.ProcessGrou
                 and p.grad.untyped_storage().data_ptr() == arena.untyped_storage().data_ptr()]
         if not live:
             continue
+        in_arena.update(id(p) for p in live)
+        if getattr(enc, "arena_reduced", False):     # already exchanged stage by stage inside the backward
+            continue
         dist.all_reduce(arena, group=group)
         if average:
             arena.mul_(1.0 / world)
-        in_arena.update(id(p) for p in live)
         calls += 1
     rest = [p for p in model.parameters() if p.grad is not None and id(p) not in in_arena]
     # a tied parameter (decoder.weight ≡ word_embeddings.weight) appears once in model.parameters()
@@ -59,6 +61,15 @@ def allreduce_gradients(model: torch.nn.Module, group: Optional[dist.ProcessGrou
             off += n
         calls += 1
     return calls
+
+
+def enable_overlapped_gradient_sync(model: torch.nn.Module, group=True) -> None:
+    """Make every native encoder inside ``model`` all-reduce its gradient arena during its own backward, one stage
+    (cross-modality / vision / language / visual-feature layers) at a time, so the NVLink traffic hides behind the
+    remaining backward compute — what DDP's bucketed hooks do for the reference (lxmert_pretrain.py:102-106).
+    ``allreduce_gradients`` afterwards only handles the parameters outside the encoders."""
+    for enc in _encoders(model):
+        enc.grad_sync_group = group
 
 
 def shard_batch(batch: dict, rank: int, world: int) -> dict:
