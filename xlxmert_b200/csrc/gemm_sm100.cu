@@ -81,7 +81,11 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& y, float& dy) {
 struct EpiIn { float4 a; uint2 h, l; };
 __device__ __forceinline__ void epilogue_fetch(const KParams& P, int row, int n, EpiIn& in) {
   const GemmEpilogue& E = P.epi;
-  if (E.flags & (EPI_MUL | EPI_GELU_GRAD))
+  if ((E.flags & EPI_MUL) && E.u_in16) {
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(E.u_in16 + static_cast<size_t>(row) * E.ld_u + n));
+    in.a = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                       __uint_as_float(w.y & 0xffff0000u));
+  } else if (E.flags & (EPI_MUL | EPI_GELU_GRAD))
     in.a = __ldg(reinterpret_cast<const float4*>(E.u_in + static_cast<size_t>(row) * E.ld_u + n));
   else if (E.addend)
     in.a = __ldg(reinterpret_cast<const float4*>(E.addend + static_cast<size_t>(row) * E.ld_addend + n));
@@ -98,7 +102,7 @@ __device__ __forceinline__ void epilogue_fetch(const KParams& P, int row, int n,
 // consecutive columns of the same row, so every global access below covers whole 32-byte sectors (64-byte fp32 /
 // 32-byte bf16 segments per row).
 template <bool ACT>
-__device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, float4 acc, const EpiIn& in) {
+__device__ __forceinline__ float4 epilogue_vec4(const KParams& P, int row, int n, float4 acc, const EpiIn& in) {
   const GemmEpilogue& E = P.epi;
   float v[4] = {acc.x * E.alpha, acc.y * E.alpha, acc.z * E.alpha, acc.w * E.alpha};
   if (E.bias) {
@@ -115,6 +119,10 @@ __device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, 
     }
     if (E.out_u)
       *reinterpret_cast<float4*>(E.out_u + static_cast<size_t>(row) * E.ld_u + n) = make_float4(dg[0], dg[1], dg[2], dg[3]);
+    if (E.out_u16)
+      *reinterpret_cast<uint2*>(E.out_u16 + static_cast<size_t>(row) * E.ld_u + n) =
+          make_uint2(pack_bf16x2(__float2bfloat16_rn(dg[0]), __float2bfloat16_rn(dg[1])),
+                     pack_bf16x2(__float2bfloat16_rn(dg[2]), __float2bfloat16_rn(dg[3])));
   } else if (E.out_u) {
     *reinterpret_cast<float4*>(E.out_u + static_cast<size_t>(row) * E.ld_u + n) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -160,6 +168,7 @@ __device__ __forceinline__ void epilogue_vec4(const KParams& P, int row, int n, 
     if (E.out_lo)
       *reinterpret_cast<uint2*>(E.out_lo + idx) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
   }
+  return make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // A_MN / B_MN: operand stored MN-major; NPARTS: 1 = hi only (1 pass), 2 = hi + lo (3 passes).  Compile-time so that
@@ -429,11 +438,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
             const int row = m0 + q * 32 + it * 8 + sub;
             if (row < P.M && col_ok) epilogue_fetch(P, row, n, in[it]);
           }
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int rr = it * 8 + sub, row = m0 + q * 32 + rr;
             const float4 acc = *reinterpret_cast<const float4*>(stage + rr * EPI_COLS + ((cq ^ ((rr >> 1) & 3)) << 2));
-            if (row < P.M && col_ok) epilogue_vec4<false>(P, row, n, acc, in[it]);
+            if (row < P.M && col_ok) {
+              const float4 v = epilogue_vec4<false>(P, row, n, acc, in[it]);
+              cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+            }
+          }
+          if (P.epi.colsum_part) {   // sums over this warp's 32 rows: fold the 8 row lanes, lanes 0-3 write 16 columns
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+            }
+            if (sub == 0 && col_ok && m0 + q * 32 < P.M)
+              *reinterpret_cast<float4*>(P.epi.colsum_part + static_cast<size_t>((m0 >> 5) + q) * P.N + n) = cs;
           }
         }
         __syncwarp();
@@ -855,9 +877,12 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream) {
     return -2;
   const GemmEpilogue& E = p.epi;
   if ((E.out_f32 && (E.ld_out % 4)) || (E.out_hi && (E.ld_split % 4)) ||
-      ((E.addend || E.addend_hi) && (E.ld_addend % 4)) || ((E.out_u || E.u_in) && (E.ld_u % 4)))
+      ((E.addend || E.addend_hi) && (E.ld_addend % 4)) ||
+      ((E.out_u || E.u_in || E.out_u16 || E.u_in16) && (E.ld_u % 4)))
     return -2;
-  if ((E.flags & (EPI_GELU_GRAD | EPI_MUL)) && !E.u_in) return -1;
+  if ((E.flags & EPI_GELU_GRAD) && !E.u_in) return -1;
+  if (E.colsum_part && ((E.flags & (EPI_GELU | EPI_TANH | EPI_RELU | EPI_GELU_GRAD)) || p.splitk_ws)) return -1;
+  if ((E.flags & EPI_MUL) && !E.u_in && !E.u_in16) return -1;
   if (E.addend_hi && !E.addend_lo) return -1;
   return launch_bk<32>(p, stream);
 }

@@ -40,8 +40,13 @@ struct GemmEpilogue {
   const __nv_bfloat16* addend_lo = nullptr;
   float* out_f32 = nullptr;         // [M, ld_out]
   float* out_u = nullptr;           // [M, ld_u] pre-activation save (EPI_GELU)
+  __nv_bfloat16* out_u16 = nullptr; // same save as bf16 (e.g. gelu' for the backward: a multiplier, 8 bits suffice)
+  const __nv_bfloat16* u_in16 = nullptr;  // bf16 multiplier for EPI_MUL (instead of u_in)
   __nv_bfloat16* out_hi = nullptr;  // [M, ld_split]
   __nv_bfloat16* out_lo = nullptr;
+  // Optional column sums of the final values (a bias gradient for free): every epilogue warp writes the sums over its
+  // 32 rows, colsum_part[(m / 32), n] with m / 32 < 4·ceil(M/128); reduce the rows with colsum_finish (fixed order).
+  float* colsum_part = nullptr;
   int ld_addend = 0, ld_u = 0, ld_out = 0, ld_split = 0;
   int flags = 0;
   float alpha = 1.0f;               // v = alpha * acc before bias
