@@ -89,3 +89,13 @@ def test_language_stack_cache_is_bit_identical(sampler):
         part = m.bert(input_ids=ids, visual_feats=code, visual_pos=vpos, attention_mask=ids > 0, language_stack=lang)
     for x, y in zip(full, part):
         assert torch.equal(x, y)
+
+
+def test_cuda_graph_replay_matches_eager(sampler):
+    """The captured per-step graph (encoder rest → head → arg-max) replays to the same codes as eager launches."""
+    g, m, ids = sampler
+    a = m.sample_image_NAR(ids, n_steps=3, return_codes=True)
+    b = m.sample_image_NAR(ids, n_steps=3, return_codes=True, cuda_graph=True)
+    c = m.sample_image_NAR(ids, n_steps=3, return_codes=True, cuda_graph=True)     # second run: pure replay
+    for x, y, z in zip(a, b, c):
+        assert torch.equal(x, y) and torch.equal(x, z)

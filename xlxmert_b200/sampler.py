@@ -71,13 +71,42 @@ class B200ImggenModel(nn.Module):
                         language_stack=language_stack)
         return self.obj_predict_head.predict(out[1])
 
+    # -- CUDA-graph replay of the per-step device work -----------------------------------------------------------
+    # At sampling batch sizes the step (≈ 150 kernels of a few µs each) is launch-bound; the whole pass — rest of the
+    # encoder on the cached language stack → cluster head → softmax-max/arg-max — is captured once per (B, L) into a
+    # CUDA graph over static buffers and replayed every step.
+    def _graph_predict(self, input_ids, code, visual_pos, language_stack):
+        key = (tuple(input_ids.shape), code.device.index)
+        st = self.__dict__.setdefault("_graphs", {}).get(key)
+        if st is None:
+            st = {"code": torch.empty_like(code), "lang": torch.empty_like(language_stack),
+                  "ids": input_ids.clone(), "pos": visual_pos.clone()}
+            st["code"].copy_(code)
+            st["lang"].copy_(language_stack)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up outside capture: weight prep, lazy function attributes
+                for _ in range(2):
+                    self._predict(st["ids"], st["code"], st["pos"], st["lang"])
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["prob"], st["id"] = self._predict(st["ids"], st["code"], st["pos"], st["lang"])
+            st["graph"] = g
+            self._graphs[key] = st
+        st["code"].copy_(code)
+        st["lang"].copy_(language_stack)
+        st["ids"].copy_(input_ids)
+        st["graph"].replay()
+        return st["prob"].clone(), st["id"].clone()
+
     def _decode(self, code, B, code_dim, grid_size):
         return self.denorm(self.G(code.permute(0, 2, 1).view(B, code_dim, grid_size, grid_size))).cpu()
 
     # -- samplers ------------------------------------------------------------------------------------
     @torch.no_grad()
     def sample_image_NAR(self, sentences, max_text_length=20, n_steps=None, return_intermediate=False,
-                         return_codes=False, cache_language=True):
+                         return_codes=False, cache_language=True, cuda_graph=False):
         """Mask-predict sampling with linear decay (imggen_model.py:169-257)."""
         self.eval()
         input_ids = self._input_ids(sentences, max_text_length)
@@ -101,7 +130,10 @@ class B200ImggenModel(nn.Module):
                 vis_mask.scatter_(1, lowest_arg, 1)
             m = vis_mask.view(B, n_grids, 1).bool()
             code = torch.where(m, self.mask_feat.view(1, 1, -1).to(code.dtype), code)
-            pred_prob, pred_code_id = self._predict(input_ids, code, visual_pos, lang)
+            if cuda_graph and lang is not None:
+                pred_prob, pred_code_id = self._graph_predict(input_ids, code, visual_pos, lang)
+            else:
+                pred_prob, pred_code_id = self._predict(input_ids, code, visual_pos, lang)
             code = torch.where(m, self.vis_emb(pred_code_id), code)
             if return_intermediate:
                 intermediate_imgs.append(self._decode(code, B, code_dim, grid_size))
