@@ -220,6 +220,25 @@ int32_t xlx_generator_fwd(const float* const* params, const void* prep, int32_t 
                           const float* const* noise, float* img, float* pre_tanh, float* const* block_out,
                           void* workspace, size_t workspace_bytes, int32_t passes, void* stream);
 
+/* ---- optimiser step of the pre-training loop ---------------------------------------------
+ * x-lxmert/src/pretrain/lxmert_pretrain.py:343-364: torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0) then
+ * transformers.optimization.AdamW.step() (4.1.1: betas (0.9, 0.999), eps 1e-6, correct_bias, weight decay applied
+ * after the Adam update as p -= lr·wd·p; :110-141 builds the two decay groups).  All arrays are HOST arrays of n
+ * entries (device pointers / element counts / per-tensor weight decay); tensors must be 16-byte aligned.
+ *   xlx_grad_sqnorm: *out (device scalar) = Σ over all tensors of ‖g‖² (deterministic two-stage reduction);
+ *                    scratch: xlx_optim_scratch_floats(elems, n) floats.
+ *   xlx_adamw_step:  in-place update of params / exp_avg / exp_avg_sq; `step` is the 1-based update count.
+ *                    sqnorm (device scalar from xlx_grad_sqnorm, or NULL) with max_grad_norm > 0 applies the clip
+ *                    coefficient min(1, max_norm / (sqrt(sqnorm) + 1e-6)) to the gradients on the fly. */
+int64_t xlx_optim_scratch_floats(const int64_t* elems, int32_t n);
+int64_t xlx_optim_launch_count(void);
+int32_t xlx_grad_sqnorm(const float* const* grads, const int64_t* elems, int32_t n, float* scratch, float* out,
+                        void* stream);
+int32_t xlx_adamw_step(float* const* params, const float* const* grads, float* const* exp_avg,
+                       float* const* exp_avg_sq, const int64_t* elems, const float* weight_decay, int32_t n, double lr,
+                       double beta1, double beta2, double eps, int32_t step, int32_t correct_bias, const float* sqnorm,
+                       double max_grad_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,7 +56,24 @@ def main():
         ms = timed(step(task), 5)
         out[f"pretrain_{task}_B{B}"] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3,
                                         "algorithmic_tflops": flop[task] * B / ms}
-    del model
+    # optimiser half of the step (lxmert_pretrain.py:343-364): fused clip + HF-AdamW over all trainable parameters
+    from xlxmert_b200.optim import B200AdamW, lxmert_param_groups
+    step("vis_mask")()                                   # leaves gradients behind
+    opt = B200AdamW(lxmert_param_groups(model, 0.01), lr=1e-4)
+    n_par = sum(p.numel() for p in model.parameters() if p.grad is not None)
+    ms = timed(lambda: opt.step(max_grad_norm=1.0), 10)
+    out["fused_clip_adamw"] = {"ms": ms, "params_with_grad": n_par, "algorithmic_bytes": 32 * n_par,
+                               "achieved_GBps": 32 * n_par / ms / 1e6,
+                               "note": "28 B/param AdamW (read g,p,m,v; write p,m,v) + 4 B/param for the norm pass"}
+    ref_params = [p for p in model.parameters() if p.grad is not None]
+    topt = torch.optim.AdamW(ref_params, lr=1e-4, eps=1e-6, weight_decay=0.01)
+
+    def torch_step():
+        torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+        topt.step()
+    ms = timed(torch_step, 10)
+    out["torch_clip_plus_AdamW_foreach"] = {"ms": ms}
+    del model, opt, topt
     torch.cuda.empty_cache()
 
     G = B200Generator()

@@ -102,6 +102,14 @@ def _sig(lib):
     lib.xlx_generator_prepare.argtypes = [P, P, P]
     lib.xlx_generator_fwd.restype = I32
     lib.xlx_generator_fwd.argtypes = [P, P, I32, P, P, P, P, P, P, SZ, I32, P]
+    F64 = C.c_double
+    lib.xlx_optim_scratch_floats.restype = I64
+    lib.xlx_optim_scratch_floats.argtypes = [P, I32]
+    lib.xlx_optim_launch_count.restype = I64
+    lib.xlx_grad_sqnorm.restype = I32
+    lib.xlx_grad_sqnorm.argtypes = [P, P, I32, P, P, P]
+    lib.xlx_adamw_step.restype = I32
+    lib.xlx_adamw_step.argtypes = [P, P, P, P, P, P, I32, F64, F64, F64, F64, I32, I32, P, F64, P]
     lib.xlx_matchhead_scratch_floats.restype = I64
     lib.xlx_matchhead_scratch_floats.argtypes = [I32]
     lib.xlx_matchhead_fwd.restype = I32

@@ -509,7 +509,7 @@ const char* xlx_strerror(int32_t code) {
   }
 }
 
-int64_t xlx_launch_count(void) { return gemm_launch_count() + aux_launch_count() + xlx_generator_launch_count(); }
+int64_t xlx_launch_count(void) { return gemm_launch_count() + aux_launch_count() + xlx_generator_launch_count() + xlx_optim_launch_count(); }
 int64_t xlx_gemm_launch_count(void) { return gemm_launch_count(); }
 void xlx_profile_gemm_begin(void) { gemm_timing_begin(); }
 int32_t xlx_profile_gemm_end(double* total_ms, double* total_flops, int64_t* launches) {
