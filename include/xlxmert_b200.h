@@ -188,6 +188,18 @@ int32_t xlx_lmhead_bwd(const xlx_dims* d, int32_t classes, const float* const* p
                        const int64_t* labels, const float* d_loss, float* d_hidden, float* const* grads,
                        void* workspace, size_t workspace_bytes, int32_t passes, void* stream);
 
+/* Row compaction around the two masked-prediction losses.  Replaces nothing in the reference: CrossEntropyLoss
+ * (lxrt/modeling.py:99,102 and :253-256) ignores rows labelled -100, yet the reference still runs the heads on them.
+ * rows[0..*count) = ascending m with labels[m] != ignore_index (rows holds M entries; count is a DEVICE int32 the
+ * caller reads back to size the head call).  gather: dst[i,:] = src[rows[i],:], labels_dst[i] = labels[rows[i]]
+ * (either pair src/dst or labels/labels_dst may be null).  scatter: dst [M, cols] = 0 then dst[rows[i],:] = src[i,:] — the gather's adjoint. */
+int32_t xlx_labelled_rows(const int64_t* labels, int32_t M, int64_t ignore_index, int64_t* rows, int32_t* count,
+                          void* stream);
+int32_t xlx_gather_rows(const float* src, const int64_t* labels, const int64_t* rows, int32_t n, int32_t cols,
+                        float* dst, int64_t* labels_dst, void* stream);
+int32_t xlx_scatter_rows(const float* src, const int64_t* rows, int32_t n, int32_t M, int32_t cols, float* dst,
+                         void* stream);
+
 /* Matched head: cls.seq_relationship = Linear(H, 2) on the pooled output (HF:661,664) + CrossEntropyLoss
  * (modeling.py:227-235).  scores [B,2]; scratch = xlx_matchhead_scratch_floats(B) floats, shared by fwd and bwd. */
 int64_t xlx_matchhead_scratch_floats(int32_t B);

@@ -21,12 +21,18 @@ def timed(fn, iters, warm=3):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
+    t0 = time.perf_counter()
     e0.record()
     for _ in range(iters):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    wall = (time.perf_counter() - t0) * 1e3 / iters
+    ev = e0.elapsed_time(e1) / iters
+    if abs(wall - ev) > 0.05 * ev:
+        print(f"[timed] wall {wall:.2f} ms vs events {ev:.2f} ms", file=sys.stderr)
+    return ev
 
 
 def main():
@@ -55,7 +61,8 @@ def main():
     for task in ("vis_mask", "word_mask", "matched"):
         ms = timed(step(task), 5)
         out[f"pretrain_{task}_B{B}"] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3,
-                                        "algorithmic_tflops": flop[task] * B / ms}
+                                        "algorithmic_tflops": flop[task] * B / ms,
+                                        "note": "FLOPs counted as the reference does them (heads on all rows)"}
     # optimiser half of the step (lxmert_pretrain.py:343-364): fused clip + HF-AdamW over all trainable parameters
     from xlxmert_b200.optim import B200AdamW, lxmert_param_groups
     step("vis_mask")()                                   # leaves gradients behind

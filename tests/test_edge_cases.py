@@ -113,3 +113,65 @@ def test_heads_large_ragged_rows():
     # all labels ignored → NaN loss like torch's CrossEntropyLoss (0/0), never a crash
     nan_loss = head.loss(h.cuda(), torch.full((3, 37), -100, dtype=torch.int64).cuda())
     assert torch.isnan(nan_loss)
+
+
+@pytest.mark.parametrize("M,frac", [(1, 1.0), (37, 0.0), (1000, 0.5), (16384, 0.15), (5000, 1.0)])
+def test_labelled_rows_compaction(M, frac):
+    """xlx_labelled_rows / gather / scatter against torch.nonzero: ascending order, exact count, adjoint pair."""
+    import ctypes as C
+    from xlxmert_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M)
+    labels = torch.randint(0, 100, (M,), generator=g)
+    labels[torch.rand(M, generator=g) >= frac] = -100
+    want = (labels != -100).nonzero().squeeze(1)
+    lab = labels.cuda()
+    rows = torch.full((M,), -1, dtype=torch.int64, device="cuda")
+    count = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.xlx_labelled_rows(lab.data_ptr(), M, -100, rows.data_ptr(), count.data_ptr(), st) == 0
+    n = int(count.item())
+    assert n == want.numel()
+    assert torch.equal(rows[:n].cpu(), want)
+    if n == 0:
+        return
+    x = torch.randn(M, 64, generator=g).cuda()
+    picked = torch.empty(n, 64, device="cuda")
+    plab = torch.empty(n, dtype=torch.int64, device="cuda")
+    assert lib.xlx_gather_rows(x.data_ptr(), lab.data_ptr(), rows.data_ptr(), n, 64, picked.data_ptr(),
+                               plab.data_ptr(), st) == 0
+    assert torch.equal(picked.cpu(), x.cpu()[want]) and torch.equal(plab.cpu(), labels[want])
+    back = torch.full((M, 64), 7.0, device="cuda")
+    assert lib.xlx_scatter_rows(picked.data_ptr(), rows.data_ptr(), n, M, 64, back.data_ptr(), st) == 0
+    ref = torch.zeros(M, 64)
+    ref[want] = x.cpu()[want]
+    assert torch.equal(back.cpu(), ref)
+
+
+def test_head_losses_identical_with_and_without_row_compaction():
+    """Dropping the −100 rows before the heads must not change the loss or any gradient beyond summation order."""
+    from xlxmert_b200.heads import B200LxmertVisualObjHead
+    d = TINY_DIMS
+    sdh = P.init_state_dict(P.objhead_param_specs(d), seed=9, randomize_ln_bias=True)
+    g = torch.Generator().manual_seed(3)
+    h = torch.randn(5, 36, d.hidden, generator=g)
+    labels = torch.randint(0, d.num_clusters, (5, 36), generator=g)
+    labels[torch.rand(5, 36, generator=g) < 0.5] = -100
+    res = []
+    for compact in (False, True):
+        head = B200LxmertVisualObjHead(d, d.num_clusters)
+        head.load_state_dict(sdh, strict=True)
+        head = head.cuda()
+        head.compact_rows = compact
+        hg = h.cuda().requires_grad_(True)
+        loss = head.loss(hg, labels.cuda())
+        loss.backward()
+        res.append((float(loss), hg.grad.cpu(), {k: p.grad.cpu() for k, p in head.named_parameters()
+                                                 if p.grad is not None}))
+    (l0, g0, p0), (l1, g1, p1) = res
+    assert abs(l0 - l1) < 1e-6 * abs(l0)
+    assert g1.shape == g0.shape and rel_err(g1, g0) < 1e-5
+    assert float(g1[labels == -100].abs().max()) == 0.0
+    assert p0.keys() == p1.keys()
+    for k in p0:
+        assert rel_err(p1[k], p0[k]) < 1e-5, k

@@ -110,6 +110,12 @@ def _sig(lib):
     lib.xlx_grad_sqnorm.argtypes = [P, P, I32, P, P, P]
     lib.xlx_adamw_step.restype = I32
     lib.xlx_adamw_step.argtypes = [P, P, P, P, P, P, I32, F64, F64, F64, F64, I32, I32, P, F64, P]
+    lib.xlx_labelled_rows.restype = I32
+    lib.xlx_labelled_rows.argtypes = [P, I32, I64, P, P, P]
+    lib.xlx_gather_rows.restype = I32
+    lib.xlx_gather_rows.argtypes = [P, P, P, I32, I32, P, P, P]
+    lib.xlx_scatter_rows.restype = I32
+    lib.xlx_scatter_rows.argtypes = [P, P, I32, I32, I32, P, P]
     lib.xlx_matchhead_scratch_floats.restype = I64
     lib.xlx_matchhead_scratch_floats.argtypes = [I32]
     lib.xlx_matchhead_fwd.restype = I32

@@ -415,4 +415,33 @@ int32_t xlx_matchhead_bwd(const xlx_dims* d, int32_t B, const float* pooled, con
   return small_linear_bwd(dscores, pooled, W, B, d->hidden, 2, dW, dbias, d_pooled, st);
 }
 
+// ---- row compaction around the masked-prediction losses --------------------------------------------------------
+// CrossEntropyLoss skips rows labelled −100 (lxrt/modeling.py:99,102,253-256); 50 % of the visual rows and 85 % of the
+// word rows are.  Compacting before the head keeps the loss and every gradient identical and skips their GEMM work.
+int32_t xlx_labelled_rows(const int64_t* labels, int32_t M, int64_t ignore_index, int64_t* rows, int32_t* count,
+                          void* stream) {
+  if (M < 1) return -21;
+  if (!labels || !rows || !count) return -24;
+  XLX_TRY(ensure_device(rows));
+  return labelled_rows(labels, M, ignore_index, rows, count, static_cast<cudaStream_t>(stream));
+}
+int32_t xlx_gather_rows(const float* src, const int64_t* labels, const int64_t* rows, int32_t n, int32_t cols,
+                        float* dst, int64_t* labels_dst, void* stream) {
+  if (n < 0 || (src && (cols < 4 || cols % 4))) return -21;
+  if (!rows || (!src != !dst) || (!labels != !labels_dst) || (!src && !labels)) return -24;
+  if (n == 0) return 0;
+  XLX_TRY(ensure_device(rows));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (src) XLX_TRY(gather_rows(src, rows, nullptr, nullptr, n, cols, dst, Split{}, st));
+  if (labels) XLX_TRY(gather_i64(labels, rows, n, labels_dst, st));
+  return 0;
+}
+int32_t xlx_scatter_rows(const float* src, const int64_t* rows, int32_t n, int32_t M, int32_t cols, float* dst,
+                         void* stream) {
+  if (n < 0 || M < 1 || n > M || cols < 4 || cols % 4) return -21;
+  if (!src || !rows || !dst) return -24;
+  XLX_TRY(ensure_device(dst));
+  return scatter_rows(src, rows, n, M, cols, dst, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -572,6 +572,54 @@ __global__ void box_pack_kernel(const float* t, int H, float* dWp) {
   if (i < 4 * H) dWp[i] = t[(i & 3) * H + (i >> 2)];
 }
 
+
+// Ordered stream compaction of the rows whose label is not `ignore`: one CTA, each thread owns a run of
+// consecutive rows, an inclusive scan over the per-thread counts places them.  M ≤ a few 10^4 (B·V or B·L).
+__global__ void __launch_bounds__(1024) labelled_rows_kernel(const int64_t* __restrict__ labels, int M,
+                                                             int64_t ignore, int64_t* __restrict__ rows,
+                                                             int32_t* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  const int t = threadIdx.x, per = (M + 1023) / 1024;
+  const int r0 = min(t * per, M), r1 = min(r0 + per, M);
+  int n = 0;
+  for (int r = r0; r < r1; ++r) n += labels[r] != ignore;
+  int incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((t & 31) >= o) incl += v;
+  }
+  if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    int w = warp_tot[t], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (t >= o) wi += v;
+    }
+    warp_tot[t] = wi - w;   // exclusive prefix of the warp totals
+    if (t == 31) *count = wi;
+  }
+  __syncthreads();
+  int at = warp_tot[t >> 5] + incl - n;
+  for (int r = r0; r < r1; ++r)
+    if (labels[r] != ignore) rows[at++] = r;
+}
+
+// dst[rows[i], :] = src[i, :]; dst was zero-filled by the caller.
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restrict__ src,
+                                                           const int64_t* __restrict__ rows, int cols,
+                                                           float* __restrict__ dst) {
+  const float4* in = reinterpret_cast<const float4*>(src + static_cast<size_t>(blockIdx.x) * cols);
+  float4* out = reinterpret_cast<float4*>(dst + static_cast<size_t>(rows[blockIdx.x]) * cols);
+  for (int c = threadIdx.x; c < cols / 4; c += blockDim.x) out[c] = in[c];
+}
+__global__ void gather_i64_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ rows, int n,
+                                  int64_t* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[rows[i]];
+}
 }  // namespace
 
 long long aux_launch_count() { return g_aux_launches.load(); }
@@ -603,6 +651,25 @@ int gather_rows(const float* table, const int64_t* ids, const uint8_t* mask, con
   if (cols % 4) return -2;
   if (!rows) return 0;
   gather_rows_kernel<<<rows, 256, 0, s>>>(table, ids, mask, fill, cols, out_f32, out.hi, out.lo);
+  return launch_rc();
+}
+
+int labelled_rows(const int64_t* labels, int M, int64_t ignore, int64_t* rows, int32_t* count, cudaStream_t s) {
+  if (M < 1) return -2;
+  labelled_rows_kernel<<<1, 1024, 0, s>>>(labels, M, ignore, rows, count);
+  return launch_rc();
+}
+int scatter_rows(const float* src, const int64_t* rows, int n, int M, int cols, float* dst, cudaStream_t s) {
+  if (cols % 4) return -2;
+  cudaError_t e = cudaMemsetAsync(dst, 0, static_cast<size_t>(M) * cols * sizeof(float), s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (!n) return 0;
+  scatter_rows_kernel<<<n, 256, 0, s>>>(src, rows, cols, dst);
+  return launch_rc();
+}
+int gather_i64(const int64_t* src, const int64_t* rows, int n, int64_t* dst, cudaStream_t s) {
+  if (!n) return 0;
+  gather_i64_kernel<<<(n + 255) / 256, 256, 0, s>>>(src, rows, n, dst);
   return launch_rc();
 }
 

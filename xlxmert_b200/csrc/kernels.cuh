@@ -124,6 +124,12 @@ int attention_fwd(AttnOperand q, AttnOperand k, AttnOperand v, const float* mask
 // h·64 + d, as split matrices with leading dimension ld_d.
 int attention_bwd(AttnOperand dctx, AttnOperand q, AttnOperand k, AttnOperand v, const float* probs, int B, int heads,
                   int Sq, int Sk, Split dq, Split dk, Split dv, int ld_d, cudaStream_t s);
+// Row compaction for the masked-prediction losses (CrossEntropyLoss ignores label −100, lxrt/modeling.py:99,253-256):
+// rows[0..count) = ascending indices m with labels[m] != ignore.  rows has room for M entries.
+int labelled_rows(const int64_t* labels, int M, int64_t ignore, int64_t* rows, int32_t* count, cudaStream_t s);
+// dst [M, cols] = 0, then dst[rows[i], :] = src[i, :] for i < n.
+int scatter_rows(const float* src, const int64_t* rows, int n, int M, int cols, float* dst, cudaStream_t s);
+int gather_i64(const int64_t* src, const int64_t* rows, int n, int64_t* dst, cudaStream_t s);
 void count_aux_launch();
 
 }  // namespace xlx

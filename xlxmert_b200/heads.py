@@ -139,6 +139,55 @@ class _HeadLossFn(torch.autograd.Function):
                                          for g, p in zip(grads, ctx.params)])
 
 
+class _LabelledRowsFn(torch.autograd.Function):
+    """hidden [M, H] → the rows whose label is not −100 (ascending); backward scatters into zeros."""
+
+    @staticmethod
+    def forward(ctx, hidden, rows, n):
+        M, H = hidden.shape
+        out = torch.empty(n, H, device=hidden.device, dtype=torch.float32)
+        rc = _lib.load().xlx_gather_rows(hidden.data_ptr(), None, rows.data_ptr(), n, H, out.data_ptr(), None, _stream())
+        _lib.check("xlx_gather_rows", rc)
+        ctx.rows, ctx.n, ctx.M = rows, n, M
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        d_out = d_out.contiguous()
+        d_hidden = torch.empty(ctx.M, d_out.shape[1], device=d_out.device, dtype=torch.float32)
+        rc = _lib.load().xlx_scatter_rows(d_out.data_ptr(), ctx.rows.data_ptr(), ctx.n, ctx.M, d_out.shape[1],
+                                          d_hidden.data_ptr(), _stream())
+        _lib.check("xlx_scatter_rows", rc)
+        return d_hidden, None, None
+
+
+def labelled_rows(hidden, labels):
+    """Drop the rows CrossEntropyLoss ignores (label −100, modeling.py:99,253-256) before a masked-prediction head:
+    same loss, same gradients, none of the head's GEMM work for rows that cannot contribute.  Costs one 4-byte
+    device→host read (the row count sizes the head's GEMMs).  Returns ``(hidden, labels)`` unchanged when every row
+    is labelled or none is (the all-ignored loss is NaN like the reference's)."""
+    if not hidden.is_cuda:
+        raise RuntimeError("the prediction heads run on CUDA (sm_100a) only; there is no CPU fallback")
+    H = hidden.shape[-1]
+    flat = labels.reshape(-1).contiguous()
+    M = flat.numel()
+    rows = torch.empty(M, dtype=torch.int64, device=hidden.device)
+    count = torch.empty(1, dtype=torch.int32, device=hidden.device)
+    lib = _lib.load()
+    _lib.check("xlx_labelled_rows", lib.xlx_labelled_rows(flat.data_ptr(), M, -100, rows.data_ptr(), count.data_ptr(),
+                                                          _stream()))
+    n = int(count.item())
+    if n == 0 or n == M:
+        return hidden, labels
+    h2 = hidden.reshape(M, H)
+    if h2.dtype != torch.float32 or not h2.is_contiguous():
+        h2 = h2.contiguous().float()
+    picked = torch.empty(n, dtype=torch.int64, device=hidden.device)
+    _lib.check("xlx_gather_rows", lib.xlx_gather_rows(None, flat.data_ptr(), rows.data_ptr(), n, 0, None,
+                                                      picked.data_ptr(), _stream()))
+    return _LabelledRowsFn.apply(h2, rows, n), picked
+
+
 class B200LxmertVisualObjHead(nn.Module):
     def __init__(self, dims: LxmertDims, num_clusters: Optional[int] = None, passes: int = 3,
                  source: Optional[nn.Module] = None):
@@ -152,6 +201,7 @@ class B200LxmertVisualObjHead(nn.Module):
             self.linear_feat = nn.Linear(dims.hidden, dims.feat_dim)
             self.out_cluster = nn.Linear(dims.feat_dim, C_)
         self.cluster_out = True
+        self.compact_rows = True      # run the head on labelled rows only (see labelled_rows)
         self.visual_losses = {"obj": {"shape": (-1,), "num": C_}}     # --visualLosses obj (pretrain.bash)
         self._fused = _FusedHead("objhead", dims, C_, passes)
 
@@ -177,6 +227,8 @@ class B200LxmertVisualObjHead(nn.Module):
 
     def loss(self, hidden_states, obj_labels):
         """``CrossEntropyLoss()(obj_logit.view(B·V, C), obj_label.flatten())`` (modeling.py:253-256), differentiable."""
+        if self.compact_rows:
+            hidden_states, obj_labels = labelled_rows(hidden_states, obj_labels)
         return _HeadLossFn.apply(self._fused, obj_labels, hidden_states, *self._params())
 
     @torch.no_grad()
@@ -237,6 +289,7 @@ class B200LxmertPreTrainingHeads(nn.Module):
             self.predictions = _LMPredictionHead(dims, embedding_weights)
             self.seq_relationship = nn.Linear(dims.hidden, 2)
         self._cdims = _lib.XlxDims.from_dims(dims)
+        self.compact_rows = True
         self._fused = _FusedHead("lmhead", dims, self.predictions.decoder.weight.shape[0], passes)
 
     def _params(self):
@@ -261,6 +314,8 @@ class B200LxmertPreTrainingHeads(nn.Module):
 
     def lm_loss(self, sequence_output, word_labels):
         """``CrossEntropyLoss()(scores.view(-1, vocab), word_labels.view(-1))`` (modeling.py:219-226)."""
+        if self.compact_rows:
+            sequence_output, word_labels = labelled_rows(sequence_output, word_labels)
         return _HeadLossFn.apply(self._fused, word_labels, sequence_output, *self._params())
 
     def matched_loss(self, pooled_output, matched_labels):
