@@ -232,6 +232,20 @@ int32_t xlx_generator_fwd(const float* const* params, const void* prep, int32_t 
                           const float* const* noise, float* img, float* pre_tanh, float* const* block_out,
                           void* workspace, size_t workspace_bytes, int32_t passes, void* stream);
 
+/* ---- nearest-centroid assignment -----------------------------------------------------------
+ * x-lxmert/feature_extraction/run_kmeans.py:124-143: index = faiss.IndexFlatL2(d); index.add(centroids);
+ * D, I = index.search(x, 1)  — the cluster id of every grid cell.  faiss 1.6 (not vendored) computes
+ * ‖x‖² + ‖c‖² − 2·x·c with an SGEMM and keeps the minimum; the same arithmetic here, as one tcgen05 GEMM against the
+ * prepared table split-bf16(2·C) with −‖c‖² as bias, followed by a row arg-max (ties → lowest index).
+ *   prepare: centroids [n_centroids, dim] fp32 → prep (xlx_kmeans_prep_bytes bytes); redo when the table changes.
+ *   assign:  x [N, dim] fp32 → ids [N] int64 and (optional) dist [N] fp32 = squared L2 distance to that centroid,
+ *            clamped at 0 like faiss.  workspace: xlx_kmeans_workspace_bytes(dim, n_centroids, N). dim % 8 == 0. */
+size_t xlx_kmeans_prep_bytes(int32_t dim, int32_t n_centroids);
+int32_t xlx_kmeans_prepare(int32_t dim, int32_t n_centroids, const float* centroids, void* prep, void* stream);
+size_t xlx_kmeans_workspace_bytes(int32_t dim, int32_t n_centroids, int32_t N);
+int32_t xlx_kmeans_assign(int32_t dim, int32_t n_centroids, const void* prep, int32_t N, const float* x, int64_t* ids,
+                          float* dist, void* workspace, size_t workspace_bytes, int32_t passes, void* stream);
+
 /* ---- optimiser step of the pre-training loop ---------------------------------------------
  * x-lxmert/src/pretrain/lxmert_pretrain.py:343-364: torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0) then
  * transformers.optimization.AdamW.step() (4.1.1: betas (0.9, 0.999), eps 1e-6, correct_bias, weight decay applied

@@ -107,6 +107,35 @@ def main():
     out[f"sample_NAR4_plus_decode_B{Bs}_cuda_graph"] = {"ms": ms, "images_per_s": Bs / ms * 1e3}
     ms = timed(lambda: m.sample_image_NAR(tok, n_steps=4, cache_language=False), 3, warm=2)
     out[f"sample_NAR4_plus_decode_B{Bs}_no_language_cache"] = {"ms": ms, "images_per_s": Bs / ms * 1e3}
+    del m, pre, G
+    torch.cuda.empty_cache()
+
+    # nearest-centroid assignment (run_kmeans.py:124-143): 10 000 centroids × 2048, device-resident and host-streamed
+    import time
+    import numpy as np
+    from oracle import kmeans_oracle as KO
+    from xlxmert_b200.kmeans import B200IndexFlatL2
+    cent = table.float()
+    index = B200IndexFlatL2(2048)
+    index.add(cent)
+    Nk = 32768
+    xg = (cent[torch.randint(0, cent.shape[0], (Nk,))] + 0.3 * torch.randn(Nk, 2048)).cuda()
+    ms = timed(lambda: index.search(xg, 1), 5)
+    out["kmeans_assign_device_N32768"] = {"ms": ms, "rows_per_s": Nk / ms * 1e3,
+                                          "algorithmic_tflops": 2 * Nk * 2048 * cent.shape[0] / ms / 1e9}
+    xh = xg.cpu().numpy()
+    xh = np.concatenate([xh] * 4)                      # 131 072 rows = 1 GiB of fp32 features from host memory
+    index.search(xh[:Nk], 1)
+    t0 = time.perf_counter()
+    index.search(xh, 1)
+    dt = time.perf_counter() - t0
+    out["kmeans_assign_host_streamed_N131072"] = {"ms": dt * 1e3, "rows_per_s": len(xh) / dt,
+                                                  "h2d_GBps": xh.nbytes / dt / 1e9}
+    t0 = time.perf_counter()
+    KO.search_l2_fp32(xh[:4096], cent.numpy())
+    dt = time.perf_counter() - t0
+    out["kmeans_assign_cpu_oracle_N4096"] = {"ms": dt * 1e3, "rows_per_s": 4096 / dt,
+                                             "note": "numpy fp32 restatement of faiss IndexFlatL2 on the host cores"}
     print(json.dumps(out))
 
 

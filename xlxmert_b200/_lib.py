@@ -110,6 +110,14 @@ def _sig(lib):
     lib.xlx_grad_sqnorm.argtypes = [P, P, I32, P, P, P]
     lib.xlx_adamw_step.restype = I32
     lib.xlx_adamw_step.argtypes = [P, P, P, P, P, P, I32, F64, F64, F64, F64, I32, I32, P, F64, P]
+    lib.xlx_kmeans_prep_bytes.restype = SZ
+    lib.xlx_kmeans_prep_bytes.argtypes = [I32, I32]
+    lib.xlx_kmeans_prepare.restype = I32
+    lib.xlx_kmeans_prepare.argtypes = [I32, I32, P, P, P]
+    lib.xlx_kmeans_workspace_bytes.restype = SZ
+    lib.xlx_kmeans_workspace_bytes.argtypes = [I32, I32, I32]
+    lib.xlx_kmeans_assign.restype = I32
+    lib.xlx_kmeans_assign.argtypes = [I32, I32, P, I32, P, P, P, P, SZ, I32, P]
     lib.xlx_labelled_rows.restype = I32
     lib.xlx_labelled_rows.argtypes = [P, I32, I64, P, P, P]
     lib.xlx_gather_rows.restype = I32

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libxlxmert_b200.so")
-SOURCES = ["gemm_sm100.cu", "kernels.cu", "attention.cu", "encoder.cu", "heads.cu", "generator.cu", "optim.cu"]
+SOURCES = ["gemm_sm100.cu", "kernels.cu", "attention.cu", "encoder.cu", "heads.cu", "generator.cu", "optim.cu", "kmeans.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
