@@ -11,6 +11,7 @@ over one batch (plus, for N > 1, one NCCL all-reduce of the flat gradient arena)
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -282,11 +283,16 @@ def run_ours(args):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = lib.xlx_launch_count()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
+        gc.collect()
+        gc.disable()          # a generation-2 collection inside a step that syncs with the host shows up as a 100 ms stall
+        try:
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+        finally:
+            gc.enable()
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)

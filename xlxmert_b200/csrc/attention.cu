@@ -115,6 +115,8 @@ attn_fwd_mma_kernel(const __grid_constant__ FwdMaps maps, int qcol, int kcol, in
   bf16* Vh = Kl + TT;
   bf16* Vl = Vh + TT;
   const int h = blockIdx.x, b = blockIdx.y;
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const size_t qrow0 = static_cast<size_t>(b) * Sq;
   {
@@ -267,6 +269,8 @@ attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, in
   bf16* Sh = Kh;
   bf16* Sl = Kl;
   const int h = blockIdx.x, b = blockIdx.y;
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const size_t qrow0 = static_cast<size_t>(b) * Sq, krow0 = static_cast<size_t>(b) * Sk;
   {
@@ -469,7 +473,7 @@ int attention_fwd(AttnOperand q, AttnOperand k, AttnOperand v, const float* mask
   if ((rc = operand_maps(&maps.m[0], &maps.m[1], q))) return rc;
   if ((rc = operand_maps(&maps.m[2], &maps.m[3], k))) return rc;
   if ((rc = operand_maps(&maps.m[4], &maps.m[5], v))) return rc;
-  attn_fwd_mma_kernel<<<dim3(heads, B), AT, smem, s>>>(maps, q.col, k.col, v.col, mask, heads, Sq, Sk, ctx.hi, ctx.lo,
+  launch_pdl(attn_fwd_mma_kernel, dim3(heads, B), dim3(AT), smem, s, maps, q.col, k.col, v.col, mask, heads, Sq, Sk, ctx.hi, ctx.lo,
                                                        ctx_f32, ld_ctx, probs);
   count_aux_launch();
   cudaError_t e = cudaGetLastError();
@@ -495,7 +499,7 @@ int attention_bwd(AttnOperand dctx, AttnOperand q, AttnOperand k, AttnOperand v,
   if ((rc = operand_maps(&maps.m[2], &maps.m[3], k))) return rc;
   if ((rc = operand_maps(&maps.m[4], &maps.m[5], v))) return rc;
   if ((rc = operand_maps(&maps.m[6], &maps.m[7], dctx))) return rc;
-  attn_bwd_mma_kernel<<<dim3(heads, B), AT, smem, s>>>(maps, q.col, k.col, v.col, dctx.col, probs, heads, Sq, Sk, dq.hi,
+  launch_pdl(attn_bwd_mma_kernel, dim3(heads, B), dim3(AT), smem, s, maps, q.col, k.col, v.col, dctx.col, probs, heads, Sq, Sk, dq.hi,
                                                        dq.lo, dk.hi, dk.lo, dv.hi, dv.lo, ld_d);
   count_aux_launch();
   cudaError_t e = cudaGetLastError();

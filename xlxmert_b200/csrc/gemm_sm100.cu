@@ -9,6 +9,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "pdl.cuh"
 #include "xlx_ptx.cuh"
 
 namespace xlx {
@@ -232,6 +233,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
   if (P.cluster == 2) cluster_sync_all();     // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // Everything above (barriers, TMEM, descriptor prefetch) may overlap the previous kernel's tail (see launch_pdl).
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (one thread) =====================
@@ -475,6 +479,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
 // out[m, n] (+)= Σ_s part[s][m][n]  — second phase of a split-K GEMM (plain fp32 output only)
 __global__ void splitk_reduce_kernel(const float4* __restrict__ part, int splits, size_t mn4, int n4, float* out,
                                      int ld_out, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < mn4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float4 a = __ldg(part + i);
@@ -645,14 +651,16 @@ int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUtensorMap
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   static const int force_cl = env_int("XLX_GEMM_FORCE_CLUSTER_LAUNCH", 0);    // experiment: cluster launch, independent CTAs
   attr[0].val.clusterDim.x = (force_cl && grid % 2 == 0) ? 2 : P.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BK, A_MN, B_MN, NPARTS, ACT>, mAhi, mAlo, mBhi, mBlo, mOut, P);
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }
@@ -812,9 +820,9 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     const size_t mn4 = static_cast<size_t>(p.M) * p.N / 4;
     size_t blocks = (mn4 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-        reinterpret_cast<const float4*>(P.part), P.splits, mn4, p.N / 4, p.epi.out_f32, p.epi.ld_out,
-        (p.epi.flags & EPI_ACCUM) ? 1 : 0);
+    launch_pdl(splitk_reduce_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream,
+               reinterpret_cast<const float4*>(P.part), P.splits, mn4, p.N / 4, p.epi.out_f32, p.epi.ld_out,
+               (p.epi.flags & EPI_ACCUM) ? 1 : 0);
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   if (g_timing) {

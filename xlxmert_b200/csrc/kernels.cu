@@ -61,6 +61,8 @@ __global__ void fill_kernel(float* dst, float v, size_t n) {
     dst[i] = v;
 }
 __global__ void concat3_kernel(const float* a, const float* b, const float* c, float* dst, int n) {
+  pdl_trigger();
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 3 * n) dst[i] = i < n ? a[i] : (i < 2 * n ? b[i - n] : c[i - 2 * n]);
 }
@@ -372,6 +374,8 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
               int M, float out_scale, const float* __restrict__ addend, bf16* hi, bf16* lo, float* out_f32,
               float* mean, float* rstd) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int H = NV * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -422,6 +426,8 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ dy, float dy_scale, const float* __restrict__ y,
               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, int M,
               float* dx, bf16* dx_hi, bf16* dx_lo, float* part) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int H = NV * 128;
   __shared__ float4 red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -488,6 +494,8 @@ ln_bwd_kernel(const float* __restrict__ dy, float dy_scale, const float* __restr
 __global__ void __launch_bounds__(256)
 colsum_finish_kernel(const float* __restrict__ part, int nblk, int H, float* o0, float* o1, float* o2, float* o3,
                      float* o4, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int h = blockIdx.x * 32 + tx;
@@ -515,6 +523,8 @@ colsum_finish_kernel(const float* __restrict__ part, int nblk, int H, float* o0,
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ xf, const bf16* __restrict__ xh, const bf16* __restrict__ xl, int M, int N,
               int ld, float* scratch, const uint8_t* __restrict__ rowmask) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 red[8][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + tx) * 4;
@@ -643,7 +653,7 @@ int fill_f32(float* dst, float v, size_t n, cudaStream_t s) {
   return launch_rc();
 }
 int concat3_f32(const float* a, const float* b, const float* c, float* dst, int n, cudaStream_t s) {
-  concat3_kernel<<<(3 * n + 255) / 256, 256, 0, s>>>(a, b, c, dst, n);
+  launch_pdl(concat3_kernel, dim3((3 * n + 255) / 256), dim3(256), 0, s, a, b, c, dst, n);
   return launch_rc();
 }
 int gather_rows(const float* table, const int64_t* ids, const uint8_t* mask, const float* fill, int rows, int cols,
@@ -783,22 +793,22 @@ int small_linear_bwd(const float* dy, const float* x, const float* W, int M, int
   return launch_rc();
 }
 
-#define XLX_LN_DISPATCH(KERNEL, H, ...)                        \
-  switch (H) {                                                 \
-    case 128: KERNEL<1> __VA_ARGS__; break;                    \
-    case 256: KERNEL<2> __VA_ARGS__; break;                    \
-    case 512: KERNEL<4> __VA_ARGS__; break;                    \
-    case 768: KERNEL<6> __VA_ARGS__; break;                    \
-    case 1024: KERNEL<8> __VA_ARGS__; break;                   \
-    default: return -4;                                        \
+#define XLX_LN_DISPATCH(KERNEL, H, GRID, ...)                                          \
+  switch (H) {                                                                         \
+    case 128: launch_pdl(KERNEL<1>, dim3(GRID), dim3(256), 0, s, __VA_ARGS__); break;  \
+    case 256: launch_pdl(KERNEL<2>, dim3(GRID), dim3(256), 0, s, __VA_ARGS__); break;  \
+    case 512: launch_pdl(KERNEL<4>, dim3(GRID), dim3(256), 0, s, __VA_ARGS__); break;  \
+    case 768: launch_pdl(KERNEL<6>, dim3(GRID), dim3(256), 0, s, __VA_ARGS__); break;  \
+    case 1024: launch_pdl(KERNEL<8>, dim3(GRID), dim3(256), 0, s, __VA_ARGS__); break; \
+    default: return -4;                                                                \
   }
 
 int layernorm_fwd(const float* y, const float* gamma, const float* beta, float eps, int M, int H, float out_scale,
                   const float* addend, Split out, float* out_f32, float* mean, float* rstd, cudaStream_t s) {
   if (!M) return 0;
   const int grid = (M + 7) / 8;
-  XLX_LN_DISPATCH(ln_fwd_kernel, H, <<<grid, 256, 0, s>>>(y, gamma, beta, eps, M, out_scale, addend, out.hi, out.lo,
-                                                         out_f32, mean, rstd));
+  XLX_LN_DISPATCH(ln_fwd_kernel, H, grid, y, gamma, beta, eps, M, out_scale, addend, out.hi, out.lo, out_f32, mean,
+                  rstd);
   return launch_rc();
 }
 int layernorm_bwd(const float* dy, float dy_scale, const float* y, const float* gamma, const float* mean,
@@ -808,16 +818,15 @@ int layernorm_bwd(const float* dy, float dy_scale, const float* y, const float* 
   if (grid > kMaxBlocks) grid = kMaxBlocks;
   if (grid < 1) grid = 1;
   *nblk_out = grid;
-  XLX_LN_DISPATCH(ln_bwd_kernel, H, <<<grid, 256, 0, s>>>(dy, dy_scale, y, gamma, mean, rstd, M, dx, dx_split.hi,
-                                                         dx_split.lo, part));
+  XLX_LN_DISPATCH(ln_bwd_kernel, H, grid, dy, dy_scale, y, gamma, mean, rstd, M, dx, dx_split.hi, dx_split.lo, part);
   return launch_rc();
 }
 int colsum_finish(const float* part, int nvec, int nblk, int H, float* const* outs, int accumulate, cudaStream_t s) {
   if (nvec < 1 || nvec > 5) return -1;
   float* o[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int v = 0; v < nvec; ++v) o[v] = outs[v];
-  colsum_finish_kernel<<<dim3((H + 31) / 32, nvec), 256, 0, s>>>(part, nblk, H, o[0], o[1], o[2], o[3], o[4],
-                                                                   accumulate);
+  launch_pdl(colsum_finish_kernel, dim3((H + 31) / 32, nvec), dim3(256), 0, s, part, nblk, H, o[0], o[1], o[2], o[3],
+             o[4], accumulate);
   return launch_rc();
 }
 int colsum(const float* x_f32, Split x, int M, int N, int ld, float* scratch, float* out, cudaStream_t s,
@@ -826,7 +835,8 @@ int colsum(const float* x_f32, Split x, int M, int N, int ld, float* scratch, fl
   int nblk = (M + 63) / 64;
   if (nblk > 128) nblk = 128;
   if (nblk < 1) nblk = 1;
-  colsum_kernel<<<dim3((N + 127) / 128, nblk), 256, 0, s>>>(x_f32, x.hi, x.lo, M, N, ld, scratch, rowmask);
+  launch_pdl(colsum_kernel, dim3((N + 127) / 128, nblk), dim3(256), 0, s, x_f32, x.hi, x.lo, M, N, ld, scratch,
+             rowmask);
   int rc = launch_rc();
   if (rc) return rc;
   float* outs[1] = {out};

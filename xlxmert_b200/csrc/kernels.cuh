@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pdl.cuh"
+
 namespace xlx {
 
 typedef __nv_bfloat16 bf16;
@@ -131,5 +133,6 @@ int labelled_rows(const int64_t* labels, int M, int64_t ignore, int64_t* rows, i
 int scatter_rows(const float* src, const int64_t* rows, int n, int M, int cols, float* dst, cudaStream_t s);
 int gather_i64(const int64_t* src, const int64_t* rows, int n, int64_t* dst, cudaStream_t s);
 void count_aux_launch();
+
 
 }  // namespace xlx
