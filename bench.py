@@ -258,6 +258,8 @@ def run_ours(args):
     h2d = ids_h.numel() * 8 + mask_h.numel() * 1 + cids_h.numel() * 8
     d2h = 4
 
+    e2e_marks = []
+
     def step_e2e():
         enc.invalidate_prepared()
         ids = ids_h.to(dev, non_blocking=True)
@@ -272,6 +274,7 @@ def run_ours(args):
         torch.cuda.current_stream().synchronize()                 # the step's result is read on the host
         for p in model.parameters():
             p.grad = None
+        e2e_marks.append(time.perf_counter())
         return float(loss_h)
 
     def timed(fn, steps, warmup):
@@ -315,6 +318,7 @@ def run_ours(args):
     ms_step, launches = timed(step_resident, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, max(3, args.steps), 5)
+    e2e_steps = [round((b - a) * 1e3, 2) for a, b in zip(e2e_marks[4:], e2e_marks[5:])]   # host clock, timed steps only
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM), events around every launch, outside the timed region
     lib.xlx_profile_gemm_begin()
@@ -347,7 +351,7 @@ def run_ours(args):
                 "config": workload_config(world, extra={"passes": passes, "batch_per_gpu": B,
                                                         "step_tflop_algorithmic": ENC_GFLOP_FWD_BWD * B / 1e3}),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e,
+                        "ms_per_step": ms_e2e, "host_ms_each_step": e2e_steps,
                         "api": "B200LxmertModel.forward(input_ids, visual_feats=vis_emb(cluster_ids), visual_pos, "
                                "attention_mask) + loss.backward(), pinned host ids in, loss scalar out"},
                 "gpu_launches": int(launches),

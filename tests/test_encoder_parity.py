@@ -131,9 +131,11 @@ def test_encoder_rejects_unsupported_shapes_loudly():
         enc(emb, None, feats, batch["visual_pos"])          # CPU tensors: no fallback
 
 
-def test_staged_backward_equals_one_shot():
-    """Issuing the backward as four stage calls (the data-parallel overlap path) is bit-identical to one call."""
-    import ctypes as C
+@pytest.mark.parametrize("stage_calls", [(1, 14), (1, 2, 4, 8), (1, 4, 2, 8), (3, 12)])
+def test_staged_backward_equals_one_shot(stage_calls):
+    """Issuing the backward as several stage calls (the data-parallel overlap path; the default split is
+    cross-modality layers, then everything below) is bit-identical to one call — whichever way the stages are
+    grouped, i.e. with and without the language stack running beside the vision stack on the second stream."""
     from xlxmert_b200 import _lib
     import xlxmert_b200.encoder as E
     sd, batch, feats, emb, mask = _case(TINY_DIMS, 4, 9, 12, 3, 4)
@@ -151,29 +153,42 @@ def test_staged_backward_equals_one_shot():
     a = run()
     # staged: call the C entry point stage by stage through the module's own hook
     enc2 = enc
-    lib = _lib.load()
     for p in enc2.parameters():
         p.grad = None
     e = emb.cuda().requires_grad_(True)
     f = feats.cuda().requires_grad_(True)
     (v, _), (l, _), _ = enc2(e, mask.cuda(), f, batch["visual_pos"].cuda())
-    old_active = E._dist_active
+    old_active, old_stages = E._dist_active, E._BWD_STAGES
     E._dist_active = (lambda g: True)
+    E._BWD_STAGES = stage_calls
     enc2.grad_sync_group = True
     import torch.distributed as dist
 
     class _W:
         def wait(self):
             return None
+    reduced = []
     old = (dist.all_reduce, dist.get_world_size, dist.get_backend)
-    dist.all_reduce = lambda t, op=None, group=None, async_op=False: _W()
+
+    def fake_all_reduce(t, op=None, group=None, async_op=False):
+        reduced.append((t.data_ptr(), t.numel()))
+        return _W()
+    dist.all_reduce = fake_all_reduce
     dist.get_world_size = lambda g=None: 1
     dist.get_backend = lambda g=None: "gloo"
     try:
         (l[-1].sum() + (v[-1] ** 2).sum()).backward()
     finally:
         dist.all_reduce, dist.get_world_size, dist.get_backend = old
-        E._dist_active = old_active
+        E._dist_active, E._BWD_STAGES = old_active, old_stages
         enc2.grad_sync_group = None
     assert enc2.arena_reduced
     assert torch.equal(a[0], e.grad) and torch.equal(a[1], f.grad) and torch.equal(a[2], enc2.last_grad_arena)
+    # the reduced slices tile the arena exactly once
+    arena = enc2.last_grad_arena
+    spans = sorted(((ptr - arena.data_ptr()) // 4, n) for ptr, n in reduced)
+    pos = 0
+    for off, n in spans:
+        assert off == pos
+        pos += n
+    assert pos == arena.numel()

@@ -116,6 +116,12 @@ struct FfnSave {
   Split in, out;
   int M = 0;
 };
+struct BwdScratch {
+  float* dy = nullptr;       // LayerNorm-input gradient [M, H]
+  Split dy_s, dqkv, du, dctx;
+  float* part = nullptr;     // partial column sums (bias / LayerNorm-affine gradients)
+  float* splitk = nullptr;   // split-K partial sums of the weight-gradient GEMMs
+};
 struct Plan {
   int B, L, V, H, I, F, heads, Ml, Mv, Mt;
   bool training;
@@ -123,12 +129,10 @@ struct Plan {
   float *y1 = nullptr, *y2 = nullptr, *tbox = nullptr, *vstats = nullptr;
   std::vector<AttSave> att;
   std::vector<FfnSave> ffn;
-  float* part = nullptr;
   size_t part_elems = 0;
-  float* splitk = nullptr;   // split-K partial sums of the weight-gradient GEMMs
-  // backward scratch
-  float *dA = nullptr, *dB = nullptr, *dy = nullptr, *dy2 = nullptr;
-  Split dy_s, dqkv, du, dctx;
+  // backward scratch: set 0 (all B·(L+V) rows) serves the caller's stream, set 1 (language rows only) the side stream
+  float *dA = nullptr, *dB = nullptr, *dy2 = nullptr;
+  BwdScratch sc[2];
   size_t bytes = 0;
 };
 
@@ -152,7 +156,7 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
   const size_t row_groups = 4 * ((Mmax + 127) / 128);          // GEMM-epilogue column-sum partials: one row per 32 rows
   if (row_groups * widest > pe) pe = row_groups * widest;
   p.part_elems = pe;
-  p.part = b.f32(pe);
+  p.sc[0].part = b.f32(pe);
 
   p.feats = b.split(Mv * F);
   p.y1 = b.f32(Mv * H);
@@ -163,24 +167,28 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
   p.vis0 = b.split(Mv * H);
   Split xin0 = b.split(Mt * H);  // input of the first cross-modality layer: [lang rows | vis rows]
 
-  // inference: every block shares one set of temporaries and layer outputs rotate through a small ring
+  // inference: the blocks of one modality share one set of temporaries and layer outputs rotate through a small ring.
+  // Language blocks use rows [0, Ml) and vision blocks rows [Ml, Mt) of every shared buffer, with their own ring
+  // positions, because the two chains run concurrently on two streams (see SideStream below).
   float* sh_y = nullptr;
-  Split sh_qkv, sh_ctx, sh_h, ring[4];
-  int ring_i = 0;
+  Split sh_qkv, sh_ctx, sh_h[2], ring[4];
+  int ring_i[3] = {0, 0, 0};        // language / vision / joint
   if (!training) {
     sh_qkv = b.split(Mt * 3 * H);
     sh_ctx = b.split(Mt * H);
     sh_y = b.f32(Mt * H);
-    sh_h = b.split(Mmax * I);
+    sh_h[0] = b.split(Ml * I);
+    sh_h[1] = b.split(Mv * I);
     for (auto& r : ring) r = b.split(Mt * H);
   }
-  auto new_state = [&](size_t M) -> Split {
+  // who: 0 = language rows, 1 = vision rows, 2 = all rows
+  auto new_state = [&](size_t M, int who) -> Split {
     if (training) return b.split(M * H);
-    Split s = ring[ring_i];
-    ring_i = (ring_i + 1) & 3;
-    return s;
+    Split s = ring[ring_i[who]];
+    ring_i[who] = (ring_i[who] + 1) & 3;
+    return who == 1 ? rows(s, Ml, H) : s;
   };
-  auto fill_att = [&](AttSave& a, size_t M, size_t probs_elems, size_t probs2_elems) {
+  auto fill_att = [&](AttSave& a, size_t M, size_t probs_elems, size_t probs2_elems, int who) {
     a.M = static_cast<int>(M);
     if (training) {
       a.qkv = b.split(M * 3 * H);
@@ -191,10 +199,11 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
       a.mean = b.f32(M);
       a.rstd = b.f32(M);
     } else {
-      a.qkv = sh_qkv; a.ctx = sh_ctx; a.y = sh_y;
+      const size_t row0 = who == 1 ? Ml : 0;
+      a.qkv = rows(sh_qkv, row0, 3 * H); a.ctx = rows(sh_ctx, row0, H); a.y = sh_y + row0 * H;
     }
   };
-  auto fill_ffn = [&](FfnSave& f, size_t M) {
+  auto fill_ffn = [&](FfnSave& f, size_t M, int who) {
     f.M = static_cast<int>(M);
     if (training) {
       f.u = b.f32(M * I);
@@ -203,7 +212,7 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
       f.mean = b.f32(M);
       f.rstd = b.f32(M);
     } else {
-      f.h = sh_h; f.y = sh_y;
+      f.h = sh_h[who]; f.y = sh_y + (who == 1 ? Ml : 0) * H;
     }
   };
   const size_t nh = p.heads;
@@ -218,12 +227,12 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
     for (int i = 0; i < n; ++i) {
       AttSave& a = p.att[blk0 + i];
       FfnSave& f = p.ffn[blk0 + i];
-      fill_att(a, M, B * nh * S * S, 0);
+      fill_att(a, M, B * nh * S * S, 0, s);
       a.in = cur;
-      a.out = new_state(M);
-      fill_ffn(f, M);
+      a.out = new_state(M, s);
+      fill_ffn(f, M, s);
       f.in = a.out;
-      f.out = (i == n - 1) ? rows(xin0, row0, H) : new_state(M);
+      f.out = (i == n - 1) ? rows(xin0, row0, H) : new_state(M, s);
       cur = f.out;
     }
   }
@@ -234,24 +243,17 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
     AttSave& sv = p.att[nl + nr + 3 * k + 2];
     FfnSave& fl = p.ffn[nl + nr + 2 * k];
     FfnSave& fv = p.ffn[nl + nr + 2 * k + 1];
-    fill_att(c, Mt, B * nh * L * V, B * nh * V * L);
+    fill_att(c, Mt, B * nh * L * V, B * nh * V * L, 2);
     c.in = X;
-    c.out = new_state(Mt);
-    Split S2 = new_state(Mt);
-    if (training) {
-      fill_att(sl, Ml, B * nh * L * L, 0);
-      fill_att(sv, Mv, B * nh * V * V, 0);
-    } else {  // shared temporaries: give the two streams disjoint row ranges
-      fill_att(sl, Ml, 0, 0);
-      fill_att(sv, Mv, 0, 0);
-      sv.qkv = rows(sh_qkv, Ml, 3 * H); sv.ctx = rows(sh_ctx, Ml, H); sv.y = sh_y + Ml * H;
-    }
+    c.out = new_state(Mt, 2);
+    Split S2 = new_state(Mt, 2);
+    fill_att(sl, Ml, B * nh * L * L, 0, 0);
+    fill_att(sv, Mv, B * nh * V * V, 0, 1);
     sl.in = rows(c.out, 0, H); sl.out = rows(S2, 0, H);
     sv.in = rows(c.out, Ml, H); sv.out = rows(S2, Ml, H);
-    Split O = new_state(Mt);
-    fill_ffn(fl, Ml);
-    fill_ffn(fv, Mv);
-    if (!training) fv.y = sh_y + Ml * H;   // fv.h may alias fl.h: the two FFNs run back to back on one stream
+    Split O = new_state(Mt, 2);
+    fill_ffn(fl, Ml, 0);
+    fill_ffn(fv, Mv, 1);
     fl.in = sl.out; fl.out = rows(O, 0, H);
     fv.in = sv.out; fv.out = rows(O, Ml, H);
     X = O;
@@ -259,13 +261,18 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
   if (training) {
     p.dA = b.f32(Mt * H);
     p.dB = b.f32(Mt * H);
-    p.dy = b.f32(Mt * H);
-    p.dctx = b.split(Mt * H);
     p.dy2 = b.f32(Mv * H);
-    p.dy_s = b.split(Mt * H);
-    p.dqkv = b.split(Mt * 3 * H);
-    p.du = b.split(Mmax * I);
-    p.splitk = b.f32(gemm_splitk_ws_floats());
+    for (int i = 0; i < 2; ++i) {
+      BwdScratch& c = p.sc[i];
+      const size_t M = i ? Ml : Mt;
+      c.dy = b.f32(M * H);
+      c.dctx = b.split(M * H);
+      c.dy_s = b.split(M * H);
+      c.dqkv = b.split(M * 3 * H);
+      c.du = b.split((i ? Ml : Mmax) * I);
+      c.splitk = b.f32(gemm_splitk_ws_floats());
+      if (i) c.part = b.f32(pe);
+    }
   }
   p.bytes = b.off + 256;
   return p;
@@ -290,8 +297,8 @@ int linear(const Run& r, Split x, int M, int K, Split w, int N, const GemmEpilog
 int dgrad(const Run& r, Split dy, int M, int N, Split w_t, int K, const GemmEpilogue& e) {
   return gemm_linear(r.passes, r.st, dy, M, N, w_t, K, e);
 }
-int wgrad(const Run& r, Split dy, int M, int N, Split x, int K, float* dw) {
-  return gemm_wgrad(r.passes, r.st, dy, M, N, x, K, dw, false, 0, r.plan.splitk);
+int wgrad(const Run& r, float* splitk, Split dy, int M, int N, Split x, int K, float* dw) {
+  return gemm_wgrad(r.passes, r.st, dy, M, N, x, K, dw, false, 0, splitk);
 }
 
 const float* P(const Run& r, int slot) { return r.params[slot]; }
@@ -376,7 +383,8 @@ int ffn_fwd(const Run& r, int blk, float* out_f32) {
 // All take the gradient wrt the block output in `dout` ([M,H] fp32) and leave the gradient wrt the block
 // input in `din`.  Parameter gradients go to the flat arena `grads` at the slot offsets.
 struct Bwd {
-  const Run* r;
+  const Run* r;            // carries the stream the blocks are issued on
+  const BwdScratch* sc;    // temporaries owned by that stream
   float* grads;
   SlotTable slots;
   float* G(int slot) const { return grads + slots.offset[slot]; }
@@ -388,88 +396,136 @@ int ln_tail_bwd(const Bwd& bw, const float* dout, const float* y, int slot_g, co
                 int M, float* dy, Split dy_s) {
   const Run& r = *bw.r;
   int nblk = 0;
-  XLX_TRY(layernorm_bwd(dout, 1.0f, y, P(r, slot_g), mean, rstd, M, r.plan.H, dy, dy_s, r.plan.part, &nblk, r.st));
+  XLX_TRY(layernorm_bwd(dout, 1.0f, y, P(r, slot_g), mean, rstd, M, r.plan.H, dy, dy_s, bw.sc->part, &nblk, r.st));
   float* outs[3] = {bw.G(slot_g), bw.G(slot_g + 1), bw.G(slot_g - 1)};
-  return colsum_finish(r.plan.part, 3, nblk, r.plan.H, outs, 0, r.st);
+  return colsum_finish(bw.sc->part, 3, nblk, r.plan.H, outs, 0, r.st);
 }
 
 int ffn_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
   const Run& r = *bw.r;
   const Plan& p = r.plan;
+  const BwdScratch& c = *bw.sc;
   const FfnSave& f = p.ffn[blk];
   const FfnW& w = r.prep.ffn[blk];
   const int s0 = ffn_slot(r.d, blk), H = p.H, I = p.I, M = f.M;
-  XLX_TRY(ln_tail_bwd(bw, dout, f.y, s0 + 4, f.mean, f.rstd, M, p.dy, p.dy_s));    // also dense bias grad (s0 + 3)
-  XLX_TRY(wgrad(r, p.dy_s, M, H, f.h, I, bw.G(s0 + 2)));
+  XLX_TRY(ln_tail_bwd(bw, dout, f.y, s0 + 4, f.mean, f.rstd, M, c.dy, c.dy_s));    // also dense bias grad (s0 + 3)
+  XLX_TRY(wgrad(r, c.splitk, c.dy_s, M, H, f.h, I, bw.G(s0 + 2)));
   GemmEpilogue e;   // du = (dy · W2) ∘ gelu'(u), the derivative was saved by the forward
-  e.flags = EPI_MUL; e.u_in = f.u; e.ld_u = I; e.out_hi = p.du.hi; e.out_lo = p.du.lo; e.ld_split = I;
-  e.colsum_part = p.part;   // the intermediate bias gradient = column sums of du, gathered by the same epilogue
-  XLX_TRY(dgrad(r, p.dy_s, M, H, w.w2_t, I, e));
+  e.flags = EPI_MUL; e.u_in = f.u; e.ld_u = I; e.out_hi = c.du.hi; e.out_lo = c.du.lo; e.ld_split = I;
+  e.colsum_part = c.part;   // the intermediate bias gradient = column sums of du, gathered by the same epilogue
+  XLX_TRY(dgrad(r, c.dy_s, M, H, w.w2_t, I, e));
   {
     float* outs[1] = {bw.G(s0 + 1)};
-    XLX_TRY(colsum_finish(p.part, 1, (M + 31) / 32, I, outs, 0, r.st));
+    XLX_TRY(colsum_finish(c.part, 1, (M + 31) / 32, I, outs, 0, r.st));
   }
-  XLX_TRY(wgrad(r, p.du, M, I, f.in, H, bw.G(s0)));
+  XLX_TRY(wgrad(r, c.splitk, c.du, M, I, f.in, H, bw.G(s0)));
   GemmEpilogue o;   // din = du · W1 + dy (residual path)
-  o.addend = p.dy; o.ld_addend = H; o.out_f32 = din; o.ld_out = H;
-  return dgrad(r, p.du, M, I, w.w1_t, H, o);
+  o.addend = c.dy; o.ld_addend = H; o.out_f32 = din; o.ld_out = H;
+  return dgrad(r, c.du, M, I, w.w1_t, H, o);
 }
 
 // common tail/head of the attention backward: everything except the attention-core call(s)
 int att_bwd_head(const Bwd& bw, int blk, const float* dout) {
   const Run& r = *bw.r;
   const Plan& p = r.plan;
+  const BwdScratch& c = *bw.sc;
   const AttSave& a = p.att[blk];
   const AttW& w = r.prep.att[blk];
   const int s0 = att_slot(r.d, blk), H = p.H, M = a.M;
-  XLX_TRY(ln_tail_bwd(bw, dout, a.y, s0 + 8, a.mean, a.rstd, M, p.dy, p.dy_s));    // also dense bias grad (s0 + 7)
-  XLX_TRY(wgrad(r, p.dy_s, M, H, a.ctx, H, bw.G(s0 + 6)));
+  XLX_TRY(ln_tail_bwd(bw, dout, a.y, s0 + 8, a.mean, a.rstd, M, c.dy, c.dy_s));    // also dense bias grad (s0 + 7)
+  XLX_TRY(wgrad(r, c.splitk, c.dy_s, M, H, a.ctx, H, bw.G(s0 + 6)));
   GemmEpilogue e;
-  e.out_hi = p.dctx.hi; e.out_lo = p.dctx.lo; e.ld_split = H;
-  return dgrad(r, p.dy_s, M, H, w.wo_t, H, e);
+  e.out_hi = c.dctx.hi; e.out_lo = c.dctx.lo; e.ld_split = H;
+  return dgrad(r, c.dy_s, M, H, w.wo_t, H, e);
 }
 int att_bwd_tail(const Bwd& bw, int blk, float* din) {
   const Run& r = *bw.r;
   const Plan& p = r.plan;
+  const BwdScratch& c = *bw.sc;
   const AttSave& a = p.att[blk];
   const AttW& w = r.prep.att[blk];
   const int s0 = att_slot(r.d, blk), H = p.H, M = a.M;
-  XLX_TRY(colsum(nullptr, p.dqkv, M, 3 * H, 3 * H, p.part, bw.G(s0 + 3), r.st));   // q.bias | k.bias | v.bias
-  XLX_TRY(wgrad(r, p.dqkv, M, 3 * H, a.in, H, bw.G(s0)));                          // q.w | k.w | v.w
+  XLX_TRY(colsum(nullptr, c.dqkv, M, 3 * H, 3 * H, c.part, bw.G(s0 + 3), r.st));   // q.bias | k.bias | v.bias
+  XLX_TRY(wgrad(r, c.splitk, c.dqkv, M, 3 * H, a.in, H, bw.G(s0)));                          // q.w | k.w | v.w
   GemmEpilogue o;
-  o.addend = p.dy; o.ld_addend = H; o.out_f32 = din; o.ld_out = H;
-  return dgrad(r, p.dqkv, M, 3 * H, w.wqkv_t, H, o);
+  o.addend = c.dy; o.ld_addend = H; o.out_f32 = din; o.ld_out = H;
+  return dgrad(r, c.dqkv, M, 3 * H, w.wqkv_t, H, o);
 }
 int att_self_bwd(const Bwd& bw, int blk, int S, const float* dout, float* din) {
   const Run& r = *bw.r;
   const Plan& p = r.plan;
+  const BwdScratch& c = *bw.sc;
   const AttSave& a = p.att[blk];
   const int H = p.H;
   XLX_TRY(att_bwd_head(bw, blk, dout));
-  Split dq = p.dqkv, dk = p.dqkv, dv = p.dqkv;
+  Split dq = c.dqkv, dk = c.dqkv, dv = c.dqkv;
   dk.hi += H; dk.lo += H; dv.hi += 2 * H; dv.lo += 2 * H;
-  XLX_TRY(attention_bwd(mat_op(p.dctx, a.M, H), qkv_op(a.qkv, a.M, H, 0), qkv_op(a.qkv, a.M, H, 1),
+  XLX_TRY(attention_bwd(mat_op(c.dctx, a.M, H), qkv_op(a.qkv, a.M, H, 0), qkv_op(a.qkv, a.M, H, 1),
                         qkv_op(a.qkv, a.M, H, 2), a.probs, p.B, p.heads, S, S, dq, dk, dv, 3 * H, r.st));
   return att_bwd_tail(bw, blk, din);
 }
 int att_cross_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
   const Run& r = *bw.r;
   const Plan& p = r.plan;
+  const BwdScratch& c = *bw.sc;
   const AttSave& a = p.att[blk];
   const int H = p.H;
   const size_t H3 = 3 * static_cast<size_t>(H);
   XLX_TRY(att_bwd_head(bw, blk, dout));
   const Split ql = a.qkv, qv = rows(a.qkv, p.Ml, H3);
-  Split dl = p.dqkv, dvv = rows(p.dqkv, p.Ml, H3);   // language rows / vision rows of dqkv
+  Split dl = c.dqkv, dvv = rows(c.dqkv, p.Ml, H3);   // language rows / vision rows of dqkv
   auto col = [](Split s, int c) { s.hi += c; s.lo += c; return s; };
   // language queries: dQ → language rows, dK/dV → vision rows
-  XLX_TRY(attention_bwd(mat_op(p.dctx, p.Ml, H), qkv_op(ql, p.Ml, H, 0), qkv_op(qv, p.Mv, H, 1), qkv_op(qv, p.Mv, H, 2),
+  XLX_TRY(attention_bwd(mat_op(c.dctx, p.Ml, H), qkv_op(ql, p.Ml, H, 0), qkv_op(qv, p.Mv, H, 1), qkv_op(qv, p.Mv, H, 2),
                         a.probs, p.B, p.heads, p.L, p.V, col(dl, 0), col(dvv, H), col(dvv, 2 * H), 3 * H, r.st));
   // vision queries: dQ → vision rows, dK/dV → language rows
-  XLX_TRY(attention_bwd(mat_op(rows(p.dctx, p.Ml, H), p.Mv, H), qkv_op(qv, p.Mv, H, 0), qkv_op(ql, p.Ml, H, 1),
+  XLX_TRY(attention_bwd(mat_op(rows(c.dctx, p.Ml, H), p.Mv, H), qkv_op(qv, p.Mv, H, 0), qkv_op(ql, p.Ml, H, 1),
                         qkv_op(ql, p.Ml, H, 2), a.probs2, p.B, p.heads, p.V, p.L, col(dvv, 0), col(dl, H),
                         col(dl, 2 * H), 3 * H, r.st));
   return att_bwd_tail(bw, blk, din);
+}
+
+// ---- second stream -------------------------------------------------------------------------------
+// The language and the vision stacks are independent between the cross-attention blocks.  Language GEMMs have
+// M = B·L = 5120 rows at the reference batch: 120 or 480 tiles on 148 SMs, i.e. 19 % of every such launch is idle tail.
+// Issuing the language-side blocks on a library-owned side stream lets the two chains fill each other's tails.  The
+// caller's stream stays the only externally visible one: fork = side waits for an event on it, join = it waits for the
+// side stream (the pattern is CUDA-graph capturable).  XLX_TWO_STREAMS=0 issues everything on the caller's stream.
+struct SideStream {
+  cudaStream_t st = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  static const bool on = [] { const char* e = getenv("XLX_TWO_STREAMS"); return !(e && e[0] == '0'); }();
+  if (!on) return nullptr;
+  static SideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = per_dev[dev];
+  if (!s.st) {
+    if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      s.st = nullptr;
+      cudaGetLastError();
+      return nullptr;
+    }
+  }
+  return &s;
+}
+// side stream continues from the current end of `main`
+int fork_to(SideStream* s, cudaStream_t main) {
+  if (!s) return 0;
+  XLX_CUDA(cudaEventRecord(s->fork, main));
+  XLX_CUDA(cudaStreamWaitEvent(s->st, s->fork, 0));
+  return 0;
+}
+// `main` continues after everything issued on the side stream so far
+int join_from(SideStream* s, cudaStream_t main) {
+  if (!s) return 0;
+  XLX_CUDA(cudaEventRecord(s->join, s->st));
+  XLX_CUDA(cudaStreamWaitEvent(main, s->join, 0));
+  return 0;
 }
 
 int check_common(const xlx_dims* d, int B, int L, int V) {
@@ -598,6 +654,11 @@ int32_t xlx_encoder_fwd(const xlx_dims* d, const float* const* params, const voi
     return last ? final_out : nullptr;
   };
 
+  // language-side blocks go to the side stream (rl), vision-side and joint blocks stay on the caller's (r)
+  SideStream* side = side_stream();
+  Run rl = r;
+  if (side) rl.st = side->st;
+  XLX_TRY(fork_to(side, r.st));
   // ---- visual feature encoder (HF:476-484): (LN(W·feat + b) + LN(Wp·pos + bp)) / 2
   XLX_TRY(split_f32(visual_feats, p.feats, static_cast<size_t>(Mv) * F, r.st));
   {
@@ -610,27 +671,30 @@ int32_t xlx_encoder_fwd(const xlx_dims* d, const float* const* params, const voi
     XLX_TRY(layernorm_fwd(p.y1, P(r, 2), P(r, 3), d->ln_eps, Mv, H, 0.5f, p.tbox, p.vis0, nullptr,
                           p.training ? p.vstats : nullptr, p.training ? p.vstats + Mv : nullptr, r.st));
   }
-  XLX_TRY(split_f32(lang_in, p.lang0, lh, r.st));
+  XLX_TRY(split_f32(lang_in, p.lang0, lh, rl.st));
 
-  // ---- language layers (HF:524-529), then vision layers (HF:532-537)
+  // ---- language layers (HF:524-529) alongside the vision layers (HF:532-537)
   for (int i = 0; i < nl; ++i) {
-    XLX_TRY(att_self_fwd(r, i, L, lang_mask, nullptr));
-    XLX_TRY(ffn_fwd(r, i, hidden_ptr(lang_hidden, i, lh, nx == 0 && i == nl - 1, lang_out)));
+    XLX_TRY(att_self_fwd(rl, i, L, lang_mask, nullptr));
+    XLX_TRY(ffn_fwd(rl, i, hidden_ptr(lang_hidden, i, lh, nx == 0 && i == nl - 1, lang_out)));
   }
   for (int i = 0; i < nr; ++i) {
     XLX_TRY(att_self_fwd(r, nl + i, V, vis_mask, nullptr));
     XLX_TRY(ffn_fwd(r, nl + i, hidden_ptr(vis_hidden, i, vh, nx == 0 && i == nr - 1, vis_out)));
   }
-  // ---- cross-modality layers (HF:540-552): cross → self → FFN
+  // ---- cross-modality layers (HF:540-552): cross (joint) → self → FFN (per modality, side by side)
   for (int k = 0; k < nx; ++k) {
     const int a0 = nl + nr + 3 * k, f0 = nl + nr + 2 * k;
     const bool last = (k == nx - 1);
+    XLX_TRY(join_from(side, r.st));
     XLX_TRY(att_cross_fwd(r, a0));
-    XLX_TRY(att_self_fwd(r, a0 + 1, L, lang_mask, nullptr));
+    XLX_TRY(fork_to(side, r.st));
+    XLX_TRY(att_self_fwd(rl, a0 + 1, L, lang_mask, nullptr));
+    XLX_TRY(ffn_fwd(rl, f0, hidden_ptr(lang_hidden, nl + k, lh, last, lang_out)));
     XLX_TRY(att_self_fwd(r, a0 + 2, V, vis_mask, nullptr));
-    XLX_TRY(ffn_fwd(r, f0, hidden_ptr(lang_hidden, nl + k, lh, last, lang_out)));
     XLX_TRY(ffn_fwd(r, f0 + 1, hidden_ptr(vis_hidden, nr + k, vh, last, vis_out)));
   }
+  XLX_TRY(join_from(side, r.st));
   // final outputs: when hidden states were requested the last state was written there — copy it out
   const int n_lang_states = nl + nx, n_vis_states = nr + nx;
   if (lang_hidden && n_lang_states > 0) {
@@ -663,7 +727,12 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
   const Plan& p = r.plan;
   if (p.bytes > workspace_bytes) return -23;
   Bwd bw;
-  bw.r = &r; bw.grads = grads; bw.slots = slot_table(d);
+  bw.r = &r; bw.sc = &p.sc[0]; bw.grads = grads; bw.slots = slot_table(d);
+  // language-side blocks: side stream + their own temporaries (falls back to the caller's stream and set 0)
+  SideStream* side = side_stream();
+  Run rl = r;
+  Bwd bwl = bw;
+  if (side) { rl.st = side->st; bwl.r = &rl; bwl.sc = &p.sc[1]; }
   const int H = p.H, F = p.F, Ml = p.Ml, Mv = p.Mv;
   const int nl = d->l_layers, nr = d->r_layers, nx = d->x_layers;
   const size_t lh = static_cast<size_t>(Ml) * H, vh = static_cast<size_t>(Mv) * H;
@@ -683,15 +752,29 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
     XLX_TRY(load_grad(cur + lh, d_vis_out, vh));
     for (int k = nx - 1; k >= 0; --k) {
       const int a0 = nl + nr + 3 * k, f0 = nl + nr + 2 * k;
-      XLX_TRY(ffn_bwd(bw, f0, cur, nxt));
-      XLX_TRY(ffn_bwd(bw, f0 + 1, cur + lh, nxt + lh));
-      XLX_TRY(att_self_bwd(bw, a0 + 1, L, nxt, cur));
+      XLX_TRY(fork_to(side, r.st));
+      XLX_TRY(ffn_bwd(bwl, f0, cur, nxt));                          // language chain
+      XLX_TRY(att_self_bwd(bwl, a0 + 1, L, nxt, cur));
+      XLX_TRY(ffn_bwd(bw, f0 + 1, cur + lh, nxt + lh));             // vision chain
       XLX_TRY(att_self_bwd(bw, a0 + 2, V, nxt + lh, cur + lh));
-      XLX_TRY(att_cross_bwd(bw, a0, cur, nxt));
+      XLX_TRY(join_from(side, r.st));
+      XLX_TRY(att_cross_bwd(bw, a0, cur, nxt));                     // joint
       float* t = cur; cur = nxt; nxt = t;
     }
   } else if (nx & 1) {
     cur = p.dB; nxt = p.dA;
+  }
+  // the language stack runs beside the vision stack / visual feature encoder when the same call asks for both
+  const bool lang_beside = side && (stages & XLX_BWD_LANGUAGE) && (stages & (XLX_BWD_VISION | XLX_BWD_VISN_FC));
+  if (stages & XLX_BWD_LANGUAGE) {
+    const Bwd& b = lang_beside ? bwl : bw;
+    if (lang_beside) XLX_TRY(fork_to(side, r.st));
+    for (int i = nl - 1; i >= 0; --i) {
+      XLX_TRY(ffn_bwd(b, i, cur, nxt));
+      XLX_TRY(att_self_bwd(b, i, L, nxt, cur));
+    }
+    // language embedding gradient
+    XLX_CUDA(cudaMemcpyAsync(d_lang_in, cur, lh * 4, cudaMemcpyDeviceToDevice, b.r->st));
   }
   if (stages & XLX_BWD_VISION) {
     for (int i = nr - 1; i >= 0; --i) {
@@ -699,35 +782,29 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
       XLX_TRY(att_self_bwd(bw, nl + i, V, nxt + lh, cur + lh));
     }
   }
-  if (stages & XLX_BWD_LANGUAGE) {
-    for (int i = nl - 1; i >= 0; --i) {
-      XLX_TRY(ffn_bwd(bw, i, cur, nxt));
-      XLX_TRY(att_self_bwd(bw, i, L, nxt, cur));
-    }
-    // language embedding gradient
-    XLX_CUDA(cudaMemcpyAsync(d_lang_in, cur, lh * 4, cudaMemcpyDeviceToDevice, r.st));
-  }
   if (stages & XLX_BWD_VISN_FC) {
     // visual feature encoder backward
     const float* dvis = cur + lh;
+    const BwdScratch& c = p.sc[0];
     int nblk = 0;
     // box branch: d(0.5·LN_b(y2))
     XLX_TRY(layernorm_bwd(dvis, 0.5f, p.y2, P(r, 6), p.vstats + 2 * Mv, p.vstats + 3 * Mv, Mv, H, p.dy2, Split(),
-                          p.part, &nblk, r.st));
+                          c.part, &nblk, r.st));
     float* o2[2] = {bw.G(6), bw.G(7)};
-    XLX_TRY(colsum_finish(p.part, 2, nblk, H, o2, 0, r.st));
-    XLX_TRY(box_linear_bwd(p.dy2, visual_pos, Mv, H, p.part, bw.G(4), bw.G(5), r.st));
+    XLX_TRY(colsum_finish(c.part, 2, nblk, H, o2, 0, r.st));
+    XLX_TRY(box_linear_bwd(p.dy2, visual_pos, Mv, H, c.part, bw.G(4), bw.G(5), r.st));
     // feature branch: d(0.5·LN_v(y1))
-    XLX_TRY(layernorm_bwd(dvis, 0.5f, p.y1, P(r, 2), p.vstats, p.vstats + Mv, Mv, H, p.dy, p.dy_s, p.part, &nblk, r.st));
+    XLX_TRY(layernorm_bwd(dvis, 0.5f, p.y1, P(r, 2), p.vstats, p.vstats + Mv, Mv, H, c.dy, c.dy_s, c.part, &nblk, r.st));
     float* o1[3] = {bw.G(2), bw.G(3), bw.G(1)};      // LN affine grads + visn_fc bias grad (Σ_rows of the LN-input grad)
-    XLX_TRY(colsum_finish(p.part, 3, nblk, H, o1, 0, r.st));
-    XLX_TRY(wgrad(r, p.dy_s, Mv, H, p.feats, F, bw.G(0)));
+    XLX_TRY(colsum_finish(c.part, 3, nblk, H, o1, 0, r.st));
+    XLX_TRY(wgrad(r, c.splitk, c.dy_s, Mv, H, p.feats, F, bw.G(0)));
     if (d_visual_feats) {
       GemmEpilogue e;
       e.out_f32 = d_visual_feats; e.ld_out = F;
-      XLX_TRY(dgrad(r, p.dy_s, Mv, H, r.prep.visn_w_t, F, e));
+      XLX_TRY(dgrad(r, c.dy_s, Mv, H, r.prep.visn_w_t, F, e));
     }
   }
+  if (lang_beside) XLX_TRY(join_from(side, r.st));
   return 0;
 }
 

@@ -100,7 +100,10 @@ class _EncoderSkeleton(nn.Module):
 
 
 # ---- autograd bridge -------------------------------------------------------------------------------
-_BWD_STAGES = (1, 2, 4, 8)      # XLX_BWD_CROSS, _VISION, _LANGUAGE, _VISN_FC (include/xlxmert_b200.h), in issue order
+# Backward stage masks (include/xlxmert_b200.h: XLX_BWD_CROSS = 1, _VISION = 2, _LANGUAGE = 4, _VISN_FC = 8) in the order the
+# data-parallel backward issues them: the cross-modality layers first, then everything below them in ONE call so that the
+# language stack runs beside the vision stack on the library's second stream.
+_BWD_STAGES = (1, 2 | 4 | 8)
 _BWD_ALL = 15
 
 
@@ -306,13 +309,24 @@ class B200LxmertEncoder(nn.Module):
         if len(self._ws_pool) < 2:
             self._ws_pool.append(t)
 
-    def _stage_range(self, stage: int):
-        if stage not in self._stage_ranges:
-            off, n = C.c_int64(), C.c_int64()
-            _lib.check("xlx_encoder_grad_stage_range",
-                       _lib.load().xlx_encoder_grad_stage_range(C.byref(self._cdims), stage, C.byref(off), C.byref(n)))
-            self._stage_ranges[stage] = (off.value, n.value)
-        return self._stage_ranges[stage]
+    def _stage_range(self, stages: int):
+        """Element range of the gradient arena completed by a mask of backward stages (their ranges must be adjacent)."""
+        if stages not in self._stage_ranges:
+            spans = []
+            for bit in (1, 2, 4, 8):
+                if stages & bit:
+                    off, n = C.c_int64(), C.c_int64()
+                    _lib.check("xlx_encoder_grad_stage_range",
+                               _lib.load().xlx_encoder_grad_stage_range(C.byref(self._cdims), bit, C.byref(off),
+                                                                        C.byref(n)))
+                    if n.value:
+                        spans.append((off.value, n.value))
+            spans.sort()
+            for (o0, n0), (o1, _) in zip(spans, spans[1:]):
+                if o0 + n0 != o1:
+                    raise ValueError(f"backward stages {stages:#x} do not cover one contiguous arena range")
+            self._stage_ranges[stages] = (spans[0][0], sum(n for _, n in spans)) if spans else (0, 0)
+        return self._stage_ranges[stages]
 
     def _grad_arena(self, dev) -> torch.Tensor:
         lib = _lib.load()
