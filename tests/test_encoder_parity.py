@@ -192,3 +192,30 @@ def test_staged_backward_equals_one_shot(stage_calls):
         assert off == pos
         pos += n
     assert pos == arena.numel()
+
+
+def test_gradient_arena_is_recycled_only_when_no_gradient_view_is_alive():
+    sd, batch, feats, emb, mask = _case(TINY_DIMS, 2, 5, 6, 3, 4)
+    enc = _encoder(TINY_DIMS, O.sub(sd, "encoder")).train()
+
+    def step():
+        e = emb.cuda().requires_grad_(True)
+        (v, _), (l, _), _ = enc(e, mask.cuda(), feats.cuda(), batch["visual_pos"].cuda())
+        (l[-1].sum() + (v[-1] ** 2).sum()).backward()
+        return enc.last_grad_arena
+
+    a1 = step()
+    p0 = next(enc.parameters())
+    kept = p0.grad.clone()
+    ptr1 = a1.data_ptr()
+    del a1
+    a2 = step()                      # gradients of step 1 are still alive (accumulation): a different arena
+    assert a2.data_ptr() != ptr1
+    assert torch.allclose(p0.grad, 2 * kept, rtol=1e-5, atol=1e-7)
+    ptr2 = a2.data_ptr()
+    del a2
+    for p in enc.parameters():
+        p.grad = None
+    a3 = step()                      # nothing refers to the old arenas any more: one of them is reused
+    assert a3.data_ptr() in (ptr1, ptr2)
+    assert torch.allclose(p0.grad, kept, rtol=1e-5, atol=1e-7)

@@ -109,7 +109,8 @@ class _PoolerFn(torch.autograd.Function):
                                 pooled.data_ptr(), ws.data_ptr(), nws, mod.passes, _stream())
         _lib.check("xlx_pooler_fwd", rc)
         if any(ctx.needs_input_grad):
-            ctx.mod, ctx.ws, ctx.nws, ctx.shape, ctx.pooled = mod, ws, nws, (B, L, H), pooled
+            ctx.mod, ctx.ws, ctx.nws, ctx.shape = mod, ws, nws, (B, L, H)
+            ctx.save_for_backward(pooled)     # an output kept as a plain ctx attribute would form a reference cycle
         return pooled
 
     @staticmethod
@@ -122,7 +123,8 @@ class _PoolerFn(torch.autograd.Function):
         d_lang = torch.empty(B, L, H, device=dev, dtype=torch.float32)
         dW = torch.empty(H, H, device=dev, dtype=torch.float32)
         db = torch.empty(H, device=dev, dtype=torch.float32)
-        rc = lib.xlx_pooler_bwd(C.byref(mod._cdims), B, L, ctx.pooled.data_ptr(), d_pooled.data_ptr(),
+        (pooled,) = ctx.saved_tensors
+        rc = lib.xlx_pooler_bwd(C.byref(mod._cdims), B, L, pooled.data_ptr(), d_pooled.data_ptr(),
                                 d_lang.data_ptr(), dW.data_ptr(), db.data_ptr(), ctx.ws.data_ptr(), ctx.nws,
                                 mod.passes, _stream())
         _lib.check("xlx_pooler_bwd", rc)

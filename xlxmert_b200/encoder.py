@@ -335,8 +335,22 @@ class B200LxmertEncoder(nn.Module):
             self._grad_slices = [(lib.xlx_encoder_grad_offset(C.byref(self._cdims), i),
                                   lib.xlx_encoder_param_elems(C.byref(self._cdims), i)) for i in range(n)]
         total = lib.xlx_encoder_grad_elems(C.byref(self._cdims))
-        # a fresh arena per backward: the returned gradients are views into it
-        return torch.empty(total, dtype=torch.float32, device=dev)
+        # The returned gradients are views into the arena, so an arena can only be recycled once nobody holds such a
+        # view any more (p.grad = None / zero_grad(set_to_none=True) of the previous step).  Recycling matters: a fresh
+        # 0.8 GB request every step fragments PyTorch's caching allocator until it falls back to cudaMalloc, which
+        # stalls the host for tens of milliseconds in the middle of a backward.
+        pool = self.__dict__.setdefault("_arena_pool", [])
+        use_count = getattr(torch._C, "_storage_Use_Count", None)
+        if use_count is not None:
+            for t in pool:
+                if t.device == dev and t.numel() == total:
+                    st = t.untyped_storage()
+                    if use_count(st._cdata) <= 2:      # the pool's tensor + the wrapper just made
+                        return t
+        t = torch.empty(total, dtype=torch.float32, device=dev)
+        if use_count is not None:
+            pool[:] = [a for a in pool if a.device == dev and a.numel() == total][-2:] + [t]
+        return t
 
     # -- partial passes (inference): the language layers never see the visual stream (HF:524-529), so a caller that
     #    re-runs the encoder with the same text (the sampler, tasks/imggen_model.py:199-243) can compute them once

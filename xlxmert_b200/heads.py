@@ -128,7 +128,10 @@ class _HeadLossFn(torch.autograd.Function):
     def forward(ctx, fused: _FusedHead, labels, hidden, *params):
         out = fused.forward(list(params), hidden, labels=labels)
         if any(ctx.needs_input_grad):
-            ctx.fused, ctx.saved, ctx.params, ctx.hshape = fused, out, params, hidden.shape
+            # everything but the returned loss: an output stored on ctx would tie the workspace (GBs of logits) into a
+            # reference cycle that only the cyclic garbage collector frees
+            saved = {k: v for k, v in out.items() if k != "loss"}
+            ctx.fused, ctx.saved, ctx.params, ctx.hshape = fused, saved, params, hidden.shape
         return out["loss"]
 
     @staticmethod
