@@ -339,7 +339,9 @@ def run_ours(args):
                 "gemm_share_of_step": (tot_ms.value / 2) / ms_step,
                 "executed_tensor_tflops": achieved * (3 if passes == 3 else 1),
                 "note": "achieved counts ALGORITHMIC FLOPs (2MNK); bf16x3 executes 3 MMAs per algorithmic MAC, "
-                        "so frac is capped at 1/3 by construction in the fp32-parity mode"}
+                        "so frac is capped at 1/3 by construction in the fp32-parity mode. The per-launch timing pass "
+                        "keeps every kernel on one stream (events between launches), so these durations exclude the "
+                        "two-stream / dependent-launch overlap the timed step enjoys"}
 
     if rank == 0:
         value = B * world / (ms_step * 1e-3)

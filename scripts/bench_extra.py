@@ -100,12 +100,12 @@ def main():
     m = m.cuda()
     Bs = 32
     tok = synth.make_batch(D, Bs, 20, 64, seed=3)["input_ids"].cuda()
-    ms = timed(lambda: m.sample_image_NAR(tok, n_steps=4), 3, warm=2)
+    ms = timed(lambda: m.sample_image_NAR(tok, n_steps=4), 6, warm=3)
     out[f"sample_NAR4_plus_decode_B{Bs}"] = {"ms": ms, "images_per_s": Bs / ms * 1e3,
                                              "algorithmic_tflops": 100.9 * Bs / ms}
-    ms = timed(lambda: m.sample_image_NAR(tok, n_steps=4, cuda_graph=True), 3, warm=2)
+    ms = timed(lambda: m.sample_image_NAR(tok, n_steps=4, cuda_graph=True), 6, warm=3)
     out[f"sample_NAR4_plus_decode_B{Bs}_cuda_graph"] = {"ms": ms, "images_per_s": Bs / ms * 1e3}
-    ms = timed(lambda: m.sample_image_NAR(tok, n_steps=4, cache_language=False), 3, warm=2)
+    ms = timed(lambda: m.sample_image_NAR(tok, n_steps=4, cache_language=False), 6, warm=3)
     out[f"sample_NAR4_plus_decode_B{Bs}_no_language_cache"] = {"ms": ms, "images_per_s": Bs / ms * 1e3}
     del m, pre, G
     torch.cuda.empty_cache()

@@ -143,3 +143,39 @@ def test_nar_sampler_steps_teacher_forced(setup):
             # teacher-force the reference's ids so that later steps see the reference's inputs
             code = torch.where(vis_mask.view(B, V, 1), table[ref_id], code)
     assert rel_err(code.cpu()[:, :, ::64], g["nar_code_sub"]) < 1e-6
+
+
+def test_training_steps_leave_no_tensor_in_a_reference_cycle(setup):
+    """A workspace caught in an autograd reference cycle (an output stored on ctx) is only released by the cyclic
+    garbage collector: memory balloons and the allocator falls back to cudaMalloc mid-step.  With the collector off,
+    the device memory in use must not grow from step to step and no tensor may end up in cyclic garbage."""
+    import gc
+    g, model, table, batch = setup
+    model.train()
+    for task in ("vis_mask", "word_mask", "matched"):
+        _step(model, batch, task)
+    model.zero_grad(set_to_none=True)
+    torch.cuda.synchronize()
+    gc.collect()
+    gc.disable()
+    old_flags = gc.get_debug()
+    try:
+        base = torch.cuda.memory_allocated()
+        for task in ("vis_mask", "word_mask", "matched") * 2:
+            out = _step(model, batch, task)
+            del out
+            model.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        grown = torch.cuda.memory_allocated() - base
+        gc.set_debug(gc.DEBUG_SAVEALL)
+        gc.collect()
+        trapped = [o for o in gc.garbage if isinstance(o, torch.Tensor)]
+        n_trapped = len(trapped)
+        del trapped
+        gc.garbage.clear()
+    finally:
+        gc.set_debug(old_flags)
+        gc.enable()
+        gc.collect()
+    assert n_trapped == 0
+    assert grown <= 1 << 20, f"device memory grew by {grown} bytes over 6 steps"

@@ -497,7 +497,7 @@ struct SideStream {
 };
 SideStream* side_stream() {
   static const bool on = [] { const char* e = getenv("XLX_TWO_STREAMS"); return !(e && e[0] == '0'); }();
-  if (!on) return nullptr;
+  if (!on || gemm_timing_active()) return nullptr;   // per-launch timing wants non-overlapping kernels
   static SideStream per_dev[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;

@@ -848,12 +848,15 @@ int tma_map_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t 
 // splits · tiles ≤ 2 · #SMs and every tile is ≤ 128 × 256 outputs
 size_t gemm_splitk_ws_floats() { return static_cast<size_t>(2 * 148) * BM * 256; }
 
+bool gemm_timing_active() { return g_timing; }
 void gemm_timing_begin() {
   g_timed.clear();
   g_timing = true;
+  g_pdl_suspended = true;
 }
 int gemm_timing_end(double* total_ms, double* total_flops, long long* launches) {
   g_timing = false;
+  g_pdl_suspended = false;
   double ms = 0, fl = 0;
   FILE* log = nullptr;
   if (const char* path = getenv("XLX_GEMM_LOG")) log = fopen(path, "w");

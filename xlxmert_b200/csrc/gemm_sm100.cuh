@@ -95,6 +95,7 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream);
 long long gemm_launch_count();
 // Per-launch CUDA-event timing of every GEMM between begin and end (algorithmic FLOPs = 2·M·N·K each).
 void gemm_timing_begin();
+bool gemm_timing_active();   // per-launch event timing is on: callers keep everything on one stream
 int gemm_timing_end(double* total_ms, double* total_flops, long long* launches);
 
 }  // namespace xlx

@@ -12,9 +12,10 @@ namespace xlx {
 // predecessor is still draining; they call pdl_wait() before touching global memory (it returns once every
 // preceding grid has completed and its writes are visible) and pdl_trigger() right away so that their own successor
 // can do the same.  Only kernels that contain pdl_wait() may be launched this way.  XLX_PDL=0 turns it off.
+inline bool g_pdl_suspended = false;   // set while per-launch event timing is on: timed launches must not overlap
 inline bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("XLX_PDL"); return !(e && e[0] == '0'); }();
-  return on;
+  return on && !g_pdl_suspended;
 }
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
