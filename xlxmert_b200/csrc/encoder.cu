@@ -117,8 +117,8 @@ struct FfnSave {
   int M = 0;
 };
 struct BwdScratch {
-  float* dy = nullptr;       // LayerNorm-input gradient [M, H]
-  Split dy_s, dqkv, du, dctx;
+  Split dy_s;                // LayerNorm-input gradient [M, H]: GEMM operand and residual-path addend
+  Split dqkv, du, dctx;
   float* part = nullptr;     // partial column sums (bias / LayerNorm-affine gradients)
   float* splitk = nullptr;   // split-K partial sums of the weight-gradient GEMMs
 };
@@ -265,7 +265,6 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
     for (int i = 0; i < 2; ++i) {
       BwdScratch& c = p.sc[i];
       const size_t M = i ? Ml : Mt;
-      c.dy = b.f32(M * H);
       c.dctx = b.split(M * H);
       c.dy_s = b.split(M * H);
       c.dqkv = b.split(M * 3 * H);
@@ -408,7 +407,7 @@ int ffn_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
   const FfnSave& f = p.ffn[blk];
   const FfnW& w = r.prep.ffn[blk];
   const int s0 = ffn_slot(r.d, blk), H = p.H, I = p.I, M = f.M;
-  XLX_TRY(ln_tail_bwd(bw, dout, f.y, s0 + 4, f.mean, f.rstd, M, c.dy, c.dy_s));    // also dense bias grad (s0 + 3)
+  XLX_TRY(ln_tail_bwd(bw, dout, f.y, s0 + 4, f.mean, f.rstd, M, nullptr, c.dy_s));    // also dense bias grad (s0 + 3)
   XLX_TRY(wgrad(r, c.splitk, c.dy_s, M, H, f.h, I, bw.G(s0 + 2)));
   GemmEpilogue e;   // du = (dy · W2) ∘ gelu'(u), the derivative was saved by the forward
   e.flags = EPI_MUL; e.u_in = f.u; e.ld_u = I; e.out_hi = c.du.hi; e.out_lo = c.du.lo; e.ld_split = I;
@@ -420,7 +419,8 @@ int ffn_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
   }
   XLX_TRY(wgrad(r, c.splitk, c.du, M, I, f.in, H, bw.G(s0)));
   GemmEpilogue o;   // din = du · W1 + dy (residual path)
-  o.addend = c.dy; o.ld_addend = H; o.out_f32 = din; o.ld_out = H;
+  o.addend_hi = c.dy_s.hi; o.addend_lo = c.dy_s.lo; o.ld_addend = H;   // residual path: + dy (kept as split bf16 only)
+  o.out_f32 = din; o.ld_out = H;
   return dgrad(r, c.du, M, I, w.w1_t, H, o);
 }
 
@@ -432,7 +432,7 @@ int att_bwd_head(const Bwd& bw, int blk, const float* dout) {
   const AttSave& a = p.att[blk];
   const AttW& w = r.prep.att[blk];
   const int s0 = att_slot(r.d, blk), H = p.H, M = a.M;
-  XLX_TRY(ln_tail_bwd(bw, dout, a.y, s0 + 8, a.mean, a.rstd, M, c.dy, c.dy_s));    // also dense bias grad (s0 + 7)
+  XLX_TRY(ln_tail_bwd(bw, dout, a.y, s0 + 8, a.mean, a.rstd, M, nullptr, c.dy_s));    // also dense bias grad (s0 + 7)
   XLX_TRY(wgrad(r, c.splitk, c.dy_s, M, H, a.ctx, H, bw.G(s0 + 6)));
   GemmEpilogue e;
   e.out_hi = c.dctx.hi; e.out_lo = c.dctx.lo; e.ld_split = H;
@@ -448,7 +448,8 @@ int att_bwd_tail(const Bwd& bw, int blk, float* din) {
   XLX_TRY(colsum(nullptr, c.dqkv, M, 3 * H, 3 * H, c.part, bw.G(s0 + 3), r.st));   // q.bias | k.bias | v.bias
   XLX_TRY(wgrad(r, c.splitk, c.dqkv, M, 3 * H, a.in, H, bw.G(s0)));                          // q.w | k.w | v.w
   GemmEpilogue o;
-  o.addend = c.dy; o.ld_addend = H; o.out_f32 = din; o.ld_out = H;
+  o.addend_hi = c.dy_s.hi; o.addend_lo = c.dy_s.lo; o.ld_addend = H;   // residual path: + dy (kept as split bf16 only)
+  o.out_f32 = din; o.ld_out = H;
   return dgrad(r, c.dqkv, M, 3 * H, w.wqkv_t, H, o);
 }
 int att_self_bwd(const Bwd& bw, int blk, int S, const float* dout, float* din) {
@@ -794,7 +795,7 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
     XLX_TRY(colsum_finish(c.part, 2, nblk, H, o2, 0, r.st));
     XLX_TRY(box_linear_bwd(p.dy2, visual_pos, Mv, H, c.part, bw.G(4), bw.G(5), r.st));
     // feature branch: d(0.5·LN_v(y1))
-    XLX_TRY(layernorm_bwd(dvis, 0.5f, p.y1, P(r, 2), p.vstats, p.vstats + Mv, Mv, H, c.dy, c.dy_s, c.part, &nblk, r.st));
+    XLX_TRY(layernorm_bwd(dvis, 0.5f, p.y1, P(r, 2), p.vstats, p.vstats + Mv, Mv, H, nullptr, c.dy_s, c.part, &nblk, r.st));
     float* o1[3] = {bw.G(2), bw.G(3), bw.G(1)};      // LN affine grads + visn_fc bias grad (Σ_rows of the LN-input grad)
     XLX_TRY(colsum_finish(c.part, 3, nblk, H, o1, 0, r.st));
     XLX_TRY(wgrad(r, c.splitk, c.dy_s, Mv, H, p.feats, F, bw.G(0)));
