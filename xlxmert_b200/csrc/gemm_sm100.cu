@@ -42,6 +42,10 @@ struct KParams {
   int kb_per_split;    // k-blocks per split (last split may be shorter)
   float* part;         // [splits][M][N] fp32 partial sums when splits > 1
   int conv, conv_H, conv_W, conv_taps, conv_kb_per_tap;   // implicit-GEMM convolution (see ConvGeometry)
+  // conv == 2 ("row halo", 3×3, W % 128 == 0): a k-block is (filter row dy, 32-channel block); its A stage is ONE haloed
+  // image row segment of 130 pixels, and the three dx taps are three UMMA descriptor views of it shifted by one pixel
+  // (64 bytes) each — every activation byte crosses L2→SM 3 times instead of 9.
+  uint32_t stage_tx;   // bytes one stage receives by TMA (= stage_bytes except in halo mode, whose A box is 130 rows)
   int cluster;         // 1, or 2 = CTA pairs on adjacent m-tiles sharing the B tile by TMA multicast
   int tiles_per_split; // tiles (cluster = 1) or tile pairs (cluster = 2) per split
   int num_items;       // work items of the launch: tiles_per_split · splits
@@ -192,7 +196,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024B alignment
 
-  const int nkb = (P.K + BK - 1) / BK;
+  const int nkb = (P.conv == 2) ? 3 * P.conv_kb_per_tap : (P.K + BK - 1) / BK;
   // Work decomposition.  cluster = 1: item → (tile, split).  cluster = 2: the two CTAs of a cluster take the m-tiles
   // 2p and 2p + 1 of the same n-tile, so that each loads half of the shared B tile and multicasts it to both.
   const int crank = (P.cluster == 2) ? static_cast<int>(cluster_ctarank()) : 0;
@@ -257,7 +261,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
           const uint32_t full = smem_u32(&bar_full[s]);
-          mbar_arrive_expect_tx(full, P.stage_bytes);
+          mbar_arrive_expect_tx(full, P.stage_tx);
           const uint32_t sA = smem_base + s * P.stage_bytes;
           const uint32_t sB = sA + NPARTS * P.a_part_bytes;
           const int k0 = kb * BK;
@@ -267,7 +271,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
             const CUtensorMap* mb = part ? &mapBlo : &mapBhi;
             const uint32_t dA = sA + part * P.a_part_bytes;
             const uint32_t dB = sB + part * P.b_part_bytes;
-            if (!A_MN && P.conv) {
+            if (!A_MN && !B_MN && P.conv == 2) {
+              // k-block → (filter row, channel block): one haloed row segment [x0 − 1, x0 + 129) and the 3 weight taps
+              const int dyi = kb / P.conv_kb_per_tap, cb = kb % P.conv_kb_per_tap;
+              tma_load_4d(dA, ma, full, cb * BK, x0 - 1, y0 + dyi - 1, img);
+#pragma unroll
+              for (int dxi = 0; dxi < 3; ++dxi)
+                tma_load_2d(dB + dxi * (P.BN * BK * 2), mb, full, ((dyi * 3 + dxi) * P.conv_kb_per_tap + cb) * BK, n0);
+              continue;
+            } else if (!A_MN && P.conv) {
               // k-block → (filter tap, channel offset); the box is the activation tensor shifted by the tap
               const int tap = kb / P.conv_kb_per_tap, c0 = (kb % P.conv_kb_per_tap) * BK;
               const int dy = P.conv_taps == 9 ? tap / 3 - 1 : 0, dx = P.conv_taps == 9 ? tap % 3 - 1 : 0;
@@ -332,7 +344,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
         const uint32_t sA = (smem_base + s * P.stage_bytes) & 0x3FFFFu;
         const uint32_t a0 = loA | (sA >> 4);
         const uint32_t b0 = loB | ((sA + NPARTS * P.a_part_bytes) >> 4);
-        if (elect_one()) {
+        if (!A_MN && !B_MN && P.conv == 2) {
+          if (elect_one()) {
+            const uint32_t b_tap = (P.BN * BK * 2) >> 4;
+#pragma unroll
+            for (int dxi = 0; dxi < 3; ++dxi) {
+              // View of the haloed row shifted by dxi pixels = dxi · 64 bytes added to the descriptor's start address.
+              // Measured on B200: the 64-byte swizzle is applied to absolute shared-memory address bits, so a start
+              // that is not aligned to the 512-byte swizzle period reads the TMA-written tile correctly with the
+              // base-offset field (bits 49-51) left at 0; filling it with (addr >> 7) & 7 gives wrong results.
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk) {
+                const uint32_t acc = (kb > kb0 || dxi > 0 || kk > 0) ? 1u : 0u;
+                const uint32_t ah = a0 + dxi * ((BK * 2) >> 4) + kk * stepA, bh = b0 + dxi * b_tap + kk * stepB;
+                if (NPARTS == 2) {
+                  umma_bf16(tmem_d, umma_desc(hiA, ah + a_part), umma_desc(hiB, bh), idesc, acc);
+                  umma_bf16(tmem_d, umma_desc(hiA, ah), umma_desc(hiB, bh + b_part), idesc, 1u);
+                  umma_bf16(tmem_d, umma_desc(hiA, ah), umma_desc(hiB, bh), idesc, 1u);
+                } else {
+                  umma_bf16(tmem_d, umma_desc(hiA, ah), umma_desc(hiB, bh), idesc, acc);
+                }
+              }
+            }
+            umma_commit(smem_u32(&bar_empty[s]));
+            if (kb == kb1 - 1) umma_commit(smem_u32(&bar_tmem_full[buf]));
+          }
+        } else if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint32_t acc = (kb > kb0 || kk > 0) ? 1u : 0u;
@@ -686,6 +723,7 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   P.a_part_bytes = BM * BK * 2;
   P.b_part_bytes = BN * BK * 2;
   P.stage_bytes = P.nparts * (P.a_part_bytes + P.b_part_bytes);
+  P.stage_tx = P.stage_bytes;
   int stages = (SMEM_LIMIT - 2048 - 1024 - STAGE_BYTES) / static_cast<int>(P.stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return -3;
@@ -726,10 +764,24 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
       bw = g.W; bh = g.H; bb = BM / hw;
     }
     const int nimg = p.M / hw;
+    static const int halo_on = env_int("XLX_CONV_HALO", 1);
+    const bool halo = halo_on && BK == 32 && g.taps == 9 && g.W % BM == 0 && !p.b.mn_major;
+    if (halo) { bw = BM + 2; bh = 1; bb = 1; }
     if ((rc = make_map4(&mAhi, p.a.hi, nimg, g.H, g.W, g.C, BK, bw, bh, bb, swzK))) return rc;
     if (P.nparts == 2) { if ((rc = make_map4(&mAlo, p.a.lo, nimg, g.H, g.W, g.C, BK, bw, bh, bb, swzK))) return rc; }
     else mAlo = mAhi;
-    P.conv = 1; P.conv_H = g.H; P.conv_W = g.W; P.conv_taps = g.taps; P.conv_kb_per_tap = g.C / BK;
+    P.conv = halo ? 2 : 1; P.conv_H = g.H; P.conv_W = g.W; P.conv_taps = g.taps; P.conv_kb_per_tap = g.C / BK;
+    if (halo) {
+      const uint32_t a_box = (BM + 2) * BK * 2;                       // 130 pixel rows of 64 bytes
+      P.a_part_bytes = (a_box + 1023u) & ~1023u;                      // parts stay 1024-byte aligned
+      P.b_part_bytes = 3 * BN * BK * 2;                               // the three dx taps of this filter row
+      P.stage_bytes = P.nparts * (P.a_part_bytes + P.b_part_bytes);
+      P.stage_tx = P.nparts * (a_box + P.b_part_bytes);
+      stages = (SMEM_LIMIT - 2048 - 1024 - STAGE_BYTES) / static_cast<int>(P.stage_bytes);
+      if (stages > MAX_STAGES) stages = MAX_STAGES;
+      if (stages < 2) return -3;
+      P.num_stages = stages;
+    }
   } else {
     if ((rc = mk(&mAhi, p.a, p.a.hi, a_rows, BM))) return rc;
     if (P.nparts == 2) { if ((rc = mk(&mAlo, p.a, p.a.lo, a_rows, BM))) return rc; }
@@ -745,7 +797,7 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   // tiles per split: single tiles, or pairs of m-tiles (an odd last m-tile gets an idle partner)
   const int num_tiles = P.cluster == 2 ? ((P.tiles_m + 1) / 2) * P.tiles_n : P.tiles_m * P.tiles_n;
   const int cta_per_item = P.cluster;
-  const int nkb = (p.K + BK - 1) / BK;
+  const int nkb = (P.conv == 2) ? 3 * P.conv_kb_per_tap : (p.K + BK - 1) / BK;
   // split-K: only for plain fp32-output GEMMs (weight gradients) whose tile count leaves most SMs idle
   P.splits = 1; P.kb_per_split = nkb; P.part = nullptr;
   const bool plain = p.epi.out_f32 && !p.epi.bias && !p.epi.addend && !p.epi.addend_hi && !p.epi.out_hi &&
