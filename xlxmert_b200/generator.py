@@ -159,7 +159,11 @@ class B200Generator(nn.Module):
             blocks = [torch.empty(B, 16 << i, 16 << i, 32, device=dev) for i in range(N_BLOCKS)]
             blocks_arr = (C.c_void_p * N_BLOCKS)(*[t.data_ptr() for t in blocks])
         nws = lib.xlx_generator_workspace_bytes(B)
-        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        # one grow-only workspace per module: a fresh multi-GB request per call fragments the caching allocator until it
+        # falls back to cudaMalloc (tens of ms); stream-ordered reuse is safe for this inference-only module
+        ws = self.__dict__.get("_ws")
+        if ws is None or ws.numel() < nws or ws.device != dev:
+            ws = self.__dict__["_ws"] = torch.empty(nws, dtype=torch.uint8, device=dev)
         rc = lib.xlx_generator_fwd(parr, prep.data_ptr(), B, emb.data_ptr(), noise_arr, img.data_ptr(),
                                    None if pre is None else pre.data_ptr(), blocks_arr, ws.data_ptr(), nws, self.passes,
                                    stream)

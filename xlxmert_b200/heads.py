@@ -83,7 +83,13 @@ class _FusedHead:
         h2 = hidden.reshape(-1, d.hidden).contiguous().float()
         M, dev = h2.shape[0], h2.device
         prep = self.prepared(params)
-        ws, nws = self.workspace(M, dev)
+        if labels is None:      # inference (sampler loop): one grow-only workspace, stream-ordered reuse
+            nws = self.fn("workspace_bytes")(C.byref(self.cdims), self.classes, M)
+            ws = getattr(self, "_ws_infer", None)
+            if ws is None or ws.numel() < nws or ws.device != dev:
+                ws = self._ws_infer = torch.empty(nws, dtype=torch.uint8, device=dev)
+        else:                   # training: the workspace carries the saved activations to the backward
+            ws, nws = self.workspace(M, dev)
         out = dict(ws=ws, nws=nws, prep=prep, M=M, feat=None, logits=None, loss=None, pred_prob=None, pred_id=None)
         if labels is not None:
             labels = labels.reshape(-1).contiguous()
