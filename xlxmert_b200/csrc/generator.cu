@@ -22,6 +22,7 @@ using namespace xlx;
 namespace {
 
 constexpr int CH = 32;          // width of every block (resolution_channels = min(·, base_dim), layers.py:161-175)
+constexpr int RES_PACK = 4;     // pixels per GEMM row of the 1×1 shortcut convolution (see Prep::res)
 constexpr int HID = 128;        // SPADE hidden width (layers.py:23)
 constexpr int EMB = 2048, CODE = 256, NBLK = 5, R0 = 8, RGB_LD = 16;
 constexpr int N_PARAMS = 10 + NBLK * 26 + NBLK * 2;
@@ -77,16 +78,20 @@ __global__ void sigma_inv_kernel(const float* __restrict__ w, const float* __res
 // scaled by *scale (nullable), as split bf16.  For grouped convs col0 is chosen per output channel:
 // col0 = (co / co_per_group) * Ci.
 __global__ void prep_conv_kernel(const float* __restrict__ w, const float* __restrict__ scale, int Co, int Ci, int taps,
-                                 int ctot, int co_per_group, int row0, int ld, bf16* hi, bf16* lo) {
+                                 int ctot, int co_per_group, int row0, int ld, bf16* hi, bf16* lo, int col_base) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Co * Ci * taps) return;
   const int tap = i % taps, ci = (i / taps) % Ci, co = i / (taps * Ci);
-  const int col0 = co_per_group ? (co / co_per_group) * Ci : 0;
+  const int col0 = col_base + (co_per_group ? (co / co_per_group) * Ci : 0);
   const float v = w[i] * (scale ? *scale : 1.0f);
   bf16 h, l;
   split_bf16(v, h, l);
   const size_t d = static_cast<size_t>(row0 + co) * ld + static_cast<size_t>(tap) * ctot + col0 + ci;
   hi[d] = h; lo[d] = l;
+}
+__global__ void repeat_bias_kernel(const float* b, int n, float* dst, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) dst[i] = b[i % n];
 }
 __global__ void concat_bias_kernel(const float* a, int na, const float* b, int nb, float* dst, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -256,7 +261,12 @@ struct Prep {
   Split bott, init;          // [256, 2048]; [64, 9·256] (rows 0-31 learned_init, 32-63 style_init)
   float* init_bias;          // [64]
   SpadeW sp[NBLK][2];
-  Split conv1[NBLK], conv2[NBLK], res[NBLK], rgb[NBLK];   // [64(pad), 288], [64, 288], [64, 32], [64, 288]
+  Split conv1[NBLK], conv2[NBLK], rgb[NBLK];   // [64(pad), 288], [64, 288], [64, 288]
+  // 1×1 shortcut convolution (layers.py:88-91) as a plain GEMM over groups of RES_PACK pixels: the weight is stored
+  // block-diagonally, [RES_PACK·32, RES_PACK·32], so that [M, 32]·Wᵀ becomes [M/4, 128]·W_bdᵀ on the same memory —
+  // four times fewer, four times deeper tiles (a K = 32 tile is pure pipeline latency)
+  Split res[NBLK];
+  float* res_bias[NBLK];     // the bias repeated RES_PACK times
   float* sig;                // 1/σ per spectrally normalised conv: 2 + 3·NBLK
   float* rgb_bias[NBLK];     // [RGB_LD]
   size_t bytes;
@@ -275,7 +285,8 @@ Prep prep_layout(void* base) {
     }
     p.conv1[i] = b.split(static_cast<size_t>(64) * 9 * CH);
     p.conv2[i] = b.split(static_cast<size_t>(64) * 9 * CH);
-    p.res[i] = b.split(static_cast<size_t>(64) * CH);
+    p.res[i] = b.split(static_cast<size_t>(RES_PACK * CH) * RES_PACK * CH);
+    p.res_bias[i] = b.f32(RES_PACK * CH);
     p.rgb[i] = b.split(static_cast<size_t>(64) * 9 * CH);
     p.rgb_bias[i] = b.f32(RGB_LD);
   }
@@ -355,9 +366,10 @@ int32_t xlx_generator_prepare(const float* const* P, void* prep, void* stream) {
   Prep p = prep_layout(prep);
   XLX_CUDA(cudaMemsetAsync(prep, 0, p.bytes - 256, st));     // padded rows / off-group blocks stay zero
   auto prep_w = [&](const float* w, const float* scale, int Co, int Ci, int taps, int ctot, int cpg, int row0,
-                    Split dst) -> int {
+                    Split dst, int col_base = 0) -> int {
     const int n = Co * Ci * taps;
-    prep_conv_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, scale, Co, Ci, taps, ctot, cpg, row0, taps * ctot, dst.hi, dst.lo);
+    prep_conv_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, scale, Co, Ci, taps, ctot, cpg, row0, taps * ctot, dst.hi, dst.lo,
+                                                       col_base);
     return krc();
   };
   auto sigma = [&](int slot, int rows, int cols, float* out) -> int {
@@ -388,7 +400,10 @@ int32_t xlx_generator_prepare(const float* const* P, void* prep, void* stream) {
     XLX_TRY(sigma(s + 20, CH, CH, sg + 2));
     XLX_TRY(prep_w(P[s + 12], sg + 0, CH, CH, 9, CH, 0, 0, p.conv1[i]));
     XLX_TRY(prep_w(P[s + 16], sg + 1, CH, CH, 9, CH, 0, 0, p.conv2[i]));
-    XLX_TRY(prep_w(P[s + 20], sg + 2, CH, CH, 1, CH, 0, 0, p.res[i]));
+    for (int g = 0; g < RES_PACK; ++g)
+      XLX_TRY(prep_w(P[s + 20], sg + 2, CH, CH, 1, RES_PACK * CH, 0, g * CH, p.res[i], g * CH));
+    repeat_bias_kernel<<<1, RES_PACK * CH, 0, st>>>(P[s + 21], CH, p.res_bias[i], RES_PACK * CH);
+    XLX_TRY(krc());
     XLX_TRY(prep_w(P[rgb_slot(i)], nullptr, 3, CH, 9, CH, 0, 0, p.rgb[i]));
     concat_bias_kernel<<<1, 64, 0, st>>>(P[rgb_slot(i) + 1], 3, nullptr, 0, p.rgb_bias[i], RGB_LD);
     XLX_TRY(krc());
@@ -477,10 +492,11 @@ int32_t xlx_generator_fwd(const float* const* P, const void* prep, int32_t B, co
       GemmEpilogue e;
       e.bias = P[s + 17]; e.out_f32 = of; e.ld_out = CH;
       XLX_TRY(conv(passes, st, w.a, B, R2, CH, 9, p.conv2[i], 64, CH, e));
-      GemmEpilogue r;
-      r.bias = P[s + 21]; r.flags = EPI_ACCUM; r.out_f32 = of; r.ld_out = CH;
-      r.out_hi = w.os.hi; r.out_lo = w.os.lo; r.ld_split = CH;
-      XLX_TRY(conv(passes, st, w.xu, B, R2, CH, 1, p.res[i], 64, CH, r));
+      GemmEpilogue r;   // shortcut: RES_PACK pixels per GEMM row, block-diagonal weight (see Prep::res)
+      const int PK = RES_PACK * CH;
+      r.bias = p.res_bias[i]; r.flags = EPI_ACCUM; r.out_f32 = of; r.ld_out = PK;
+      r.out_hi = w.os.hi; r.out_lo = w.os.lo; r.ld_split = PK;
+      XLX_TRY(gemm_linear(passes, st, w.xu, static_cast<int>(npix2 / RES_PACK), PK, p.res[i], PK, r));
     }
     if (block_out && block_out[i])
       XLX_CUDA(cudaMemcpyAsync(block_out[i], of, npix2 * CH * 4, cudaMemcpyDeviceToDevice, st));
