@@ -46,6 +46,7 @@ struct KParams {
   // image row segment of 130 pixels, and the three dx taps are three UMMA descriptor views of it shifted by one pixel
   // (64 bytes) each — every activation byte crosses L2→SM 3 times instead of 9.
   uint32_t stage_tx;   // bytes one stage receives by TMA (= stage_bytes except in halo mode, whose A box is 130 rows)
+  int conv_tapbox;     // halo mode: the B maps are rank-3 (channel, row, dx) and one box fetches all three dx taps
   int cluster;         // 1, or 2 = CTA pairs on adjacent m-tiles sharing the B tile by TMA multicast
   int tiles_per_split; // tiles (cluster = 1) or tile pairs (cluster = 2) per split
   int num_items;       // work items of the launch: tiles_per_split · splits
@@ -275,9 +276,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
               // k-block → (filter row, channel block): one haloed row segment [x0 − 1, x0 + 129) and the 3 weight taps
               const int dyi = kb / P.conv_kb_per_tap, cb = kb % P.conv_kb_per_tap;
               tma_load_4d(dA, ma, full, cb * BK, x0 - 1, y0 + dyi - 1, img);
+              if (P.conv_tapbox) {   // one request for the three dx taps (the TMA unit is request-rate bound here)
+                tma_load_3d(dB, mb, full, (dyi * 3 * P.conv_kb_per_tap + cb) * BK, n0, 0);
+              } else {
 #pragma unroll
-              for (int dxi = 0; dxi < 3; ++dxi)
-                tma_load_2d(dB + dxi * (P.BN * BK * 2), mb, full, ((dyi * 3 + dxi) * P.conv_kb_per_tap + cb) * BK, n0);
+                for (int dxi = 0; dxi < 3; ++dxi)
+                  tma_load_2d(dB + dxi * (P.BN * BK * 2), mb, full, ((dyi * 3 + dxi) * P.conv_kb_per_tap + cb) * BK, n0);
+              }
               continue;
             } else if (!A_MN && P.conv) {
               // k-block → (filter tap, channel offset); the box is the activation tensor shifted by the tap
@@ -607,6 +612,22 @@ int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, 
   return 0;
 }
 
+// Weight matrix [rows, kext] (K index = tap·C + c) seen as rank 3 (c, row, dx) with the dx axis striding by C elements:
+// one box (32, box_rows, 3) lands in shared memory as three consecutive [box_rows, 32] tap matrices.
+int make_map_taps(CUtensorMap* out, const void* ptr, uint64_t kext, uint64_t rows, uint64_t ld, uint64_t tap_stride,
+                  uint32_t box_rows, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -10;
+  cuuint64_t gdim[3] = {kext, rows, 3};
+  cuuint64_t gstride[2] = {ld * 2, tap_stride * 2};
+  cuuint32_t box[3] = {32, box_rows, 3};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -11;
+}
+
 // NHWC bf16 tensor [B, H, W, C] as a rank-4 tensor map (C innermost) with box (bc, bw, bh, bb).
 struct Map4Key {
   const void* ptr;
@@ -794,6 +815,19 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   if ((rc = mk(&mBhi, p.b, p.b.hi, b_rows, b_box_rows))) return rc;
   if (P.nparts == 2) { if ((rc = mk(&mBlo, p.b, p.b.lo, b_rows, b_box_rows))) return rc; }
   else mBlo = mBhi;
+  P.conv_tapbox = 0;
+  static const int tapbox_on = env_int("XLX_CONV_TAPBOX", 1);
+  if (P.conv == 2 && tapbox_on) {
+    const uint64_t kext = p.b.kext ? p.b.kext : p.K, C = static_cast<uint64_t>(p.conv.C);
+    CUtensorMap t_hi, t_lo;
+    int trc = make_map_taps(&t_hi, p.b.hi, kext, b_rows, p.b.ld, C, BN, swzK);
+    if (!trc && P.nparts == 2) trc = make_map_taps(&t_lo, p.b.lo, kext, b_rows, p.b.ld, C, BN, swzK);
+    if (!trc) {       // (the driver rejects the non-monotonic strides → keep the three 2-D requests)
+      mBhi = t_hi;
+      mBlo = P.nparts == 2 ? t_lo : t_hi;
+      P.conv_tapbox = 1;
+    }
+  }
   // tiles per split: single tiles, or pairs of m-tiles (an odd last m-tile gets an idle partner)
   const int num_tiles = P.cluster == 2 ? ((P.tiles_m + 1) / 2) * P.tiles_n : P.tiles_m * P.tiles_n;
   const int cta_per_item = P.cluster;

@@ -118,6 +118,12 @@ __device__ __forceinline__ void tma_prefetch_2d(const void* map, int c0, int c1)
 
 // 4-D tiled load (implicit-GEMM convolution over an NHWC tensor: coordinates = channel, x, y, image).  Coordinates
 // may be negative / past the end: those elements are zero-filled, which is exactly the conv's zero padding.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
