@@ -102,20 +102,39 @@ __global__ void concat_bias_kernel(const float* a, int na, const float* b, int n
 // x: [B, HW, ld] fp32 (first CH channels used).  acc[b][c][0..1] += (Σx, Σx²) in fp64.  grid (chunks, B), 256 thr.
 __global__ void __launch_bounds__(256)
 in_stats_kernel(const float* __restrict__ x, int ld, int HW, double* acc) {
-  __shared__ double s1[8][CH], s2[8][CH];
-  const int c = threadIdx.x & 31, lane = threadIdx.x >> 5, b = blockIdx.y;
-  const float* xb = x + static_cast<size_t>(b) * HW * ld;
-  double a1 = 0.0, a2 = 0.0;
-  for (int p = blockIdx.x * 8 + lane; p < HW; p += gridDim.x * 8) {
-    const double v = static_cast<double>(__ldg(xb + static_cast<size_t>(p) * ld + c));
-    a1 += v; a2 += v * v;
+  // thread = (pixel lane, channel quad): 16-byte loads, two pixels in flight per thread
+  __shared__ double s1[32][CH + 1], s2[32][CH + 1];
+  const int c4 = threadIdx.x & 7, lane = threadIdx.x >> 3, b = blockIdx.y;
+  const float* xb = x + static_cast<size_t>(b) * HW * ld + c4 * 4;
+  double a1[4] = {0.0, 0.0, 0.0, 0.0}, a2[4] = {0.0, 0.0, 0.0, 0.0};
+  const int step = gridDim.x * 32;
+  int p = blockIdx.x * 32 + lane;
+  for (; p + step < HW; p += 2 * step) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(xb + static_cast<size_t>(p) * ld));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + static_cast<size_t>(p + step) * ld));
+    const float uf[4] = {u.x, u.y, u.z, u.w}, vf[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double du = uf[k], dv = vf[k];
+      a1[k] += du; a2[k] += du * du;
+      a1[k] += dv; a2[k] += dv * dv;
+    }
   }
-  s1[lane][c] = a1; s2[lane][c] = a2;
+  for (; p < HW; p += step) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(xb + static_cast<size_t>(p) * ld));
+    const float uf[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const double du = uf[k]; a1[k] += du; a2[k] += du * du; }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { s1[lane][c4 * 4 + k] = a1[k]; s2[lane][c4 * 4 + k] = a2[k]; }
   __syncthreads();
-  if (lane == 0) {
-    for (int i = 1; i < 8; ++i) { a1 += s1[i][c]; a2 += s2[i][c]; }
-    atomicAdd(acc + (static_cast<size_t>(b) * CH + c) * 2, a1);
-    atomicAdd(acc + (static_cast<size_t>(b) * CH + c) * 2 + 1, a2);
+  if (threadIdx.x < CH) {
+    const int c = threadIdx.x;
+    double t1 = 0.0, t2 = 0.0;
+    for (int i = 0; i < 32; ++i) { t1 += s1[i][c]; t2 += s2[i][c]; }
+    atomicAdd(acc + (static_cast<size_t>(b) * CH + c) * 2, t1);
+    atomicAdd(acc + (static_cast<size_t>(b) * CH + c) * 2 + 1, t2);
   }
 }
 // InstanceNorm2d(affine=False): biased variance over H×W, eps 1e-5 (layers.py:16)
@@ -181,11 +200,14 @@ __global__ void spade_act_kernel(const float* __restrict__ x, int ldx, const flo
                                  size_t npix_out, bf16* hi, bf16* lo) {
   const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (t >= npix_out * (CH / 4)) return;
-  const int c4 = t % (CH / 4);
-  const size_t p = t / (CH / 4);
-  const int Ro = R * up;
-  const int ox = p % Ro, oy = (p / Ro) % Ro;
-  const size_t b = p / (static_cast<size_t>(Ro) * Ro);
+  // every extent is a power of two (CH/4 = 8, Ro = 16…256): shifts and masks instead of 64-bit divisions, which used
+  // to cost more than the memory traffic of this kernel
+  static_assert(CH / 4 == 8, "index math below assumes 8 channel quads per pixel");
+  const int c4 = static_cast<int>(t & 7);
+  const size_t p = t >> 3;
+  const int Ro = R * up, lg = 31 - __clz(Ro);
+  const int ox = static_cast<int>(p & (Ro - 1)), oy = static_cast<int>((p >> lg) & (Ro - 1));
+  const size_t b = p >> (2 * lg);
   float4 mu = make_float4(0, 0, 0, 0), rs = make_float4(1, 1, 1, 1);
   if (gb) {
     mu = __ldg(reinterpret_cast<const float4*>(mean + b * CH + c4 * 4));
@@ -221,8 +243,11 @@ __global__ void rgb_accumulate_kernel(const float* __restrict__ rgb, int r, int 
                                       float* acc, float* img, float* pre_tanh) {
   const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (t >= n) return;
-  const int ox = t % T, oy = (t / T) % T, c = (t / (static_cast<size_t>(T) * T)) % 3;
-  const size_t b = t / (static_cast<size_t>(T) * T * 3);
+  const int lg = 31 - __clz(T);                       // T is a power of two (256)
+  const int ox = static_cast<int>(t & (T - 1)), oy = static_cast<int>((t >> lg) & (T - 1));
+  const unsigned plane = static_cast<unsigned>(t >> (2 * lg));   // b·3 + c
+  const int c = plane % 3u;
+  const size_t b = plane / 3u;
   const float* rb = rgb + b * r * r * RGB_LD + c;
   float v;
   if (r == T) {
