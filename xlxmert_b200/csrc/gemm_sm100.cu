@@ -530,8 +530,9 @@ __global__ void splitk_reduce_kernel(const float4* __restrict__ part, int splits
       const float4 b = __ldg(part + s * mn4 + i);
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
-    const size_t m = i / n4, c = i % n4;
-    float4* dst = reinterpret_cast<float4*>(out + m * ld_out) + c;
+    // the partial-sum workspace holds < 2^32 float4s: 32-bit division (the 64-bit one costs ~10× more)
+    const unsigned i32 = static_cast<unsigned>(i), m = i32 / static_cast<unsigned>(n4), c = i32 - m * n4;
+    float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(m) * ld_out) + c;
     if (accumulate) {
       const float4 o = *dst;
       a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;

@@ -153,10 +153,11 @@ __global__ void in_finish_kernel(const double* __restrict__ acc, int n, int HW, 
 __global__ void resize_split_kernel(const float* __restrict__ x, int ld, int Hi, int Ho, size_t npix, bf16* hi, bf16* lo) {
   const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (t >= npix * (CH / 4)) return;
-  const int c4 = t % (CH / 4);
-  const size_t p = t / (CH / 4);
-  const int ox = p % Ho, oy = (p / Ho) % Ho;
-  const size_t b = p / (static_cast<size_t>(Ho) * Ho);
+  const int c4 = static_cast<int>(t & 7);             // CH/4 = 8 and Ho is a power of two: no 64-bit divisions
+  const size_t p = t >> 3;
+  const int lg = 31 - __clz(Ho);
+  const int ox = static_cast<int>(p & (Ho - 1)), oy = static_cast<int>((p >> lg) & (Ho - 1));
+  const size_t b = p >> (2 * lg);
   const float scale = static_cast<float>(Hi) / static_cast<float>(Ho);
   int y0, y1, x0, x1;
   float ly0, ly1, lx0, lx1;
