@@ -72,6 +72,16 @@ def main():
     out["fused_clip_adamw"] = {"ms": ms, "params_with_grad": n_par, "algorithmic_bytes": 32 * n_par,
                                "achieved_GBps": 32 * n_par / ms / 1e6,
                                "note": "28 B/param AdamW (read g,p,m,v; write p,m,v) + 4 B/param for the norm pass"}
+    # whole training iteration as lxmert_pretrain.py:343-364 runs it: forward, backward, clip, AdamW (weights really
+    # change every step, so the encoder re-splits them)
+    fstep = step("vis_mask")
+
+    def full_iteration():
+        fstep()
+        opt.step(max_grad_norm=1.0)
+    ms = timed(full_iteration, 5)
+    out["pretrain_vis_mask_B256_with_optimizer"] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3}
+    fstep()
     ref_params = [p for p in model.parameters() if p.grad is not None]
     topt = torch.optim.AdamW(ref_params, lr=1e-4, eps=1e-6, weight_decay=0.01)
 
