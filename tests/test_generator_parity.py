@@ -66,3 +66,18 @@ def test_generator_rejects_other_architectures_and_cpu():
     G = B200Generator()
     with pytest.raises(RuntimeError):
         G(torch.zeros(1, 2048, 8, 8))
+
+
+def test_single_pass_bf16_mode_tracks_the_default_mode():
+    """``passes=1`` (plain bf16 operands, hi parts only) runs the same kernels with one operand part per stage — the
+    row-halo convolution and its rank-3 weight box included.  Not a parity mode: it must stay close, not equal."""
+    from xlxmert_b200.generator import B200Generator
+    g, G, code, B = _setup()
+    G1 = B200Generator(passes=1)
+    G1.load_state_dict(G.state_dict(), strict=True)
+    G1 = G1.cuda().eval()
+    ref, pre_ref, _ = G(code.view(B, 8, 8, 2048), train=False, return_intermediates=True)
+    out, pre, _ = G1(code.view(B, 8, 8, 2048), train=False, return_intermediates=True)
+    assert torch.isfinite(out).all()
+    assert rel_err(pre.cpu(), pre_ref.cpu()) < 5e-2
+    assert float((out - ref).abs().mean()) < 1e-2
