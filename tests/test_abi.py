@@ -109,3 +109,41 @@ def test_backward_stage_ranges_tile_the_gradient_arena():
             assert o0 + n0 == o1
         off, n = C.c_int64(), C.c_int64()
         assert lib.xlx_encoder_grad_stage_range(C.byref(cd), 3, C.byref(off), C.byref(n)) == -25
+
+
+def test_stage_mask_ranges_and_host_side_argument_checks():
+    """Host logic that needs no GPU: the module-level union of backward-stage ranges (what the data-parallel backward
+    all-reduces after each call), the size queries of the late additions, and argument errors that must be raised
+    before anything touches a device."""
+    import numpy as np
+    from xlxmert_b200 import _lib
+    from xlxmert_b200.config import TINY_DIMS
+    from xlxmert_b200.encoder import B200LxmertEncoder, _BWD_STAGES
+    from xlxmert_b200.kmeans import B200IndexFlatL2
+    lib = _lib.load()
+    enc = B200LxmertEncoder(dims=TINY_DIMS)
+    total = lib.xlx_encoder_grad_elems(C.byref(enc._cdims))
+    assert _BWD_STAGES == (1, 14)
+    (o1, n1), (o2, n2) = enc._stage_range(1), enc._stage_range(14)
+    assert o2 == 0 and o2 + n2 == o1 and o1 + n1 == total            # [everything below | cross-modality layers]
+    assert enc._stage_range(15) == (0, total)
+    with pytest.raises(ValueError):
+        enc._stage_range(1 | 4)                                       # cross + language: not adjacent in the arena
+    # parameter list cache: same objects, rebuilt after a parameter is replaced inside a layer
+    p0 = enc._param_list()
+    assert enc._param_list() is p0
+    lin = enc.layer[0].attention.self.query
+    lin.weight = torch.nn.Parameter(lin.weight.detach().clone())
+    p1 = enc._param_list()
+    assert p1 is not p0 and any(a is lin.weight for a in p1)
+    # k-means index: faiss call shape, loud failures
+    assert lib.xlx_kmeans_prep_bytes(2048, 10000) > 2 * 10000 * 2048 * 2
+    assert lib.xlx_kmeans_prep_bytes(2047, 10000) == 0 and lib.xlx_kmeans_workspace_bytes(2048, 10000, 0) == 0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B200IndexFlatL2(8, device="cpu").add(np.zeros((4, 8), np.float32))
+    with pytest.raises(ValueError):
+        B200IndexFlatL2(8).add(np.zeros((4, 9), np.float32))
+    with pytest.raises(RuntimeError, match="before add"):
+        B200IndexFlatL2(8).search(np.zeros((1, 8), np.float32), 1)
+    with pytest.raises(NotImplementedError):
+        B200IndexFlatL2(8).search(np.zeros((1, 8), np.float32), 5)
