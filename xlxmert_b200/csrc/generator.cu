@@ -238,6 +238,63 @@ __global__ void spade_act_kernel(const float* __restrict__ x, int ldx, const flo
   store_split(hi, lo, p * CH + c4 * 4, o);
 }
 
+// ×2 variant of spade_act_kernel: a thread owns one SOURCE pixel (4 channels) and produces its 2 × 2 output pixels from
+// the 3 × 3 source neighbourhood — every source value (and its SPADE modulation) is evaluated 2.25× instead of 4× per
+// output and the index arithmetic is paid once per four outputs.  Same operation order per output as the generic
+// kernel: output 2j / 2j+1 blends sources (j−1, j) / (j, j+1) with bilinear_src's weights; at the borders the clamped
+// neighbour carries weight 0 or duplicates the centre, which is exactly what upsample_bilinear2d computes.
+__global__ void __launch_bounds__(256)
+spade_up2_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
+                 const float* __restrict__ gb, const float* __restrict__ noise, const float* __restrict__ noise_w, int R,
+                 size_t npix_src, bf16* hi, bf16* lo) {
+  const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (t >= npix_src * (CH / 4)) return;
+  const int c4 = static_cast<int>(t & 7);
+  const size_t p = t >> 3;
+  const int lg = 31 - __clz(R);
+  const int k = static_cast<int>(p & (R - 1)), j = static_cast<int>((p >> lg) & (R - 1));
+  const size_t b = p >> (2 * lg);
+  float4 mu = make_float4(0, 0, 0, 0), rs = make_float4(1, 1, 1, 1);
+  if (gb) {
+    mu = __ldg(reinterpret_cast<const float4*>(mean + b * CH + c4 * 4));
+    rs = __ldg(reinterpret_cast<const float4*>(rstd + b * CH + c4 * 4));
+  }
+  const float nw = (noise && noise_w) ? __ldg(noise_w) : 0.f;
+  const size_t base = b * R * R;
+  auto fetch = [&](int y, int xx) -> float4 {
+    const size_t pix = base + static_cast<size_t>(y) * R + xx;
+    if (gb) return spade_pixel(x, ldx, gb, pix, c4, mu, rs, noise, nw);
+    return __ldg(reinterpret_cast<const float4*>(x + pix * ldx + c4 * 4));
+  };
+  const int ys[3] = {j > 0 ? j - 1 : 0, j, j < R - 1 ? j + 1 : R - 1};
+  const int xs[3] = {k > 0 ? k - 1 : 0, k, k < R - 1 ? k + 1 : R - 1};
+  float4 g[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[a][c] = fetch(ys[a], xs[c]);
+  const int Ro = 2 * R;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    int i0, i1;
+    float ly0, ly1;
+    bilinear_src(2 * j + dy, 0.5f, R, i0, i1, ly0, ly1);
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      float lx0, lx1;
+      bilinear_src(2 * k + dx, 0.5f, R, i0, i1, lx0, lx1);
+      const float4 v00 = g[dy][dx], v01 = g[dy][dx + 1], v10 = g[dy + 1][dx], v11 = g[dy + 1][dx + 1];
+      float4 o;
+      o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+      o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+      o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+      o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+      const size_t op = (b * Ro + static_cast<size_t>(2 * j + dy)) * Ro + (2 * k + dx);
+      store_split(hi, lo, op * CH + c4 * 4, o);
+    }
+  }
+}
+
 // ToRGB tail (layers.py:126-132, 241-251): img[b, c, :, :] (+)= bilinear(rgb[b, :, :, c] → T×T); the last block
 // applies tanh and optionally exports the pre-tanh sum.  rgb: [B, r, r, RGB_LD] fp32; img NCHW [B, 3, T, T].
 __global__ void rgb_accumulate_kernel(const float* __restrict__ rgb, int r, int T, size_t n, int first, int last,
@@ -492,12 +549,13 @@ int32_t xlx_generator_fwd(const float* const* P, const void* prep, int32_t B, co
     // cbn1 → noise1 → LeakyReLU → ×2 bilinear (layers.py:96-101)
     XLX_TRY(instance_stats(x, ldx, B, R * R, w, st));
     XLX_TRY(spade_params(i, 0, i));
-    spade_act_kernel<<<blocks_for(npix2 * (CH / 4)), 256, 0, st>>>(x, ldx, w.mean, w.rstd, w.gb, n1, P[s + 24], R, 2,
-                                                                   npix2, w.a.hi, w.a.lo);
+    const size_t npix1 = npix2 / 4;
+    spade_up2_kernel<<<blocks_for(npix1 * (CH / 4)), 256, 0, st>>>(x, ldx, w.mean, w.rstd, w.gb, n1, P[s + 24], R, npix1,
+                                                                   w.a.hi, w.a.lo);
     XLX_TRY(krc());
     // residual branch input: ×2 bilinear of x (layers.py:88-91)
-    spade_act_kernel<<<blocks_for(npix2 * (CH / 4)), 256, 0, st>>>(x, ldx, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                                   R, 2, npix2, w.xu.hi, w.xu.lo);
+    spade_up2_kernel<<<blocks_for(npix1 * (CH / 4)), 256, 0, st>>>(x, ldx, nullptr, nullptr, nullptr, nullptr, nullptr, R,
+                                                                   npix1, w.xu.hi, w.xu.lo);
     XLX_TRY(krc());
     // conv1 (spectral norm folded into the prepared weight)
     {
