@@ -13,7 +13,7 @@ Works with any ``torch.distributed`` backend (NCCL on the B200 box, gloo in the 
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist

@@ -8,7 +8,6 @@ MaskLM + ObjPredict + Matched, ``--visualLosses obj``; the QA head is not part o
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Optional
 
 import numpy as np
