@@ -6,6 +6,8 @@ PARITY UNPINNED: faiss is a third-party dependency that is not vendored in the r
 assignments.  This restates faiss's published algorithm for the flat L2 index (``knn_L2sqr`` BLAS path: distances as
 ‖x‖² + ‖c‖² − 2·x·cᵀ from an SGEMM, negative round-off clamped to 0, the smallest distance kept, lowest index on
 ties) in fp32, plus an fp64 brute-force version used to tell real disagreements from near-ties.
+tests/test_kmeans.py cross-checks both functions against scikit-learn's pairwise_distances_argmin_min — an independent
+implementation of the same definition, not the reference's dependency, so the header stays "unpinned".
 Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.
 """
 import numpy as np

@@ -30,6 +30,20 @@ def test_oracle_fp32_agrees_with_fp64():
     assert np.array_equal(I2[:, 0], np.arange(5)) and (D2 >= 0).all() and (D2 < 1e-3).all()
 
 
+def test_oracle_agrees_with_scikit_learn():
+    """faiss is absent, so the restatement is cross-checked against an independent implementation of the same
+    definition (nearest centroid under squared L2): scikit-learn's pairwise_distances_argmin_min."""
+    sk = pytest.importorskip("sklearn.metrics")
+    x, c = _data(500, 211, 96, 7)
+    idx, dist = sk.pairwise_distances_argmin_min(x.astype(np.float64), c.astype(np.float64), metric="sqeuclidean")
+    best, i64, margin = KO.search_l2_fp64(x, c)
+    assert np.array_equal(i64, idx)
+    assert np.allclose(best, dist, rtol=1e-9, atol=1e-9)
+    D, I = KO.search_l2_fp32(x, c)
+    safe = margin > 1e-3
+    assert np.array_equal(I[safe, 0], idx[safe]) and np.allclose(D[:, 0], dist, rtol=1e-4, atol=1e-3)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("N,K,d,chunk", [(1, 1, 32, 64), (257, 97, 64, 100), (1000, 1001, 256, 4096),
                                           (4096, 10000, 2048, 1536)])
