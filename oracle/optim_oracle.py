@@ -8,8 +8,9 @@ CPU restatement of the optimiser half of the reference's training step
 * ``transformers.optimization.AdamW.step`` as published in transformers **4.1.1** (the version pinned in
   ``/root/reference/requirements.txt:11``; the class was removed from the 5.5.0 installed here, so its source is not
   available in this container and this restatement follows the published algorithm — parity for this row is
-  therefore "unpinned" by reference-run goldens; ``tests/test_optim.py`` additionally cross-checks the decay-free
-  case against ``torch.optim.Adam``-style arithmetic computed independently).
+  therefore "unpinned" by reference-run goldens; ``tests/test_optim_oracle.py`` cross-checks it on CPU against
+  ``torch.nn.utils.clip_grad_norm_`` and against ``torch.optim.AdamW`` where the two algorithms coincide (eps = 0, no
+  weight decay), plus a hand-computed step for the decay placement).
 
       exp_avg    ← β₁·exp_avg + (1 − β₁)·g
       exp_avg_sq ← β₂·exp_avg_sq + (1 − β₂)·g²
