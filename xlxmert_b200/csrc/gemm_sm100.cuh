@@ -7,10 +7,14 @@
 // GEMM to ≈ 2^-16 relative (needed for the reference's fp32 parity bar);
 // passes = 1 uses the hi parts only (plain bf16 tensor-core GEMM).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + UMMA issuer, warps 2-5 = epilogue
-// (TMEM → registers → global).  Shared memory is a ring of stages filled by TMA
-// (cp.async.bulk.tensor, hardware swizzle) and drained by tcgen05.mma; the accumulator is double
-// buffered in TMEM (2 × BN fp32 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+// Roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM owner + UMMA issuer, warps 2-17 = epilogue
+// (TMEM → registers → 64-byte-swizzled shared-memory transpose → coalesced global traffic or a TMA store).  Shared
+// memory is a ring of stages filled by TMA (cp.async.bulk.tensor, hardware swizzle) and drained by tcgen05.mma; the
+// accumulator is double buffered in TMEM (2 × BN fp32 columns) so the epilogue of tile i overlaps the main loop of
+// tile i+1.  Tiles are 128 × BN (BN ≤ 256) × 32; CTA pairs share the B tile by TMA multicast; weight-gradient
+// shapes split K with a deterministic partial-sum reduce; kernels are launched with programmatic dependent launch.
+// Convolutions run as implicit GEMMs over NHWC activations (ConvGeometry): one 4-D TMA box per filter tap, or — for
+// 3×3 at width ≥ 128 — one haloed row per filter row whose three dx taps are shifted descriptor views ("row halo").
 //
 // This is the workhorse behind every nn.Linear on the hot path (HF modeling_lxmert.py:217-350 Q/K/V,
 // attention output, intermediate, output; lxrt/modeling.py:38-53 cluster head) and their dgrad / wgrad.
