@@ -145,9 +145,9 @@ def golden_pretrain(name, d, B, wseed, bseed):
         head = model.obj_predict_head(o[1], out_keys=["obj", "feat"])
         logits = head["obj"]
         prob, idx = torch.softmax(logits, dim=2).max(dim=2)
-        top2 = logits.topk(2, dim=2).values
+        top2v, top2i = logits.topk(2, dim=2)
         rec.update(head_feat_sub=head["feat"][:, ::8, ::32], head_logits_sub=logits[:, ::8, ::100],
-                   head_argmax=idx, head_maxprob=prob, head_margin=top2[..., 0] - top2[..., 1])
+                   head_argmax=idx, head_maxprob=prob, head_margin=top2v[..., 0] - top2v[..., 1], head_top2=top2i)
 
         # teacher-forced NAR sampling, 4 steps (imggen_model.py:199-243): the masks chosen by the
         # reference run are stored and replayed by the tests (topk tie order is implementation-defined).
@@ -170,10 +170,64 @@ def golden_pretrain(name, d, B, wseed, bseed):
             pl = model.obj_predict_head(lx[1], out_keys=["obj"])["obj"]
             pred_prob, pred_id = torch.softmax(pl, dim=2).max(dim=2)
             code = torch.where(vis_mask.view(B, n_grids, 1).bool(), model.vis_emb(pred_id), code)
+            t2v, t2i = pl.topk(2, dim=2)
             rec[f"nar_mask{i}"] = vis_mask
             rec[f"nar_prob{i}"] = pred_prob
             rec[f"nar_id{i}"] = pred_id
+            rec[f"nar_top2_{i}"] = t2i
+            rec[f"nar_margin{i}"] = t2v[..., 0] - t2v[..., 1]
         rec["nar_code_sub"] = code[:, :, ::64]
+    save(name, rec)
+
+
+def golden_sampler(name, d, B, wseed, bseed, n_steps=4):
+    """Reference NAR sampling loop (imggen_model.py:199-243) at the BASELINE batch size of config 5 (B = 32), run with
+    the reference's ``XLxmertForPretraining`` sub-modules exactly as ``ImggenModel`` chains them; every step's mask,
+    max-probability, arg-max, top-2 ids and top-2 logit margin are stored so that the GPU test can replay the masks
+    (teacher forcing) and assert the arg-max margin-stratified."""
+    model = refshim.build_pretraining_model(
+        num_clusters=d.num_clusters, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, task_qa=False)
+    sd_bert = P.init_state_dict(P.model_param_specs(d), seed=wseed, randomize_ln_bias=True)
+    sd_head = P.init_state_dict(P.objhead_param_specs(d), seed=wseed + 1, randomize_ln_bias=True)
+    table = synth.centroid_table(d)
+    g = torch.Generator().manual_seed(wseed + 3)
+    mask_feat = 0.05 * torch.randn(d.feat_dim, generator=g)
+    model.set_visual_embedding(table.clone())
+    full = {"bert." + k: v for k, v in sd_bert.items()}
+    full.update({"obj_predict_head." + k: v for k, v in sd_head.items() if k != "out_cluster.weight"})
+    full["mask_feat"] = mask_feat
+    missing, unexpected = model.load_state_dict(full, strict=False)
+    assert not unexpected, unexpected
+    model.eval()
+    batch = synth.make_batch(d, B, 20, 64, seed=bseed)
+    ids, vpos = batch["input_ids"], batch["visual_pos"]
+    n_grids = 64
+    rec = dict(meta=np.array([B, 20, 64, wseed, bseed, n_steps]),
+               weights_checksum=torch.tensor(checksum(sd_bert) + checksum(sd_head), dtype=torch.float64))
+    with torch.no_grad():
+        for i in range(n_steps):
+            n_mask = int((n_steps - i) / n_steps * n_grids)
+            if i == 0:
+                vis_mask = torch.ones(B, n_grids).long()
+                code = torch.zeros(B, n_grids, d.feat_dim)
+            else:
+                _, lowest_arg = pred_prob.topk(n_mask, dim=1, largest=False)
+                vis_mask = torch.zeros(B, n_grids).long()
+                vis_mask.scatter_(1, lowest_arg, 1)
+            code = torch.where(vis_mask.view(B, n_grids, 1).bool(),
+                               model.mask_feat.view(1, 1, -1).to(dtype=code.dtype), code)
+            lx = model.bert(input_ids=ids, visual_feats=code, visual_pos=vpos, attention_mask=ids > 0,
+                            return_dict=True)
+            pl = model.obj_predict_head(lx[1], out_keys=["obj"])["obj"]
+            pred_prob, pred_id = torch.softmax(pl, dim=2).max(dim=2)
+            code = torch.where(vis_mask.view(B, n_grids, 1).bool(), model.vis_emb(pred_id), code)
+            t2v, t2i = pl.topk(2, dim=2)
+            rec[f"mask{i}"] = vis_mask.to(torch.uint8)
+            rec[f"prob{i}"] = pred_prob
+            rec[f"id{i}"] = pred_id.to(torch.int32)
+            rec[f"top2_{i}"] = t2i.to(torch.int32)
+            rec[f"margin{i}"] = t2v[..., 0] - t2v[..., 1]
+        rec["code_sub"] = code[:, ::4, ::128]
     save(name, rec)
 
 
@@ -210,6 +264,72 @@ def golden_generator(name, B, wseed, bseed):
     save(name, rec)
 
 
+def golden_generator_batch(name, B, wseed, bseed, keep=(0, 5, 10, 15)):
+    """Reference ``Generator`` at a batch whose 128-pixel GEMM tiles span several images at every stage (B = 16:
+    8x8 stage = 64 pixels per image, 2 images per tile).  Stored: image / pre-tanh sub-samples of every image, block
+    outputs of the images in ``keep``."""
+    layers = refshim.import_generator_layers()
+    G = layers.Generator(base_dim=32, emb_dim=2048, norm_type="spade_in", target_size=256, init_H=8,
+                         init_W=8, SN=True, codebook_dim=256)
+    sd = P.init_generator_state_dict(seed=wseed)
+    G.load_state_dict(sd, strict=True)
+    G.eval()
+    d = DEFAULT_DIMS
+    batch = synth.make_batch(d, B, 20, 64, seed=bseed)
+    code = synth.visual_feats_from(synth.centroid_table(d), batch["cluster_ids"])
+    emb = code.permute(0, 2, 1).reshape(B, 2048, 8, 8)
+    hs, pre = [], []
+    hooks = [rb.register_forward_hook(lambda m, i, o: hs.append(o.detach())) for rb in G.resblocks]
+    hooks.append(G.last.register_forward_hook(lambda m, i, o: pre.append(i[0].detach())))
+    with torch.no_grad():
+        img = G(emb, train=False)
+    for h in hooks:
+        h.remove()
+    keep = [k for k in keep if k < B]
+    rec = dict(meta=np.array([B, wseed, bseed]), keep=np.array(keep),
+               weights_checksum=torch.tensor(checksum(sd), dtype=torch.float64),
+               img_sub=img[:, :, ::8, ::8], pre_tanh_sub=pre[0][:, :, ::8, ::8],
+               img_mean_per_image=img.mean(dim=(1, 2, 3)))
+    for i, h in enumerate(hs):
+        s_ = max(1, h.shape[-1] // 16)
+        rec[f"h{i}_sub"] = h[keep][:, :, ::s_, ::s_]
+    save(name, rec)
+
+
+def golden_generator_noise(name, B, wseed, bseed, noise_seed, noise_weight=0.05):
+    """Reference ``Generator.forward(train=True)`` with NON-ZERO noise weights (a trained G; layers.py:56-62) under a
+    fixed ``torch.manual_seed``: NoiseInjection draws ``image.new_empty(B,1,R,R).normal_()`` from the global CPU
+    generator, noise1 then noise2 of each block in order, so the test re-draws the identical maps from the seed."""
+    layers = refshim.import_generator_layers()
+    G = layers.Generator(base_dim=32, emb_dim=2048, norm_type="spade_in", target_size=256, init_H=8,
+                         init_W=8, SN=True, codebook_dim=256)
+    sd = P.init_generator_state_dict(seed=wseed)
+    for k in sd:
+        if k.endswith("noise1.weight") or k.endswith("noise2.weight"):
+            sd[k] = torch.full_like(sd[k], noise_weight)
+    G.load_state_dict(sd, strict=True)
+    G.eval()
+    d = DEFAULT_DIMS
+    batch = synth.make_batch(d, B, 20, 64, seed=bseed)
+    code = synth.visual_feats_from(synth.centroid_table(d), batch["cluster_ids"])
+    emb = code.permute(0, 2, 1).reshape(B, 2048, 8, 8)
+    hs, pre = [], []
+    hooks = [rb.register_forward_hook(lambda m, i, o: hs.append(o.detach())) for rb in G.resblocks]
+    hooks.append(G.last.register_forward_hook(lambda m, i, o: pre.append(i[0].detach())))
+    torch.manual_seed(noise_seed)
+    with torch.no_grad():
+        img = G(emb, train=True)
+    for h in hooks:
+        h.remove()
+    rec = dict(meta=np.array([B, wseed, bseed, noise_seed]), noise_weight=np.float32(noise_weight),
+               weights_checksum=torch.tensor(checksum(sd), dtype=torch.float64),
+               img_sub=img[:, :, ::4, ::4], pre_tanh_sub=pre[0][:, :, ::4, ::4])
+    for i, h in enumerate(hs):
+        s_ = max(1, h.shape[-1] // 16)
+        rec[f"h{i}_sub"] = h[:, :, ::s_, ::s_]
+    save(name, rec)
+
+
 def save(name, rec):
     os.makedirs(OUT, exist_ok=True)
     arrs = {}
@@ -229,7 +349,7 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     d = DEFAULT_DIMS
-    which = sys.argv[1:] or ["model", "ragged", "pretrain", "generator"]
+    which = sys.argv[1:] or ["model", "ragged", "pretrain", "generator", "sampler", "generator_b16", "generator_noise"]
     if "model" in which:
         golden_model("model_b2_l20_v64", d, B=2, L=20, V=64, wseed=0, bseed=0)
     if "ragged" in which:
@@ -238,6 +358,12 @@ def main():
         golden_pretrain("pretrain_b2", d, B=2, wseed=0, bseed=0)
     if "generator" in which:
         golden_generator("generator_b2", B=2, wseed=0, bseed=0)
+    if "sampler" in which:
+        golden_sampler("sampler_b32", d, B=32, wseed=0, bseed=11)
+    if "generator_b16" in which:
+        golden_generator_batch("generator_b16", B=16, wseed=0, bseed=3)
+    if "generator_noise" in which:
+        golden_generator_noise("generator_noise_b2", B=2, wseed=0, bseed=0, noise_seed=1234)
 
 
 if __name__ == "__main__":

@@ -106,6 +106,21 @@ def test_encoder_backward_matches_oracle_default_dims():
     print("worst parameter-gradient error:", worst)
 
 
+def test_encoder_backward_batch_16_engages_split_k():
+    """B = 16 → 1 024 vision rows / 1 344 joint rows: the weight-gradient GEMMs have K ≥ 512 and take the split-K path
+    (gemm_sm100.cu: nkb / 8 ≥ 2), the language-side ones (320 rows) do not — both against the oracle."""
+    worst = _grad_check(D, 16, 20, 64, 2, 3)
+    print("B=16 worst parameter-gradient error:", worst)
+
+
+def test_encoder_backward_at_bench_batch_256():
+    """BASELINE.json configs[1] at its own size: B = 256, L = 20, V = 64 — the exact tile counts, cluster pairing, wave
+    quantisation and split-K factors of the timed bench step — outputs, input gradients and every parameter gradient
+    against the CPU oracle (≈ 1 min of host time)."""
+    worst = _grad_check(D, 256, 20, 64, 0, 7)
+    print("B=256 worst parameter-gradient error:", worst)
+
+
 def test_encoder_backward_ragged_shapes():
     _grad_check(D, 3, 13, 36, 5, 9)
 

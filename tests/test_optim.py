@@ -72,3 +72,41 @@ def test_fused_adamw_rejects_cpu_parameters():
     p.grad = torch.ones(4)
     with pytest.raises(TypeError):
         B200AdamW([p]).step()
+
+
+def test_optimizer_step_invalidates_prepared_weight_caches():
+    """the fused step writes through raw pointers; the split-bf16 weight copies of the native modules
+    are keyed on (data_ptr, _version), so the step must bump the version counters.  forward → step → forward must
+    change the output and equal a model rebuilt from the updated weights."""
+    from test_pretrain_parity import build_model
+    from xlxmert_b200 import synth
+    from xlxmert_b200.config import DEFAULT_DIMS as d
+    from xlxmert_b200.optim import B200AdamW
+
+    model, table = build_model(5)
+    model.train()
+    batch = {k: v.cuda() for k, v in synth.make_batch(d, 2, 12, 64, seed=1).items()}
+    kw = dict(input_ids=batch["input_ids"], visual_pos=batch["visual_pos"], attention_mask=batch["attention_mask"],
+              cluster_ids=batch["cluster_ids"], vis_mask=batch["vis_mask"], task="vis_mask",
+              label_dict={"obj_labels": batch["obj_labels"]})
+    versions = {n: p._version for n, p in model.named_parameters()}
+    opt = B200AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3)
+    l0 = model(**kw)["total_loss"]
+    l0.backward()
+    stepped = [n for n, p in model.named_parameters() if p.grad is not None]
+    assert stepped
+    opt.step(max_grad_norm=1.0)
+    for n, p in model.named_parameters():
+        if n in stepped:
+            assert p._version > versions[n], n
+    for p in model.parameters():
+        p.grad = None
+    with torch.no_grad():
+        l1 = model(**kw)["total_loss"]
+    assert abs(float(l1) - float(l0)) > 1e-4 * abs(float(l0)), "the forward after the step still sees the old weights"
+    fresh, _ = build_model(5)
+    fresh.load_state_dict({k: v.detach().clone() for k, v in model.state_dict().items()}, strict=True)
+    fresh.train()
+    with torch.no_grad():
+        l2 = fresh(**kw)["total_loss"]
+    assert abs(float(l2) - float(l1)) <= 1e-6 * abs(float(l1)), (float(l1), float(l2))

@@ -99,3 +99,36 @@ def test_cuda_graph_replay_matches_eager(sampler):
     c = m.sample_image_NAR(ids, n_steps=3, return_codes=True, cuda_graph=True)     # second run: pure replay
     for x, y, z in zip(a, b, c):
         assert torch.equal(x, y) and torch.equal(x, z)
+
+
+def test_nar_teacher_forced_at_batch_32():
+    """BASELINE.json configs[4] batch size (32 per GPU): the reference's own 4-step NAR run (golden ``sampler_b32``,
+    oracle/make_golden.py::golden_sampler) replayed with its masks; per step the max-probability must agree to 2e-3 and
+    the arg-max margin-stratified (exact above the margin, member of the reference top-2 below)."""
+    from xlxmert_b200.sampler import B200ImggenModel
+    from util import assert_argmax_stratified, rel_err
+    g = load_golden("sampler_b32")
+    B, L, V, wseed, bseed, n_steps = (int(x) for x in g["meta"])
+    pre, table = build_model(wseed)
+    m = B200ImggenModel(D, num_clusters=D.num_clusters)
+    m.set_visual_embedding(table.clone())
+    m.load_state_dict({k: v for k, v in pre.state_dict().items() if not k.startswith("cls.")}, strict=False)
+    m = m.cuda().eval()
+    table = table.cuda()
+    batch = synth.make_batch(D, B, L, V, seed=bseed)
+    ids, vpos = batch["input_ids"].cuda(), batch["visual_pos"].cuda()
+    code = torch.zeros(B, V, D.feat_dim, device="cuda")
+    flips = 0
+    with torch.no_grad():
+        lang = m.bert.language_stack(ids, ids > 0)
+        for i in range(n_steps):
+            vis_mask = torch.from_numpy(g[f"mask{i}"]).cuda().bool()
+            code = torch.where(vis_mask.view(B, V, 1), m.mask_feat.view(1, 1, -1), code)
+            prob, pid = m._predict(ids, code, vpos, lang)
+            assert rel_err(prob.cpu(), g[f"prob{i}"]) < 2e-3, i
+            flips += assert_argmax_stratified(pid, g[f"id{i}"], g[f"top2_{i}"], g[f"margin{i}"], 2e-4,
+                                              f"NAR B=32 step {i}")
+            ref_id = torch.from_numpy(g[f"id{i}"]).cuda().long()
+            code = torch.where(vis_mask.view(B, V, 1), table[ref_id], code)
+    assert rel_err(code.cpu()[:, ::4, ::128], g["code_sub"]) < 1e-6
+    print(f"[argmax NAR B=32] total flips over {n_steps} steps x {B * V} rows: {flips}")

@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libxlxmert_b200.so")
+GEMM_TEST = os.path.join(LIBDIR, "gemm_test")     # standalone tcgen05-GEMM probe (csrc/gemm_test.cu), run by tests/test_gemm_probe.py
 SOURCES = ["gemm_sm100.cu", "kernels.cu", "attention.cu", "encoder.cu", "heads.cu", "generator.cu", "optim.cu", "kmeans.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -46,7 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "build.stamp")
     want = source_hash()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == want:
+    if (not force and os.path.exists(LIB) and os.path.exists(GEMM_TEST) and os.path.exists(stamp)
+            and open(stamp).read().strip() == want):
         return LIB
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     objs = []
@@ -58,7 +60,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(" ".join(cmd))
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(o)
-    for s, p in procs:
+    probe = subprocess.Popen([_nvcc(), *[f for f in flags if f != "-fPIC" and f != "-Xcompiler"],
+                              os.path.join(CSRC, "gemm_test.cu"), os.path.join(CSRC, "gemm_sm100.cu"), "-o", GEMM_TEST,
+                              "-lcuda"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    for s, p in procs + [("gemm_test.cu", probe)]:
         out, _ = p.communicate()
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {s}:\n{out.decode()}")

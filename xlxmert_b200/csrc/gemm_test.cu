@@ -1,7 +1,9 @@
 // Standalone correctness probe for the tcgen05 GEMM (run on the B200 box through gpurun):
 //   gemm_test M N K passes a_mn b_mn epi
 // epi bits: 1 bias, 2 gelu(+save u), 4 addend, 8 split output check, 16 gelu-grad, 32 accumulate,
-//           64 multiply by u_in, 128 (with 2) save gelu'(u) instead of u
+//           64 multiply by u_in, 128 (with 2) save gelu'(u) instead of u,
+//           256 pass a split-K workspace (weight-gradient shapes: small M·N, long K); the problem is then ALSO run without
+//               the workspace and the two outputs must agree to 1e-6 of max|out| (split-K on == split-K off)
 // Compares against a double-precision CPU reference on sampled entries and prints max relative error.
 #include <cmath>
 #include <cstdio>
@@ -79,9 +81,25 @@ int main(int argc, char** argv) {
   if (epi & 32) p.epi.flags |= EPI_ACCUM;
   if (epi & 64) { p.epi.flags |= EPI_MUL; p.epi.u_in = duin; p.epi.ld_u = N; }
   if (epi & 128) p.epi.flags |= EPI_SAVE_DGELU;
+  std::vector<float> out_nosplit;
+  float* dws = nullptr;
+  if (epi & 256) {
+    // reference run without the workspace (split-K cannot engage), on a copy of the initial output
+    int rc0 = gemm_launch(p, 0);
+    if (rc0) { printf("gemm_launch (no split-K) rc=%d\n", rc0); return 3; }
+    CK(cudaDeviceSynchronize());
+    out_nosplit.resize(nmn);
+    CK(cudaMemcpy(out_nosplit.data(), dout, nmn * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(dout, out0.data(), nmn * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&dws, gemm_splitk_ws_floats() * 4));
+    CK(cudaMemset(dws, 0xff, gemm_splitk_ws_floats() * 4));   // NaN-fill: a partial sum that is read before written shows
+    p.splitk_ws = dws; p.splitk_ws_floats = gemm_splitk_ws_floats();
+  }
+  long long launches0 = gemm_launch_count();
   int rc = gemm_launch(p, 0);
   if (rc) { printf("gemm_launch rc=%d\n", rc); return 3; }
   CK(cudaDeviceSynchronize());
+  const bool splitk_engaged = (gemm_launch_count() - launches0) > 1;   // main kernel + reduce kernel
   std::vector<float> out(nmn), usave(nmn);
   std::vector<__nv_bfloat16> ohi(nmn), olo(nmn);
   CK(cudaMemcpy(out.data(), dout, nmn * 4, cudaMemcpyDeviceToHost));
@@ -142,6 +160,19 @@ int main(int argc, char** argv) {
   double rel = max_err / fmax(max_ref, 1e-30);
   double tol = passes == 3 ? 5e-5 : 2e-2;
   bool ok = rel < tol && (!(epi & 8) || max_split_err < 1e-4 * max_ref) && (!(epi & 2) || max_u_err < tol * max_ref + 1e-5);
+  if (epi & 256) {
+    double dmax = 0, omax = 0;
+    for (size_t i = 0; i < nmn; ++i) {
+      dmax = fmax(dmax, fabs(static_cast<double>(out[i]) - out_nosplit[i]));
+      omax = fmax(omax, fabs(static_cast<double>(out_nosplit[i])));
+      if (out[i] != out[i]) dmax = 1e30;
+    }
+    const bool same = dmax <= 1e-6 * omax;
+    printf("  split-K %s: max|on - off| = %.3e (%.2e of max|out|) %s\n", splitk_engaged ? "engaged" : "NOT engaged", dmax,
+           dmax / fmax(omax, 1e-30), same ? "OK" : "FAIL");
+    ok = ok && same;
+    if (argc > 9 && atoi(argv[9]) && !splitk_engaged) { printf("  expected split-K to engage\n"); ok = false; }
+  }
   printf("M=%d N=%d K=%d passes=%d a_mn=%d b_mn=%d epi=%d : max_abs_err=%.3e max_ref=%.3e rel=%.3e split_err=%.3e u_err=%.3e %s\n",
          M, N, K, passes, a_mn, b_mn, epi, max_err, max_ref, rel, max_split_err, max_u_err, ok ? "OK" : "FAIL");
   if (reps > 0) {

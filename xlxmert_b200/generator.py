@@ -130,10 +130,24 @@ class B200Generator(nn.Module):
             self._prep_key = key
         return self._prep, self._parr
 
+    def _noise_active(self) -> bool:
+        """Whether any NoiseInjection weight is non-zero (layers.py:56-62: they are initialised to 0, so a random-init G
+        is deterministic).  Reading ten device scalars costs ten host syncs, so the answer is cached per weight version
+        — which also keeps the forward capturable in a CUDA graph."""
+        ws = [w for rb in self.resblocks for w in (rb.noise1.weight, rb.noise2.weight)]
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        cached = self.__dict__.get("_noise_key")
+        if cached is None or cached[0] != key:
+            cached = (key, bool(torch.cat([w.detach().reshape(-1) for w in ws]).ne(0).any().item()))
+            self.__dict__["_noise_key"] = cached
+        return cached[1]
+
     @torch.no_grad()
-    def forward(self, emb, train=True, return_intermediates: bool = False):
+    def forward(self, emb, train=True, return_intermediates: bool = False, noise=None):
         """``emb``: ``[B, 2048, 8, 8]`` (any strides) or ``[B, 8, 8, 2048]`` → ``[B, 3, 256, 256]`` in (−1, 1).
-        ``train`` only gates noise injection (layers.py:56-62, 246), as in the reference."""
+        ``train`` only gates noise injection (layers.py:56-62, 246), as in the reference.  ``noise`` (optional, with
+        ``train=True``): the ten standard-normal maps to inject instead of fresh draws — ``[B, R, R]`` (or
+        ``[B, 1, R, R]``) for noise1 / noise2 of each block in order, R = 8, 16, 16, 32, …, 128, 256."""
         lib = _lib.load()
         if not emb.is_cuda:
             raise RuntimeError("B200Generator runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -147,7 +161,16 @@ class B200Generator(nn.Module):
         prep, parr = self._prepared()
         stream = torch.cuda.current_stream().cuda_stream
         noise_arr, noise_keep = None, []
-        if train and any(float(w) != 0.0 for rb in self.resblocks for w in (rb.noise1.weight, rb.noise2.weight)):
+        if train and noise is not None:
+            want = [s for i in range(N_BLOCKS) for s in (8 << i, 16 << i)]
+            if len(noise) != len(want):
+                raise ValueError(f"noise must hold {len(want)} maps")
+            for t, r in zip(noise, want):
+                if t.numel() != B * r * r:
+                    raise ValueError(f"noise map of {t.numel()} elements where [B={B}, {r}, {r}] is expected")
+                noise_keep.append(t.to(device=dev, dtype=torch.float32).reshape(B, r, r).contiguous())
+            noise_arr = (C.c_void_p * len(noise_keep))(*[t.data_ptr() for t in noise_keep])
+        elif train and self._noise_active():
             for i in range(N_BLOCKS):
                 r = 8 << i
                 noise_keep += [torch.randn(B, r, r, device=dev), torch.randn(B, 2 * r, 2 * r, device=dev)]

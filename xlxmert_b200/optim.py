@@ -99,6 +99,8 @@ class B200AdamW(torch.optim.Optimizer):
                                         int(bool(group["correct_bias"])), None if sq is None else sq.data_ptr(),
                                         float(max_grad_norm), torch.cuda.current_stream().cuda_stream)
                 _lib.check("xlx_adamw_step", rc)
-            for p in ps:      # the data pointers were written behind autograd's back: bump the version counters
-                p.data = p.data
+            # The kernels wrote through raw pointers, behind autograd's back.  Bump the version counters so that every
+            # cache keyed on (data_ptr, _version) — the split-bf16 weight copies of the encoder, heads and generator —
+            # is rebuilt before the next forward.  (`p.data = p.data` does NOT change `_version`.)
+            torch.autograd.graph.increment_version(ps)
         return loss
