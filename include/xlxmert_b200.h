@@ -92,9 +92,12 @@ int32_t xlx_encoder_fwd(const xlx_dims* d, const float* const* params, const voi
                         int32_t training, int32_t passes, void* stream);
 
 /* Backward of the above (the reference gets it from torch autograd: lxmert_pretrain.py:338).
- * d_lang_out / d_vis_out: gradients wrt the two outputs (NULL = zero).  Writes d_lang_in [B,L,H],
- * d_visual_feats [B,V,F] (NULL to skip) and every parameter gradient into `grads` (overwritten, not
- * accumulated).
+ * d_lang_out / d_vis_out: gradients wrt the two outputs (NULL = that output is not part of the loss).  Writes
+ * d_lang_in [B,L,H], d_visual_feats [B,V,F] (NULL to skip) and every parameter gradient into `grads` (overwritten,
+ * not accumulated).  With x_layers > 0, a NULL d_lang_out (d_vis_out) leaves the last cross-modality layer's
+ * lang_self_att / lang_inter / lang_output (visn_self_att / visn_inter / visn_output) parameters without gradient, as
+ * in the reference's autograd graph: those blocks are skipped and their 16 arena slots are NOT written — the caller
+ * must report "no gradient" for them (the reference loop's `param.grad = None`, lxmert_pretrain.py:363-364).
  * `stages` is a mask of XLX_BWD_* (XLX_BWD_ALL for the whole backward).  The stages must be issued in the order
  * CROSS, VISION, LANGUAGE, VISN_FC, in one call or several (the state between stages lives in the workspace): a
  * data-parallel caller enqueues the all-reduce of the gradient-arena range a stage completed

@@ -91,6 +91,27 @@ def test_pretrain_losses_and_gradients_match_reference(setup, task):
         # the centroid table is frozen (modeling.py:146-151); the LM head is untouched by this task
         assert model.vis_emb.weight.grad is None
         assert model.cls.predictions.bias.grad is None
+    # Parameters outside the task's autograd graph get NO gradient (None, not zeros) — the reference's semantics, which
+    # decide what AdamW skips (no weight decay, no step count) and what DDP's find_unused_parameters walks (SURVEY §5.8,
+    # lxmert_pretrain.py:102-106,363-364): the last cross-modality layer's self-attention + FFN of the modality whose
+    # output the task does not read.
+    nx = D.x_layers - 1
+    lang_tail = [n for n, _ in model.bert.encoder.named_parameters()
+                 if n.startswith((f"x_layers.{nx}.lang_self_att", f"x_layers.{nx}.lang_inter", f"x_layers.{nx}.lang_output"))]
+    vis_tail = [n for n, _ in model.bert.encoder.named_parameters()
+                if n.startswith((f"x_layers.{nx}.visn_self_att", f"x_layers.{nx}.visn_inter", f"x_layers.{nx}.visn_output"))]
+    assert len(lang_tail) == 16 and len(vis_tail) == 16
+    grads = {n: p.grad for n, p in model.bert.encoder.named_parameters()}
+    unused = lang_tail if task == "vis_mask" else vis_tail
+    for n in unused:
+        assert grads[n] is None, (task, n)
+    for n, gr in grads.items():
+        if n not in unused:
+            assert gr is not None and bool(torch.isfinite(gr).all()), (task, n)
+    if task == "vis_mask":
+        assert model.bert.pooler.dense.weight.grad is None
+    else:
+        assert model.mask_feat.grad is None and model.obj_predict_head.linear_feat.weight.grad is None
     if task == "word_mask":
         # tied decoder / word-embedding weight receives both contributions through one Parameter
         assert model.cls.predictions.decoder.weight is model.bert.embeddings.word_embeddings.weight

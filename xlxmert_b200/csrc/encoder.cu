@@ -753,11 +753,21 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
     XLX_TRY(load_grad(cur + lh, d_vis_out, vh));
     for (int k = nx - 1; k >= 0; --k) {
       const int a0 = nl + nr + 3 * k, f0 = nl + nr + 2 * k;
+      // An output without upstream gradient (d_lang_out == NULL: the vis_mask task; d_vis_out == NULL: word_mask and
+      // matched) leaves the LAST cross-modality layer's self-attention + FFN of that modality outside the graph: the
+      // reference's autograd gives those parameters no gradient at all and AdamW skips them.  Their
+      // blocks are not run, their arena slots are not written (the caller reports None), and the zero-filled rows of
+      // `cur` are exactly the gradient the cross-attention block below has to see.
+      const bool skip_lang = (k == nx - 1) && !d_lang_out, skip_vis = (k == nx - 1) && !d_vis_out;
       XLX_TRY(fork_to(side, r.st));
-      XLX_TRY(ffn_bwd(bwl, f0, cur, nxt));                          // language chain
-      XLX_TRY(att_self_bwd(bwl, a0 + 1, L, nxt, cur));
-      XLX_TRY(ffn_bwd(bw, f0 + 1, cur + lh, nxt + lh));             // vision chain
-      XLX_TRY(att_self_bwd(bw, a0 + 2, V, nxt + lh, cur + lh));
+      if (!skip_lang) {
+        XLX_TRY(ffn_bwd(bwl, f0, cur, nxt));                        // language chain
+        XLX_TRY(att_self_bwd(bwl, a0 + 1, L, nxt, cur));
+      }
+      if (!skip_vis) {
+        XLX_TRY(ffn_bwd(bw, f0 + 1, cur + lh, nxt + lh));           // vision chain
+        XLX_TRY(att_self_bwd(bw, a0 + 2, V, nxt + lh, cur + lh));
+      }
       XLX_TRY(join_from(side, r.st));
       XLX_TRY(att_cross_bwd(bw, a0, cur, nxt));                     // joint
       float* t = cur; cur = nxt; nxt = t;

@@ -153,6 +153,9 @@ class _EncoderFn(torch.autograd.Function):
                                  lang_out.data_ptr(), vis_out.data_ptr(), _ptr(lang_hidden), _ptr(vis_hidden),
                                  ws.data_ptr(), ws_bytes, int(training), enc.passes, _stream_ptr())
         _lib.check("xlx_encoder_fwd", rc)
+        # an output the loss does not read must arrive in backward as None (not as a tensor of zeros): it decides which
+        # blocks of the last cross-modality layer are part of the graph at all
+        ctx.set_materialize_grads(False)
         if training:
             ctx.enc, ctx.ws, ctx.ws_bytes, ctx.shape = enc, ws, ws_bytes, (B, L, V)
             ctx.prep, ctx.parr, ctx.params = prep, parr, params
@@ -212,9 +215,12 @@ class _EncoderFn(torch.autograd.Function):
                 grads.mul_(1.0 / world)
             enc.arena_reduced = True
         enc._release_workspace(ctx.ws)
+        # the last cross-modality layer's self-attention + FFN of a modality whose output got no upstream gradient are
+        # outside the graph: no gradient (None), exactly what the reference's autograd reports
+        unused = enc._unused_slots(d_lang_out is None, d_vis_out is None)
         pgrads = []
-        for p, (off, n) in zip(ctx.params, enc._grad_slices):
-            pgrads.append(grads[off:off + n].view(p.shape) if p.requires_grad else None)
+        for i, (p, (off, n)) in enumerate(zip(ctx.params, enc._grad_slices)):
+            pgrads.append(grads[off:off + n].view(p.shape) if (p.requires_grad and i not in unused) else None)
         ctx.ws = None
         return (None, None, None, None, None, None, d_lang_in, d_feats, *pgrads)
 
@@ -349,6 +355,23 @@ class B200LxmertEncoder(nn.Module):
                     raise ValueError(f"backward stages {stages:#x} do not cover one contiguous arena range")
             self._stage_ranges[stages] = (spans[0][0], sum(n for _, n in spans)) if spans else (0, 0)
         return self._stage_ranges[stages]
+
+    def _unused_slots(self, no_lang_grad: bool, no_vis_grad: bool):
+        """C-ABI slots that ``xlx_encoder_bwd`` leaves unwritten when an output has no upstream gradient (see the
+        header): slot layout of an x-layer = ATT(visual_attention) 10, ATT(lang_self_att) 10, ATT(visn_self_att) 10,
+        FFN(lang) 6, FFN(visn) 6."""
+        d = self.dims
+        if d.x_layers == 0 or not (no_lang_grad or no_vis_grad):
+            return frozenset()
+        base = 8 + (d.l_layers + d.r_layers) * 16 + (d.x_layers - 1) * 42
+        out = set()
+        if no_lang_grad:
+            out.update(range(base + 10, base + 20))
+            out.update(range(base + 30, base + 36))
+        if no_vis_grad:
+            out.update(range(base + 20, base + 30))
+            out.update(range(base + 36, base + 42))
+        return frozenset(out)
 
     def _grad_arena(self, dev) -> torch.Tensor:
         lib = _lib.load()

@@ -94,6 +94,8 @@ class B200IndexFlatL2:
         dev_i = [torch.empty(R, dtype=torch.int64, device=self.device) for _ in range(2)]
         dev_d = [torch.empty(R, dtype=torch.float32, device=self.device) for _ in range(2)]
         streams = [torch.cuda.Stream(self.device) for _ in range(2)]
+        for st in streams:       # add() queued the centroid upload + xlx_kmeans_prepare on the current stream
+            st.wait_stream(torch.cuda.current_stream(self.device))
         busy = [None, None]
         for i, r0 in enumerate(range(0, N, R)):
             s = i & 1

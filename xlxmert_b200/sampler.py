@@ -76,8 +76,18 @@ class B200ImggenModel(nn.Module):
     # encoder on the cached language stack → cluster head → softmax-max/arg-max — is captured once per (B, L) into a
     # CUDA graph over static buffers and replayed every step.
     def _graph_predict(self, input_ids, code, visual_pos, language_stack):
+        # the weight-prepare kernels run during warm-up, outside the capture: a graph is only valid for the parameter
+        # values it was captured with, so the parameters' (data_ptr, version) are part of the key (load_state_dict,
+        # set_visual_embedding, fine-tuning → a fresh capture; stale graphs are dropped)
+        pkey = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self.vis_emb is not None:
+            pkey += ((self.vis_emb.weight.data_ptr(), self.vis_emb.weight._version),)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        if self.__dict__.get("_graphs_pkey") != pkey:
+            graphs.clear()
+            self.__dict__["_graphs_pkey"] = pkey
         key = (tuple(input_ids.shape), code.device.index)
-        st = self.__dict__.setdefault("_graphs", {}).get(key)
+        st = graphs.get(key)
         if st is None:
             st = {"code": torch.empty_like(code), "lang": torch.empty_like(language_stack),
                   "ids": input_ids.clone(), "pos": visual_pos.clone()}
