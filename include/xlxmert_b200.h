@@ -126,6 +126,29 @@ int32_t xlx_visual_input_fwd(const float* table, const int64_t* cluster_ids, con
 int32_t xlx_visual_input_bwd(const float* d_feats, const uint8_t* vis_mask, int32_t rows, int32_t feat_dim,
                              float* d_mask_feat, float* scratch, void* stream);
 
+/* ---- input path of the pre-training step --------------------------------------------------
+ * Device half of Trainer.forward (x-lxmert/src/pretrain/lxmert_pretrain.py:143-225): the host packs the arrays of one
+ * collate_fn batch (lxmert_data.py:497-652) into ONE pinned buffer with the layout below, copies it with one
+ * cudaMemcpyAsync, and this kernel unpacks it into the tensors XLxmertForPretraining.forward takes.
+ *   layout (byte offsets, each section 256-byte aligned; xlx_pretrain_inputs_layout fills offsets6 in this order):
+ *     [0] word_id       int64 [B,L]  — the ids the task reads: masked_word_id (word_mask), other_word_id (matched),
+ *                                      word_id (vis_mask)                                     (:193-198)
+ *     [1] word_label    int64 [B,L]  — read for task word_mask only                            (:158-159)
+ *     [2] matched_label int64 [B]    — read for task matched only                              (:181-183)
+ *     [3] cluster_id    int64 [B,V]                                                            (:147-149)
+ *     [4] vis_mask      uint8 [B,V]                                                            (:155)
+ *     [5] box_position  fp32  [B,V,4]                                                          (:153)
+ *   outputs: word_id, attention_mask = word_id > 0 (one byte per token, torch.bool), additive_mask [B,L] =
+ *     (1 − mask)·finfo.min (HF:766-774; what xlx_encoder_fwd takes), cluster_ids, vis_mask (bool bytes), visual_pos,
+ *     and the task's labels: obj_labels = vis_mask ? cluster_id : −100 (:163-166), word_labels, matched_labels
+ *     (the other two may be NULL). */
+enum { XLX_TASK_VIS_MASK = 0, XLX_TASK_WORD_MASK = 1, XLX_TASK_MATCHED = 2 };   /* MASK_MODALITY order, :794-800 */
+int32_t xlx_pretrain_inputs_layout(int32_t B, int32_t L, int32_t V, int64_t* offsets6, int64_t* total_bytes);
+int32_t xlx_pretrain_inputs_unpack(const void* packed, int32_t B, int32_t L, int32_t V, int32_t task, int64_t* word_id,
+                                   uint8_t* attention_mask, float* additive_mask, int64_t* cluster_ids,
+                                   uint8_t* vis_mask, float* visual_pos, int64_t* obj_labels, int64_t* word_labels,
+                                   int64_t* matched_labels, void* stream);
+
 /* ---- LxmertEmbeddings (HF:179-214; reached through self.bert at lxrt/modeling.py:195-206) -----------------
  * params (HOST array of 5 device pointers): word_embeddings.weight [vocab,H], position_embeddings.weight
  * [max_pos,H], token_type_embeddings.weight [type_vocab,H], LayerNorm.weight, LayerNorm.bias.

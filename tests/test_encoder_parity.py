@@ -91,7 +91,13 @@ def _grad_check(d, B, L, V, wseed, bseed, passes=3, out_tol=OUT_TOL, grad_tol=GR
     for name, p in enc.named_parameters():
         ref = sdo[name].grad
         assert p.grad is not None, name
-        if float(ref.abs().max()) < 1e-6:     # mathematically zero (key bias: softmax shift invariance)
+        if name.endswith("key.bias"):
+            # mathematically zero (softmax is invariant to a per-query shift of the scores): both sides hold summation
+            # noise only, which grows with the row count — judged against the scale of the sibling query-bias gradient
+            scale = float(sdo[name.replace("key.bias", "query.bias")].grad.abs().max())
+            assert float(p.grad.abs().max()) < 1e-3 * scale + 1e-6, (name, float(p.grad.abs().max()), scale)
+            continue
+        if float(ref.abs().max()) < 1e-6:
             assert float(p.grad.abs().max()) < 1e-4, name
             continue
         e = rel_err(p.grad.cpu(), ref)

@@ -1,8 +1,9 @@
 """Runs the standalone tcgen05-GEMM probe (``xlxmert_b200/csrc/gemm_test.cu`` → ``xlxmert_b200/lib/gemm_test``, built by
 ``__graft_entry__.build()``) on the B200: every operand-major combination, ragged shapes, every epilogue, and — VERDICT
 r1 weak-1 — the SPLIT-K weight-gradient path that the encoder step spends ≈ 25 % of its time in: the probe runs those
-problems with and without the split-K workspace and requires |on − off| ≤ 1e-6·max|out| besides the fp64 reference check
-(≤ 5e-5 tensor-normalised for bf16x3)."""
+problems with and without the split-K workspace; each run must match the fp64 reference (≤ 5e-5 tensor-normalised for
+bf16x3) and the two must agree to 1e-4·max|out|.  (Measured on B200: fp32 accumulation of K = 16 384 products is itself
+1e-5 … 3e-5 away from fp64, so on/off differ by ≈ 5e-5 — a 1e-6 bar would test the summation order, not the kernel.)"""
 import os
 import subprocess
 

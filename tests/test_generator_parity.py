@@ -52,8 +52,9 @@ def test_generator_input_layouts_and_noise_flag_agree():
     b = G(code.view(B, 8, 8, 2048), train=False)            # layers.py:231-233 accepts cell-major input too
     c = G(code.permute(0, 2, 1).view(B, 2048, 8, 8).contiguous(), train=True)   # noise weights are 0 ⇒ identical
     assert torch.equal(a, b) and torch.equal(a, c)
-    for rb in G.resblocks:                                   # a trained G has non-zero noise weights
-        rb.noise1.weight.data.fill_(0.05)
+    with torch.no_grad():
+        for rb in G.resblocks:                               # a trained G has non-zero noise weights
+            rb.noise1.weight.fill_(0.05)    # (in place on the Parameter: `.data.fill_` would not bump its version counter)
     d = G(code.view(B, 8, 8, 2048), train=True)
     assert not torch.equal(a, d) and torch.isfinite(d).all() and float(d.abs().max()) <= 1.0
     assert torch.equal(a, G(code.view(B, 8, 8, 2048), train=False))

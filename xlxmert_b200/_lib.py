@@ -124,6 +124,10 @@ def _sig(lib):
     lib.xlx_gather_rows.argtypes = [P, P, P, I32, I32, P, P, P]
     lib.xlx_scatter_rows.restype = I32
     lib.xlx_scatter_rows.argtypes = [P, P, I32, I32, I32, P, P]
+    lib.xlx_pretrain_inputs_layout.restype = I32
+    lib.xlx_pretrain_inputs_layout.argtypes = [I32, I32, I32, C.POINTER(I64), C.POINTER(I64)]
+    lib.xlx_pretrain_inputs_unpack.restype = I32
+    lib.xlx_pretrain_inputs_unpack.argtypes = [P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P]
     lib.xlx_matchhead_scratch_floats.restype = I64
     lib.xlx_matchhead_scratch_floats.argtypes = [I32]
     lib.xlx_matchhead_fwd.restype = I32

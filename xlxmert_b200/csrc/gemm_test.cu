@@ -3,7 +3,10 @@
 // epi bits: 1 bias, 2 gelu(+save u), 4 addend, 8 split output check, 16 gelu-grad, 32 accumulate,
 //           64 multiply by u_in, 128 (with 2) save gelu'(u) instead of u,
 //           256 pass a split-K workspace (weight-gradient shapes: small M·N, long K); the problem is then ALSO run without
-//               the workspace and the two outputs must agree to 1e-6 of max|out| (split-K on == split-K off)
+//               the workspace and the two outputs must agree to 1e-4 of max|out| (split-K on vs off).  They cannot be
+//               bit-identical: the summation order differs, and the fp32 accumulation of K = 16 384 products in TMEM is
+//               itself only good to ≈ 1e-5 of max|out| against fp64 (measured: 1e-5 … 3e-5 for either variant, the split
+//               one being the closer of the two) — so the bar is twice the 5e-5 each side is held to against fp64.
 // Compares against a double-precision CPU reference on sampled entries and prints max relative error.
 #include <cmath>
 #include <cstdio>
@@ -167,7 +170,7 @@ int main(int argc, char** argv) {
       omax = fmax(omax, fabs(static_cast<double>(out_nosplit[i])));
       if (out[i] != out[i]) dmax = 1e30;
     }
-    const bool same = dmax <= 1e-6 * omax;
+    const bool same = dmax <= 1e-4 * omax;
     printf("  split-K %s: max|on - off| = %.3e (%.2e of max|out|) %s\n", splitk_engaged ? "engaged" : "NOT engaged", dmax,
            dmax / fmax(omax, 1e-30), same ? "OK" : "FAIL");
     ok = ok && same;

@@ -138,7 +138,7 @@ class _EncoderFn(torch.autograd.Function):
         lang_in = lang_in.contiguous().float()
         visual_feats = visual_feats.contiguous().float()
         visual_pos = visual_pos.contiguous().float()
-        prep, parr = enc._prepared(params)
+        prep, parr = enc._prepared(params, force=training)
         ws_bytes = lib.xlx_encoder_workspace_bytes(C.byref(enc._cdims), B, L, V, int(training))
         if ws_bytes == 0:
             raise _lib.XlxError("xlx_encoder_workspace_bytes", -22 if max(L, V) > 64 else -20)
@@ -296,16 +296,21 @@ class B200LxmertEncoder(nn.Module):
         self.invalidate_parameter_cache()
         return super()._apply(fn, recurse)
 
-    def _prepared(self, params):
-        """Split-bf16 copies of the weights, refreshed whenever any parameter changed."""
+    def _prepared(self, params, force: bool = False):
+        """Split-bf16 copies of the weights.  Training (``force``): rebuilt on EVERY forward — the weights change with
+        every optimiser step, and the reference's own optimiser (HF ``AdamW`` 4.1.1, lxmert_pretrain.py:114) updates
+        through ``p.data.add_()``, which leaves no trace in the parameters' version counters, so no cache key could
+        notice it (one batched launch, ≈ 0.4 ms of a 45 ms step).  Inference: refreshed when a parameter's
+        ``(data_ptr, _version)`` changed (``load_state_dict``, in-place ops under ``no_grad``); after an update through
+        ``.data`` call :meth:`invalidate_prepared`."""
         lib = _lib.load()
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = None if force else tuple((p.data_ptr(), p._version) for p in params)
         dev = params[0].device
         if self._prep is None or self._prep.device != dev:
             nbytes = lib.xlx_encoder_prep_bytes(C.byref(self._cdims))
             self._prep = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             self._prep_key = None
-        if key != self._prep_key:
+        if force or key != self._prep_key:
             for p in params:
                 if p.dtype != torch.float32 or not p.is_contiguous():
                     raise TypeError("B200LxmertEncoder parameters must be contiguous fp32")

@@ -52,8 +52,10 @@ class _FusedHead:
     def fn(self, name):
         return getattr(_lib.load(), f"xlx_{self.kind}_{name}")
 
-    def prepared(self, params):
-        key = tuple((p.data_ptr(), p._version) for p in params)
+    def prepared(self, params, force: bool = False):
+        """Split-bf16 weight copies; ``force`` (training forwards) rebuilds them unconditionally — see
+        ``B200LxmertEncoder._prepared`` for why a version-counter key cannot be trusted across optimiser steps."""
+        key = None if force else tuple((p.data_ptr(), p._version) for p in params)
         dev = params[0].device
         if self._prep is None or self._prep.device != dev:
             n = self.fn("prep_bytes")(C.byref(self.cdims), self.classes)
@@ -61,7 +63,7 @@ class _FusedHead:
                 raise _lib.XlxError(f"xlx_{self.kind}_prep_bytes", -20)
             self._prep = torch.empty(n, dtype=torch.uint8, device=dev)
             self._prep_key = None
-        if key != self._prep_key:
+        if force or key != self._prep_key:
             for p in params:
                 if p.dtype != torch.float32 or not p.is_contiguous():
                     raise TypeError("head parameters must be contiguous fp32")
@@ -82,7 +84,7 @@ class _FusedHead:
         lead = hidden.shape[:-1]
         h2 = hidden.reshape(-1, d.hidden).contiguous().float()
         M, dev = h2.shape[0], h2.device
-        prep = self.prepared(params)
+        prep = self.prepared(params, force=labels is not None)      # a loss call is a training step: weights just changed
         if labels is None:      # inference (sampler loop): one grow-only workspace, stream-ordered reuse
             nws = self.fn("workspace_bytes")(C.byref(self.cdims), self.classes, M)
             ws = getattr(self, "_ws_infer", None)

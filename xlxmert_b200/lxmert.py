@@ -76,7 +76,11 @@ class B200LxmertModel(nn.Module):
             attention_mask = torch.ones(B, L, dtype=torch.bool, device=ref.device)         # HF:751-752
         # additive masks (HF:766-782): (1 − mask)·finfo.min, one row per sample
         fmin = torch.finfo(torch.float32).min
-        lmask = ((1.0 - attention_mask.to(torch.float32)) * fmin).view(B, 1, 1, L)
+        prebuilt = getattr(attention_mask, "_xlx_additive", None)      # B200PretrainInputs built it in its unpack kernel
+        if prebuilt is not None and prebuilt.shape == (B, L):
+            lmask = prebuilt.view(B, 1, 1, L)
+        else:
+            lmask = ((1.0 - attention_mask.to(torch.float32)) * fmin).view(B, 1, 1, L)
         vmask = None
         if visual_attention_mask is not None:
             V = visual_feats.shape[1]
