@@ -235,6 +235,27 @@ int32_t xlx_matchhead_bwd(const xlx_dims* d, int32_t B, const float* pooled, con
                           const float* scores, const float* d_loss, float* d_pooled, float* dW, float* dbias,
                           float* scratch, void* stream);
 
+/* ---- sampling-loop transitions (tasks/imggen_model.py:49-257) ----------------------
+ * The index / select work between two encoder passes, on the device (the reference: torch.topk + scatter_ +
+ * torch.where + nn.Embedding).  code [B,V,F] fp32 (in place), vis_mask / visited: one byte per cell, pred_prob [B,V],
+ * pred_id [B,V] from xlx_objhead_fwd, table = centroid table [classes,F], mask_feat [F].  V ≤ 64, F % 4 == 0.
+ * Ties between EQUAL probabilities go to the lower cell index (torch.topk leaves that order unspecified).
+ *   nar_update  (mask-predict, :199-243): pred_prob == NULL → initial state (all cells masked, code = mask_feat);
+ *               else code ← vis_mask ? table[pred_id] : code  (:238-243), vis_mask_next ← the n_mask_next cells of lowest
+ *               pred_prob (:209-212), code ← vis_mask_next ? mask_feat : code (:215-218 of the next iteration).
+ *               vis_mask_next may alias vis_mask.
+ *   ar_update   (one cell per step, :135-153): position ≥ 0 → that cell; < 0 → the unvisited cell of highest pred_prob;
+ *               code[b,cell] ← table[pred_id[b,cell]], vis_mask ← 0 there, visited ← 1 (confidence order only).
+ *   remask_cell (:111-113): code[:,cell] ← mask_feat, vis_mask[:,cell] ← 1. */
+int32_t xlx_sampler_nar_update(float* code, const uint8_t* vis_mask, const float* pred_prob, const int64_t* pred_id,
+                               const float* table, const float* mask_feat, int32_t B, int32_t V, int32_t F,
+                               int32_t n_mask_next, uint8_t* vis_mask_next, void* stream);
+int32_t xlx_sampler_ar_update(float* code, uint8_t* vis_mask, uint8_t* visited, const float* pred_prob,
+                              const int64_t* pred_id, const float* table, int32_t B, int32_t V, int32_t F,
+                              int32_t position, void* stream);
+int32_t xlx_sampler_remask_cell(float* code, uint8_t* vis_mask, const float* mask_feat, int32_t B, int32_t V, int32_t F,
+                                int32_t cell, void* stream);
+
 /* ---- Generator.forward (image_generator/src/layers.py:223-253) ----------------------------------------------
  * Canonical architecture only (scripts/train_generator.bash, tasks/sample_images.py:53-67): base_dim 32, emb_dim
  * 2048, codebook_dim 256, norm 'spade_in', SN, 8×8 grid → 256×256 RGB, five up-sampling residual blocks.

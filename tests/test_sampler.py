@@ -132,3 +132,92 @@ def test_nar_teacher_forced_at_batch_32():
             code = torch.where(vis_mask.view(B, V, 1), table[ref_id], code)
     assert rel_err(code.cpu()[:, ::4, ::128], g["code_sub"]) < 1e-6
     print(f"[argmax NAR B=32] total flips over {n_steps} steps x {B * V} rows: {flips}")
+
+
+def _torch_nar_transition(code, vis_mask, pred_prob, pred_id, table, mask_feat, n_next):
+    """imggen_model.py:238-243 then :209-218 of the next iteration, with torch ops."""
+    B, V, F = code.shape
+    code = torch.where(vis_mask.view(B, V, 1).bool(), table[pred_id], code)
+    nxt = torch.zeros(B, V, dtype=torch.long, device=code.device)
+    if n_next > 0:
+        _, lowest = pred_prob.topk(n_next, dim=1, largest=False)
+        nxt.scatter_(1, lowest, 1)
+    code = torch.where(nxt.view(B, V, 1).bool(), mask_feat.view(1, 1, -1), code)
+    return code, nxt.to(torch.uint8)
+
+
+@pytest.mark.parametrize("B,n_next", [(1, 0), (3, 1), (32, 16), (32, 48), (5, 64)])
+def test_device_nar_transition_equals_topk_scatter_where(sampler, B, n_next):
+    """a17 index work (topk + scatter_ + where + embedding gather) on the device: bit-exact against the torch
+    statements on tie-free probabilities; on exact ties the lower cell index ranks first (documented rule)."""
+    g, m, ids = sampler
+    gen = torch.Generator().manual_seed(B * 100 + n_next)
+    V, F = 64, D.feat_dim
+    code0 = torch.randn(B, V, F, generator=gen).cuda()
+    vis_mask = (torch.rand(B, V, generator=gen) < 0.5).to(torch.uint8).cuda()
+    prob = torch.rand(B, V, generator=gen).cuda()
+    assert all(len(set(r.tolist())) == V for r in prob.cpu())           # tie-free
+    pid = torch.randint(0, D.num_clusters, (B, V), generator=gen).cuda()
+    want_code, want_mask = _torch_nar_transition(code0, vis_mask, prob, pid, m.vis_emb.weight, m.mask_feat, n_next)
+    code, mask = code0.clone(), vis_mask.clone()
+    m._nar_update(code, mask, prob, pid, n_next)
+    assert torch.equal(mask, want_mask) and torch.equal(code, want_code)
+    # ties: all-equal probabilities → the first n_next cells
+    flat = torch.full((B, V), 0.25, device="cuda")
+    code, mask = code0.clone(), vis_mask.clone()
+    m._nar_update(code, mask, flat, pid, n_next)
+    assert mask[:, :n_next].all() and not mask[:, n_next:].any()
+    # initial state: every cell masked, code = mask_feat
+    m._nar_update(code, mask, None, None, V)
+    assert mask.all() and torch.equal(code, m.mask_feat.view(1, 1, -1).expand(B, V, F))
+
+
+def test_device_ar_transition_equals_reference_statements(sampler):
+    """imggen_model.py:140-153 (confidence order) and :137-139 (fixed position) against torch ops."""
+    from xlxmert_b200 import _lib
+    g, m, ids = sampler
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(5)
+    B, V, F = 7, 64, D.feat_dim
+    code = torch.randn(B, V, F, generator=gen).cuda()
+    vis_mask = torch.ones(B, V, dtype=torch.uint8, device="cuda")
+    visited = (torch.rand(B, V, generator=gen) < 0.3).to(torch.uint8).cuda()
+    prob = torch.rand(B, V, generator=gen).cuda()
+    pid = torch.randint(0, D.num_clusters, (B, V), generator=gen).cuda()
+    table = m.vis_emb.weight
+    # torch statements
+    masked = prob.masked_fill(visited.bool(), -10000)
+    _, top = masked.topk(1, dim=1, largest=True)
+    upd = torch.zeros(B, V, dtype=torch.long, device="cuda").scatter_(1, top, 1)
+    want_code = torch.where(upd.view(B, V, 1).bool(), table[pid], code)
+    want_vis = vis_mask.clone().long().scatter_(1, top, 0).to(torch.uint8)
+    want_visited = visited.clone().long().scatter_(1, top, 1).to(torch.uint8)
+    c, vm, vs = code.clone(), vis_mask.clone(), visited.clone()
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check("ar", lib.xlx_sampler_ar_update(c.data_ptr(), vm.data_ptr(), vs.data_ptr(), prob.data_ptr(), pid.data_ptr(),
+                                               table.data_ptr(), B, V, F, -1, s))
+    assert torch.equal(c, want_code) and torch.equal(vm, want_vis) and torch.equal(vs, want_visited)
+    # fixed position 11, then masking it again
+    c, vm = code.clone(), vis_mask.clone()
+    _lib.check("ar", lib.xlx_sampler_ar_update(c.data_ptr(), vm.data_ptr(), None, None, pid.data_ptr(), table.data_ptr(),
+                                               B, V, F, 11, s))
+    want = code.clone()
+    want[:, 11] = table[pid[:, 11]]
+    assert torch.equal(c, want) and int(vm[:, 11].sum()) == 0 and int(vm.sum()) == B * (V - 1)
+    _lib.check("remask", lib.xlx_sampler_remask_cell(c.data_ptr(), vm.data_ptr(), m.mask_feat.data_ptr(), B, V, F, 11, s))
+    assert torch.equal(c[:, 11], m.mask_feat.view(1, -1).expand(B, F)) and bool(vm.all())
+
+
+def test_fused_argmax_epilogue_equals_materialised_logits(sampler):
+    """K4: predict() takes softmax(2).max(2) straight from the logits GEMM's accumulators (row statistics per tile +
+    merge) — the [M, 10000] logits are never written.  Must equal torch's softmax/max over the materialised logits of
+    the same head: indices bit-exact (same accumulators, same first-index rule), probabilities to fp32 rounding."""
+    g, m, ids = sampler
+    gen = torch.Generator().manual_seed(9)
+    for rows in (1, 64, 2048, 777):
+        h = torch.randn(rows, D.hidden, generator=gen).cuda()
+        logits = m.obj_predict_head(h, out_keys=["obj"])["obj"]
+        p_ref, i_ref = torch.softmax(logits, dim=-1).max(dim=-1)
+        p, i = m.obj_predict_head.predict(h)
+        assert torch.equal(i, i_ref), rows
+        assert float((p - p_ref).abs().max()) <= 2e-6 * float(p_ref.max()), rows

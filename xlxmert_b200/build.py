@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libxlxmert_b200.so")
 GEMM_TEST = os.path.join(LIBDIR, "gemm_test")     # standalone tcgen05-GEMM probe (csrc/gemm_test.cu), run by tests/test_gemm_probe.py
-SOURCES = ["gemm_sm100.cu", "kernels.cu", "attention.cu", "encoder.cu", "heads.cu", "generator.cu", "optim.cu", "kmeans.cu", "inputs.cu"]
+SOURCES = ["gemm_sm100.cu", "kernels.cu", "attention.cu", "encoder.cu", "heads.cu", "generator.cu", "optim.cu", "kmeans.cu", "inputs.cu", "sampler.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

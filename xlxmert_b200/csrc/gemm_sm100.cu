@@ -427,6 +427,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
       }
+      // row-statistics epilogue state (thread = row domain): running max, Σ exp(x − max), first index of the max
+      float rs_m = -INFINITY, rs_s = 0.f;
+      int rs_arg = 0x7fffffff;
       for (int c = half; c <= last_c; c += EPI_WARPS / 4) {
         uint32_t r[EPI_COLS];
         tmem_ld_32x16(taddr + c * EPI_COLS, r);
@@ -437,6 +440,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
           if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
         }
         if (P.debug & 1) continue;
+        if (P.epi.rowstat) {
+          // this thread holds columns nb … nb+15 of its own row: fold them into the running statistics
+          const int nb = n0 + c * EPI_COLS;
+          float v[EPI_COLS];
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < EPI_COLS; ++j) {
+            const int col = nb + j;
+            float x = __uint_as_float(r[j]) * P.epi.alpha;
+            if (col < P.epi.rowstat_cols) {
+              if (P.epi.bias) x += __ldg(P.epi.bias + col);
+            } else {
+              x = -INFINITY;
+            }
+            v[j] = x;
+            cm = fmaxf(cm, x);
+          }
+          if (cm > rs_m) {           // strictly greater: an equal value later in the row never replaces the first index
+            int a = 0;
+#pragma unroll
+            for (int j = EPI_COLS - 1; j >= 0; --j) a = (v[j] == cm) ? j : a;
+            rs_s *= expf(rs_m - cm);      // exp(−inf) = 0 on the first chunk
+            rs_m = cm;
+            rs_arg = nb + a;
+          }
+          if (rs_m > -INFINITY) {
+#pragma unroll
+            for (int j = 0; j < EPI_COLS; ++j) rs_s += expf(v[j] - rs_m);
+          }
+          continue;
+        }
         const int wsw = (lane >> 1) & 3;
 #pragma unroll
         for (int g = 0; g < EPI_COLS / 4; ++g)
@@ -505,6 +539,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
           }
         }
         __syncwarp();
+      }
+      if (P.epi.rowstat) {
+        const int row = m0 + q * 32 + lane;
+        if (row < P.M) {
+          const int slots = P.tiles_n * (EPI_WARPS / 4);
+          float* o = P.epi.rowstat + (static_cast<size_t>(row) * slots + (n0 / P.BN) * (EPI_WARPS / 4) + half) * 3;
+          o[0] = rs_m; o[1] = rs_s; o[2] = __int_as_float(rs_arg);
+        }
       }
     }
   }
@@ -932,6 +974,10 @@ int tma_map_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t 
                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   return make_map(out, ptr, inner, outer, ld, box_inner, box_outer, swz);
 }
+int gemm_rowstat_slots(int N) {
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);      // launch_bk's tile width (XLX_GEMM_BN must not be forced)
+  return ((N + BN - 1) / BN) * (EPI_WARPS / 4);
+}
 // splits · tiles ≤ 2 · #SMs and every tile is ≤ 128 × 256 outputs
 size_t gemm_splitk_ws_floats() { return static_cast<size_t>(2 * 148) * BM * 256; }
 
@@ -982,6 +1028,9 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream) {
   if (E.colsum_part && ((E.flags & (EPI_GELU | EPI_TANH | EPI_RELU | EPI_GELU_GRAD)) || p.splitk_ws)) return -1;
   if ((E.flags & EPI_MUL) && !E.u_in && !E.u_in16) return -1;
   if (E.addend_hi && !E.addend_lo) return -1;
+  if (E.rowstat && (E.out_f32 || E.out_hi || E.out_u || E.out_u16 || E.colsum_part || p.splitk_ws || E.flags ||
+                    E.rowstat_cols < 1 || E.rowstat_cols > p.N || getenv("XLX_GEMM_BN")))
+    return -1;
   return launch_bk<32>(p, stream);
 }
 

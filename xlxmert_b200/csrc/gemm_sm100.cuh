@@ -51,6 +51,13 @@ struct GemmEpilogue {
   // Optional column sums of the final values (a bias gradient for free): every epilogue warp writes the sums over its
   // 32 rows, colsum_part[(m / 32), n] with m / 32 < 4·ceil(M/128); reduce the rows with colsum_finish (fixed order).
   float* colsum_part = nullptr;
+  // Optional per-row soft-max statistics INSTEAD of any output (the sampler's softmax(logits).max(-1),
+  // tasks/imggen_model.py:232-235, without ever writing the [M, classes] logits): every epilogue warp folds the columns
+  // it reads of a tile (after alpha and bias) into (max, Σ exp(x − max), first index of the max) and writes them to
+  // rowstat[(row · slots + slot) · 3 + {0,1,2}] (index stored as int bits), slot = n_tile · 4 + warp-of-quadrant,
+  // slots = gemm_rowstat_slots(N).  Columns ≥ rowstat_cols (padding) are ignored.  Finish with rowstat_merge().
+  float* rowstat = nullptr;
+  int rowstat_cols = 0;
   int ld_addend = 0, ld_u = 0, ld_out = 0, ld_split = 0;
   int flags = 0;
   float alpha = 1.0f;               // v = alpha * acc before bias
@@ -88,6 +95,8 @@ struct GemmProblem {
   size_t splitk_ws_floats = 0;
 };
 size_t gemm_splitk_ws_floats();
+// number of partial (max, sumexp, argmax) triples per row a rowstat epilogue writes for an N-column GEMM
+int gemm_rowstat_slots(int N);
 // Cached 2-D TMA descriptor of a row-major bf16 matrix [outer, inner] with leading dimension ld (elements) and a
 // box of box_inner × box_outer elements; swizzle_bytes ∈ {0, 32, 64, 128}.  0 on success.
 int tma_map_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,

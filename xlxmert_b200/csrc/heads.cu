@@ -56,7 +56,7 @@ HeadPrep head_prep_layout(const HeadDims& h, void* base) {
 
 struct HeadWs {
   Split x, t, feat, dlogits, dfeat, du;
-  float *u, *g, *mean, *rstd, *logits, *lse, *rowloss, *stats, *dt, *dg, *part, *dbc, *splitk;
+  float *u, *g, *mean, *rstd, *logits, *lse, *rowloss, *stats, *dt, *dg, *part, *dbc, *splitk, *rowstat;
   size_t bytes;
 };
 HeadWs head_ws_layout(const HeadDims& h, int M, void* base) {
@@ -86,6 +86,7 @@ HeadWs head_ws_layout(const HeadDims& h, int M, void* base) {
   w.part = b.f32(pe);
   w.dbc = b.f32(Cp);
   w.splitk = b.f32(gemm_splitk_ws_floats());
+  w.rowstat = b.f32(m * gemm_rowstat_slots(h.Cp) * 3);
   w.bytes = b.total();
   return w;
 }
@@ -127,6 +128,17 @@ int head_fwd(const HeadDims& h, const float* const* params, const void* prep_bas
     e.bias = params[5]; e.out_f32 = feat_out; e.ld_out = F; e.out_hi = w.feat.hi; e.out_lo = w.feat.lo; e.ld_split = F;
     XLX_TRY(gemm_linear(passes, st, w.t, M, H, p.wf, F, e));
     dec_in = w.feat; Kc = F;
+  }
+  if (pred_prob && pred_id && !logits_out && !labels) {
+    // sampler step (tasks/imggen_model.py:228-235): softmax(logits).max(-1) straight from the accumulators — the
+    // [M, classes] logits are never written; per-tile partial statistics (12 B per row and quarter tile) are merged
+    static const bool fused = [] { const char* e = getenv("XLX_FUSED_ARGMAX"); return !(e && e[0] == '0'); }();
+    if (fused && !getenv("XLX_GEMM_BN")) {
+      GemmEpilogue e;
+      e.bias = p.bc; e.rowstat = w.rowstat; e.rowstat_cols = C;
+      XLX_TRY(gemm_linear(passes, st, dec_in, M, Kc, p.wc, Cp, e, C));
+      return rowstat_merge(w.rowstat, M, gemm_rowstat_slots(Cp), pred_prob, pred_id, st);
+    }
   }
   {
     GemmEpilogue e;

@@ -262,6 +262,36 @@ softmax_argmax_kernel(const float* __restrict__ logits, int ld, int C, float* pr
   (void)s_v;
 }
 
+// warp per row over the partial statistics of a rowstat GEMM epilogue
+__global__ void rowstat_merge_kernel(const float* __restrict__ rs, int M, int slots, float* prob, int64_t* id) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* p = rs + static_cast<size_t>(row) * slots * 3;
+  float mx = -INFINITY;
+  for (int i = lane; i < slots; i += 32) mx = fmaxf(mx, __ldg(p + 3 * i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  int best = 0x7fffffff;
+  for (int i = lane; i < slots; i += 32) {
+    const float m = __ldg(p + 3 * i), s = __ldg(p + 3 * i + 1);
+    const float w = expf(m - mx);                    // 0 for an empty partial (m = −inf)
+    sum += s * w;
+    if (w == 1.0f) best = min(best, __float_as_int(__ldg(p + 3 * i + 2)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  }
+  if (lane == 0) {
+    prob[row] = 1.0f / sum;
+    id[row] = best;
+  }
+}
+
 // thread per row, C ≤ 8
 __global__ void small_ce_kernel(const float* __restrict__ logits, int M, int C, const int64_t* __restrict__ labels,
                                 int64_t ignore, float* rowloss, const float* __restrict__ stats,
@@ -756,6 +786,11 @@ int softmax_argmax(const float* logits, int ld, int M, int C, float* prob, int64
   if (ld % 4) return -2;
   if (M < 1 || C < 1) return -21;
   softmax_argmax_kernel<<<M, CE_T, 0, s>>>(logits, ld, C, prob, id);
+  return launch_rc();
+}
+int rowstat_merge(const float* rowstat, int M, int slots, float* prob, int64_t* id, cudaStream_t s) {
+  if (M < 1 || slots < 1) return -21;
+  launch_pdl(rowstat_merge_kernel, dim3((M + 7) / 8), dim3(256), 0, s, rowstat, M, slots, prob, id);
   return launch_rc();
 }
 int small_ce_fwd(const float* logits, int M, int C, const int64_t* labels, int64_t ignore_index, float* rowloss,

@@ -75,6 +75,14 @@ int ce_bwd(const float* logits, int ld, int M, int C, int Cp, const int64_t* lab
 // (tasks/imggen_model.py:232-235).
 int softmax_argmax(const float* logits, int ld, int M, int C, float* prob, int64_t* id, cudaStream_t s);
 
+// Finish of a GEMM row-statistics epilogue (gemm_sm100.cuh: GemmEpilogue::rowstat): rowstat [M, slots, 3] partial
+// (max, Σ exp(x − max), first index of the max) → prob[m] = softmax(row).max() = 1 / Σ_j exp(x_j − max), id[m] = its index.
+// Index rule = softmax_argmax's (torch.max over the PROBABILITIES, first index): among the partial maxima whose
+// probability rounds to the row maximum's (expf(m_p − max) == 1.0f) the lowest index wins.  Identical to the
+// materialised kernel unless two DISTINCT logits of a row lie within 2^-25 of its maximum inside one partial — which
+// fp32 spacing rules out whenever max|logit| ≥ 1.
+int rowstat_merge(const float* rowstat, int M, int slots, float* prob, int64_t* id, cudaStream_t s);
+
 // Same loss for a tiny class count (C ≤ 8, row stride C): rowloss/stats as ce_fwd; dlogits fp32 [M,C].
 int small_ce_fwd(const float* logits, int M, int C, const int64_t* labels, int64_t ignore_index, float* rowloss,
                  float* stats, cudaStream_t s);

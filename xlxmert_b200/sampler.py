@@ -2,8 +2,9 @@
 
 Same attributes (``bert``, ``obj_predict_head``, ``mask_feat``, ``vis_emb``, ``G``), same ``set_visual_embedding`` /
 ``set_image_generator`` / ``denorm`` and the two samplers with the reference's keywords.  Every encoder pass, the
-cluster head with its fused ``softmax(2).max(2)`` and the generator run in ``libxlxmert_b200.so``; the loop itself
-stays host-driven exactly like the reference (SURVEY.md §8f ranks moving it on device as the next step).
+cluster head with ``softmax(2).max(2)`` fused into the logits GEMM, the loop transitions (confidence ranking, re-masking,
+centroid gather — the reference's ``topk`` / ``scatter_`` / ``where`` / ``vis_emb``) and the generator run in
+``libxlxmert_b200.so``; the host only computes the schedule, nothing is read back between steps.
 
 ``sentences`` may be a list of strings (needs a tokenizer: pass one to the constructor — the reference downloads
 ``unc-nlp/lxmert-base-uncased``, impossible offline) or an already tokenised ``LongTensor [B, L]``.
@@ -121,13 +122,36 @@ class B200ImggenModel(nn.Module):
         torch.cuda.current_stream().synchronize()
         return pin.clone()
 
+    # -- device-side loop transitions (csrc/sampler.cu) --------------------------------------------------------------
+    def _nar_update(self, code, vis_mask, pred_prob, pred_id, n_mask_next):
+        """topk(largest=False) + scatter_ + the two torch.where of imggen_model.py:209-218,238-243 in one kernel."""
+        from . import _lib
+        B, V, F = code.shape
+        rc = _lib.load().xlx_sampler_nar_update(
+            code.data_ptr(), vis_mask.data_ptr(), None if pred_prob is None else pred_prob.data_ptr(),
+            None if pred_id is None else pred_id.data_ptr(), self.vis_emb.weight.data_ptr(), self._mask_feat32().data_ptr(),
+            B, V, F, n_mask_next, vis_mask.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check("xlx_sampler_nar_update", rc)
+
+    def _mask_feat32(self):
+        mf = self.mask_feat.detach()
+        return mf if (mf.dtype == torch.float32 and mf.is_contiguous()) else mf.float().contiguous()
+
+    def _check_device(self, input_ids):
+        if not input_ids.is_cuda or self.vis_emb is None or not self.vis_emb.weight.is_cuda:
+            raise RuntimeError("B200ImggenModel samples on CUDA (sm_100a) only — move the model and its visual "
+                               "embedding to the GPU; there is no CPU fallback")
+
     # -- samplers ------------------------------------------------------------------------------------
     @torch.no_grad()
     def sample_image_NAR(self, sentences, max_text_length=20, n_steps=None, return_intermediate=False,
                          return_codes=False, cache_language=True, cuda_graph=False):
-        """Mask-predict sampling with linear decay (imggen_model.py:169-257)."""
+        """Mask-predict sampling with linear decay (imggen_model.py:169-257).  The loop body never returns to the host:
+        encoder pass → cluster head with the soft-max / arg-max fused into the logits GEMM → one transition kernel
+        (re-masking by confidence rank + centroid gather); only the schedule ``n_mask`` is host arithmetic."""
         self.eval()
         input_ids = self._input_ids(sentences, max_text_length)
+        self._check_device(input_ids)
         B, dev = input_ids.shape[0], input_ids.device
         grid_size, code_dim = 8, self.dims.feat_dim
         n_grids = grid_size ** 2
@@ -137,24 +161,23 @@ class B200ImggenModel(nn.Module):
         intermediate_imgs = []
         pred_prob = pred_code_id = None
         lang = self.bert.language_stack(input_ids, input_ids > 0) if cache_language else None
+        code = torch.empty(B, n_grids, code_dim, device=dev, dtype=torch.float32)
+        vis_mask = torch.empty(B, n_grids, dtype=torch.uint8, device=dev)
+        self._nar_update(code, vis_mask, None, None, n_grids)          # i = 0: every cell masked (:204-206,215-218)
         for i in range(n_steps):
-            n_mask = int((n_steps - i) / n_steps * n_grids)
-            if i == 0:
-                vis_mask = torch.ones(B, n_grids, dtype=torch.long, device=dev)
-                code = torch.zeros(B, n_grids, code_dim, device=dev)
-            else:
-                _, lowest_arg = pred_prob.topk(n_mask, dim=1, largest=False)
-                vis_mask = torch.zeros(B, n_grids, dtype=torch.long, device=dev)
-                vis_mask.scatter_(1, lowest_arg, 1)
-            m = vis_mask.view(B, n_grids, 1).bool()
-            code = torch.where(m, self.mask_feat.view(1, 1, -1).to(code.dtype), code)
             if cuda_graph and lang is not None:
                 pred_prob, pred_code_id = self._graph_predict(input_ids, code, visual_pos, lang)
             else:
                 pred_prob, pred_code_id = self._predict(input_ids, code, visual_pos, lang)
-            code = torch.where(m, self.vis_emb(pred_code_id), code)
+            # cells masked in this step take their predicted centroid; the next step's mask = the n_mask least confident
+            n_next = int((n_steps - (i + 1)) / n_steps * n_grids) if i + 1 < n_steps else 0
             if return_intermediate:
-                intermediate_imgs.append(self._decode(code, B, code_dim, grid_size))
+                # the reference decodes the fully predicted grid of every step, before re-masking
+                full = code.clone()
+                keep = vis_mask.clone()
+                self._nar_update(full, keep, pred_prob, pred_code_id, 0)
+                intermediate_imgs.append(self._decode(full, B, code_dim, grid_size))
+            self._nar_update(code, vis_mask, pred_prob, pred_code_id, n_next)
         if return_intermediate:
             return intermediate_imgs
         if return_codes:
@@ -166,8 +189,10 @@ class B200ImggenModel(nn.Module):
                         position_confidence=True, n_steps=None, seed=None, return_intermediate=False,
                         return_codes=False, cache_language=True):
         """One grid cell per step (imggen_model.py:49-167): random, raster (TLBR) or highest-confidence order."""
+        from . import _lib
         self.eval()
         input_ids = self._input_ids(sentences, max_text_length)
+        self._check_device(input_ids)
         B, dev = input_ids.shape[0], input_ids.device
         grid_size, code_dim = 8, self.dims.feat_dim
         n_grids = grid_size ** 2
@@ -183,32 +208,29 @@ class B200ImggenModel(nn.Module):
                 extra = list(range(n_steps - n_grids))
                 (random.Random(seed) if seed is not None else random).shuffle(extra)
                 positions = extra + positions
-        if position_confidence:
-            visited = torch.zeros(B, n_grids, device=dev)
-        vis_mask = torch.ones(B, n_grids, dtype=torch.long, device=dev)
-        code = torch.zeros(B, n_grids, code_dim, device=dev)
-        current = None
+        lib = _lib.load()
+        code = torch.empty(B, n_grids, code_dim, device=dev, dtype=torch.float32)
+        vis_mask = torch.empty(B, n_grids, dtype=torch.uint8, device=dev)
+        visited = torch.zeros(B, n_grids, dtype=torch.uint8, device=dev)
+        self._nar_update(code, vis_mask, None, None, n_grids)          # every cell masked, code = mask_feat (:95-99)
+        table, mf = self.vis_emb.weight, self._mask_feat32()
+        pred_prob = pred_code_id = None
         lang = self.bert.language_stack(input_ids, input_ids > 0) if cache_language else None
         for i in range(n_steps):
+            stream = torch.cuda.current_stream().cuda_stream
+            position = -1                                              # confidence order: chosen on the device
             if position_random:
-                current = positions.pop() % n_grids
-                vis_mask[:, current] = 1
+                position = positions.pop() % n_grids
+                _lib.check("xlx_sampler_remask_cell",
+                           lib.xlx_sampler_remask_cell(code.data_ptr(), vis_mask.data_ptr(), mf.data_ptr(), B, n_grids,
+                                                       code_dim, position, stream))
             elif position_TLBR:
-                current = i
-            code = torch.where(vis_mask.view(B, n_grids, 1).bool(), self.mask_feat.view(1, 1, -1).to(code.dtype), code)
+                position = i
             pred_prob, pred_code_id = self._predict(input_ids, code, visual_pos, lang)
-            if position_TLBR or position_random:
-                update_mask = torch.zeros(B, n_grids, dtype=torch.bool, device=dev)
-                update_mask[:, current] = True
-                vis_mask[:, current] = 0
-            else:
-                masked = pred_prob.masked_fill(visited.bool(), -10000)
-                _, top_arg = masked.topk(1, dim=1, largest=True)
-                update_mask = torch.zeros(B, n_grids, dtype=torch.long, device=dev)
-                update_mask.scatter_(1, top_arg, 1)
-                vis_mask.scatter_(1, top_arg, 0)
-                visited.scatter_(1, top_arg, 1)
-            code = torch.where(update_mask.view(B, n_grids, 1).bool(), self.vis_emb(pred_code_id), code)
+            _lib.check("xlx_sampler_ar_update",
+                       lib.xlx_sampler_ar_update(code.data_ptr(), vis_mask.data_ptr(), visited.data_ptr(),
+                                                 pred_prob.data_ptr(), pred_code_id.data_ptr(), table.data_ptr(), B,
+                                                 n_grids, code_dim, position, stream))
             if return_intermediate:
                 intermediate_imgs.append(self._decode(code, B, code_dim, grid_size))
         if return_intermediate:
