@@ -65,10 +65,56 @@ def extended_mask(attention_mask: Tensor, dtype) -> Tensor:
     return (1.0 - m) * torch.finfo(dtype).min
 
 
+# ---- dropout (training mode) -----------------------------------------------------------------------
+# The reference's training forward applies nn.Dropout at HF:189,212 (embeddings), :236,262-266 (attention
+# probabilities), :282,286 / :344,348 (dropout(dense(x)) before the residual add) and :474,482 (visual feature
+# encoder).  The masks themselves are random; what the oracle pins is the ARITHMETIC around them: a test installs a
+# provider that returns, per site, the multiplier tensor (0 or 1/(1−p)) — materialised from the product's own
+# counter-based generator (xlx_dropout_mask, site numbering of csrc/dropout.cuh) — and every dropout call below
+# multiplies by it, exactly like nn.Dropout does with its own mask.  Without a provider: eval / p = 0.
+_DROP_PROVIDER = None
+
+
+class dropout_masks:
+    """``with dropout_masks(provider): ...`` — ``provider(site: int, kind: 'hidden'|'probs', shape) -> Tensor | None``."""
+
+    def __init__(self, provider):
+        self.provider = provider
+
+    def __enter__(self):
+        global _DROP_PROVIDER
+        self.prev, _DROP_PROVIDER = _DROP_PROVIDER, self.provider
+        return self
+
+    def __exit__(self, *exc):
+        global _DROP_PROVIDER
+        _DROP_PROVIDER = self.prev
+        return False
+
+
+def _drop(x: Tensor, site: Optional[int], kind: str) -> Tensor:
+    if _DROP_PROVIDER is None or site is None:
+        return x
+    m = _DROP_PROVIDER(site, kind, tuple(x.shape))
+    return x if m is None else x * m.to(x.dtype)
+
+
+def site_probs(att_block: int, direction: int = 0) -> int:
+    return 16 + 4 * att_block + direction
+
+
+def site_att_out(att_block: int) -> int:
+    return 16 + 4 * att_block + 2
+
+
+def site_ffn_out(n_att: int, ffn_block: int) -> int:
+    return 16 + 4 * n_att + ffn_block
+
+
 # ---- attention blocks ---------------------------------------------------------------------------
 
 def attention(sd: SD, hidden: Tensor, ctx: Tensor, mask: Optional[Tensor], heads: int,
-              return_probs: bool = False):
+              return_probs: bool = False, drop_site: Optional[int] = None):
     """``LxmertAttention.forward`` (HF:238-274): per-head ``softmax(QKᵀ/√d + mask)·V``."""
     B, Sq, H = hidden.shape
     Sk = ctx.shape[1]
@@ -80,58 +126,78 @@ def attention(sd: SD, hidden: Tensor, ctx: Tensor, mask: Optional[Tensor], heads
     if mask is not None:
         s = s + mask                                      # additive mask after scaling (HF:258-259)
     p = torch.softmax(s, dim=-1)
-    o = (p @ v).permute(0, 2, 1, 3).reshape(B, Sq, H)     # merge heads (HF:268-271)
+    o = (_drop(p, drop_site, "probs") @ v).permute(0, 2, 1, 3).reshape(B, Sq, H)   # dropout(probs)·V, merge heads (HF:262-271)
     return (o, p) if return_probs else o
 
 
-def attention_output(sd: SD, x: Tensor, residual: Tensor) -> Tensor:
-    """``LxmertAttentionOutput`` / ``LxmertOutput`` (HF:277-288, 339-350): ``LN(W·x + b + residual)``."""
-    return layer_norm(linear(x, sd["dense.weight"], sd["dense.bias"]) + residual,
-                      sd["LayerNorm.weight"], sd["LayerNorm.bias"])
+def attention_output(sd: SD, x: Tensor, residual: Tensor, drop_site: Optional[int] = None,
+                     drop_mask: Optional[Tensor] = None) -> Tensor:
+    """``LxmertAttentionOutput`` / ``LxmertOutput`` (HF:277-288, 339-350): ``LN(dropout(W·x + b) + residual)``."""
+    y = linear(x, sd["dense.weight"], sd["dense.bias"])
+    y = y * drop_mask.to(y.dtype) if drop_mask is not None else _drop(y, drop_site, "hidden")
+    return layer_norm(y + residual, sd["LayerNorm.weight"], sd["LayerNorm.bias"])
 
 
-def self_att_layer(sd: SD, x: Tensor, mask, heads: int) -> Tensor:
-    """``LxmertSelfAttentionLayer`` (HF:306-324)."""
-    return attention_output(sub(sd, "output"), attention(sub(sd, "self"), x, x, mask, heads), x)
+def self_att_layer(sd: SD, x: Tensor, mask, heads: int, blk: Optional[int] = None) -> Tensor:
+    """``LxmertSelfAttentionLayer`` (HF:306-324).  ``blk``: attention-block number (dropout sites)."""
+    ps, os_ = (None, None) if blk is None else (site_probs(blk), site_att_out(blk))
+    return attention_output(sub(sd, "output"), attention(sub(sd, "self"), x, x, mask, heads, drop_site=ps), x, os_)
 
 
-def cross_att_layer(sd: SD, x: Tensor, ctx: Tensor, ctx_mask, heads: int) -> Tensor:
+def cross_att_layer(sd: SD, x: Tensor, ctx: Tensor, ctx_mask, heads: int, probs_site: Optional[int] = None,
+                    out_mask: Optional[Tensor] = None) -> Tensor:
     """``LxmertCrossAttentionLayer`` (HF:291-303); the residual is the query-side input."""
-    return attention_output(sub(sd, "output"), attention(sub(sd, "att"), x, ctx, ctx_mask, heads), x)
+    return attention_output(sub(sd, "output"), attention(sub(sd, "att"), x, ctx, ctx_mask, heads, drop_site=probs_site),
+                            x, drop_mask=out_mask)
 
 
-def ffn(sd_inter: SD, sd_out: SD, x: Tensor) -> Tensor:
+def ffn(sd_inter: SD, sd_out: SD, x: Tensor, drop_site: Optional[int] = None) -> Tensor:
     """``LxmertIntermediate`` + ``LxmertOutput`` (HF:327-350)."""
     h = gelu_erf(linear(x, sd_inter["dense.weight"], sd_inter["dense.bias"]))
-    return attention_output(sd_out, h, x)
+    return attention_output(sd_out, h, x, drop_site)
 
 
-def layer(sd: SD, x: Tensor, mask, heads: int) -> Tensor:
-    """``LxmertLayer`` (HF:353-366): self-attention block then FFN block."""
-    a = self_att_layer(sub(sd, "attention"), x, mask, heads)
-    return ffn(sub(sd, "intermediate"), sub(sd, "output"), a)
+def layer(sd: SD, x: Tensor, mask, heads: int, blk: Optional[int] = None, n_att: int = 0) -> Tensor:
+    """``LxmertLayer`` (HF:353-366): self-attention block then FFN block (``blk`` = its number in both plans)."""
+    a = self_att_layer(sub(sd, "attention"), x, mask, heads, blk)
+    return ffn(sub(sd, "intermediate"), sub(sd, "output"), a, None if blk is None else site_ffn_out(n_att, blk))
 
 
-def xlayer(sd: SD, lang: Tensor, lmask, vis: Tensor, vmask, heads: int):
+def xlayer(sd: SD, lang: Tensor, lmask, vis: Tensor, vmask, heads: int, att_blk: Optional[int] = None,
+           ffn_blk: Optional[int] = None, n_att: int = 0):
     """``LxmertXLayer`` (HF:369-457): cross (shared weights, both directions read the layer
-    inputs, HF:385-406) → self (HF:408-412) → FFN (HF:414-423)."""
+    inputs, HF:385-406) → self (HF:408-412) → FFN (HF:414-423).  ``att_blk`` / ``ffn_blk``: number of this layer's
+    first attention / FFN block (cross, lang-self, vis-self / lang, vis) for the dropout sites; the product runs the
+    shared cross-attention output layer once over [language rows | vision rows], so ONE site covers both."""
     xa = sub(sd, "visual_attention")
-    l1 = cross_att_layer(xa, lang, vis, vmask, heads)
-    v1 = cross_att_layer(xa, vis, lang, lmask, heads)
-    l2 = self_att_layer(sub(sd, "lang_self_att"), l1, lmask, heads)
-    v2 = self_att_layer(sub(sd, "visn_self_att"), v1, vmask, heads)
-    l3 = ffn(sub(sd, "lang_inter"), sub(sd, "lang_output"), l2)
-    v3 = ffn(sub(sd, "visn_inter"), sub(sd, "visn_output"), v2)
+    lm = vm = None
+    ps0 = ps1 = None
+    if att_blk is not None and _DROP_PROVIDER is not None:
+        B, L, H = lang.shape
+        V = vis.shape[1]
+        joint = _DROP_PROVIDER(site_att_out(att_blk), "hidden", (B * (L + V), H))
+        if joint is not None:
+            lm, vm = joint[:B * L].reshape(B, L, H), joint[B * L:].reshape(B, V, H)
+        ps0, ps1 = site_probs(att_blk, 0), site_probs(att_blk, 1)
+    l1 = cross_att_layer(xa, lang, vis, vmask, heads, ps0, lm)
+    v1 = cross_att_layer(xa, vis, lang, lmask, heads, ps1, vm)
+    sl = None if att_blk is None else att_blk + 1
+    sv = None if att_blk is None else att_blk + 2
+    l2 = self_att_layer(sub(sd, "lang_self_att"), l1, lmask, heads, sl)
+    v2 = self_att_layer(sub(sd, "visn_self_att"), v1, vmask, heads, sv)
+    l3 = ffn(sub(sd, "lang_inter"), sub(sd, "lang_output"), l2, None if ffn_blk is None else site_ffn_out(n_att, ffn_blk))
+    v3 = ffn(sub(sd, "visn_inter"), sub(sd, "visn_output"), v2,
+             None if ffn_blk is None else site_ffn_out(n_att, ffn_blk + 1))
     return l3, v3
 
 
 def visual_feature_encoder(sd: SD, feats: Tensor, pos: Tensor) -> Tensor:
-    """``LxmertVisualFeatureEncoder`` (HF:476-484): ``(LN(Wf·x) + LN(Wp·pos)) / 2``."""
+    """``LxmertVisualFeatureEncoder`` (HF:476-484): ``dropout((LN(Wf·x) + LN(Wp·pos)) / 2)``."""
     x = layer_norm(linear(feats, sd["visn_fc.weight"], sd["visn_fc.bias"]),
                    sd["visn_layer_norm.weight"], sd["visn_layer_norm.bias"])
     y = layer_norm(linear(pos, sd["box_fc.weight"], sd["box_fc.bias"]),
                    sd["box_layer_norm.weight"], sd["box_layer_norm.bias"])
-    return (x + y) / 2
+    return _drop((x + y) / 2, 1, "hidden")
 
 
 def encoder(sd: SD, lang: Tensor, lmask, feats: Tensor, pos: Tensor, vmask=None, *, heads: int,
@@ -140,21 +206,23 @@ def encoder(sd: SD, lang: Tensor, lmask, feats: Tensor, pos: Tensor, vmask=None,
     layer's output: 9 L + 5 X language states, 5 R + 5 X vision states."""
     vis = visual_feature_encoder(sub(sd, "visn_fc"), feats, pos)
     lang_states, vis_states = [], []
+    n_att = n_l + n_r + 3 * n_x           # block numbering of the dropout sites (csrc/dropout.cuh)
     for i in range(n_l):
-        lang = layer(sub(sd, f"layer.{i}"), lang, lmask, heads)
+        lang = layer(sub(sd, f"layer.{i}"), lang, lmask, heads, i, n_att)
         lang_states.append(lang)
     for i in range(n_r):
-        vis = layer(sub(sd, f"r_layers.{i}"), vis, vmask, heads)
+        vis = layer(sub(sd, f"r_layers.{i}"), vis, vmask, heads, n_l + i, n_att)
         vis_states.append(vis)
     for i in range(n_x):
-        lang, vis = xlayer(sub(sd, f"x_layers.{i}"), lang, lmask, vis, vmask, heads)
+        lang, vis = xlayer(sub(sd, f"x_layers.{i}"), lang, lmask, vis, vmask, heads, n_l + n_r + 3 * i,
+                           n_l + n_r + 2 * i, n_att)
         lang_states.append(lang)
         vis_states.append(vis)
     return lang_states, vis_states
 
 
 def embeddings(sd: SD, input_ids: Tensor, token_type_ids: Optional[Tensor] = None) -> Tensor:
-    """``LxmertEmbeddings`` (HF:191-214), dropout omitted (eval / p = 0)."""
+    """``LxmertEmbeddings`` (HF:191-214); dropout (HF:212) only under ``dropout_masks``."""
     B, L = input_ids.shape
     if token_type_ids is None:
         token_type_ids = torch.zeros_like(input_ids)
@@ -165,7 +233,7 @@ def embeddings(sd: SD, input_ids: Tensor, token_type_ids: Optional[Tensor] = Non
     e = (emb(input_ids, sd["word_embeddings.weight"], padding_idx=0)
          + emb(pos, sd["position_embeddings.weight"], padding_idx=0)
          + emb(token_type_ids, sd["token_type_embeddings.weight"], padding_idx=0))
-    return layer_norm(e, sd["LayerNorm.weight"], sd["LayerNorm.bias"])
+    return _drop(layer_norm(e, sd["LayerNorm.weight"], sd["LayerNorm.bias"]), 0, "hidden")
 
 
 def pooler(sd: SD, lang: Tensor) -> Tensor:

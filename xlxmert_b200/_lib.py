@@ -24,11 +24,27 @@ class XlxDims(C.Structure):
                    d.x_layers, d.ln_eps)
 
 
+class XlxDropout(C.Structure):
+    """``xlx_dropout`` (include/xlxmert_b200.h): probabilities + the step's seed."""
+    _fields_ = [("p_hidden", C.c_float), ("p_attn", C.c_float), ("seed", C.c_uint64)]
+
+
 class XlxError(RuntimeError):
     def __init__(self, fn: str, code: int):
         self.code = code
         msg = load().xlx_strerror(code).decode()
         super().__init__(f"{fn} failed with code {code}: {msg}")
+
+
+def step_dropout(module, dims):
+    """``xlx_dropout`` for one training-mode forward of ``module`` (None when dropout is off): probabilities from the
+    dims, a fresh 62-bit seed drawn on the HOST from torch's default CPU generator (reproducible under
+    ``torch.manual_seed``, no device sync)."""
+    import torch
+    if not module.training or (dims.hidden_dropout <= 0.0 and dims.attention_dropout <= 0.0):
+        return None
+    seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    return XlxDropout(float(dims.hidden_dropout), float(dims.attention_dropout), seed)
 
 
 def lib_path() -> str:
@@ -59,9 +75,14 @@ def _sig(lib):
     lib.xlx_encoder_workspace_bytes.restype = SZ
     lib.xlx_encoder_workspace_bytes.argtypes = [D, I32, I32, I32, I32]
     lib.xlx_encoder_fwd.restype = I32
-    lib.xlx_encoder_fwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, SZ, I32, I32, P]
+    DR = C.POINTER(XlxDropout)
+    lib.xlx_encoder_fwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, SZ, I32, I32, DR, P]
+    lib.xlx_dropout_mask.restype = I32
+    lib.xlx_dropout_mask.argtypes = [C.c_uint64, C.c_uint32, C.c_float, I32, I64, I32, P, P]
+    lib.xlx_dropout_site.restype = I32
+    lib.xlx_dropout_site.argtypes = [D, I32, I32, I32]
     lib.xlx_encoder_bwd.restype = I32
-    lib.xlx_encoder_bwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, SZ, I32, I32, P]
+    lib.xlx_encoder_bwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, SZ, I32, I32, DR, P]
     lib.xlx_encoder_grad_stage_range.restype = I32
     lib.xlx_encoder_grad_stage_range.argtypes = [D, I32, C.POINTER(I64), C.POINTER(I64)]
     PP = P
@@ -70,9 +91,9 @@ def _sig(lib):
     lib.xlx_embeddings_scratch_bytes.restype = SZ
     lib.xlx_embeddings_scratch_bytes.argtypes = [D, I32, I32]
     lib.xlx_embeddings_fwd.restype = I32
-    lib.xlx_embeddings_fwd.argtypes = [D, I32, I32, P, P, PP, P, P, P]
+    lib.xlx_embeddings_fwd.argtypes = [D, I32, I32, P, P, PP, P, P, DR, P]
     lib.xlx_embeddings_bwd.restype = I32
-    lib.xlx_embeddings_bwd.argtypes = [D, I32, I32, I32, I32, I32, P, P, PP, P, P, PP, P, SZ, P]
+    lib.xlx_embeddings_bwd.argtypes = [D, I32, I32, I32, I32, I32, P, P, PP, P, P, PP, P, SZ, DR, P]
     lib.xlx_pooler_workspace_bytes.restype = SZ
     lib.xlx_pooler_workspace_bytes.argtypes = [D, I32]
     lib.xlx_pooler_fwd.restype = I32

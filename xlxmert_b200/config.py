@@ -24,6 +24,11 @@ class LxmertDims:
     type_vocab: int = 2
     num_clusters: int = 10000
     ln_eps: float = 1e-12
+    #: nn.Dropout probabilities of a TRAINING-mode forward (HF config hidden_dropout_prob / attention_probs_dropout_prob,
+    #: both 0.1 in the reference's run — ``dims_from_hf_config`` copies them).  Dims built by hand default to 0: the
+    #: parity tests and the bench compare against the reference at p = 0.
+    hidden_dropout: float = 0.0
+    attention_dropout: float = 0.0
 
     @property
     def head_dim(self) -> int:

@@ -102,10 +102,11 @@ __device__ __forceinline__ float quad_max(float v) {
 // ---- forward ------------------------------------------------------------------------------------------
 // maps: [0] Q hi, [1] Q lo, [2] K hi, [3] K lo, [4] V hi, [5] V lo — 2-D maps over the split [rows, ld] matrices
 struct FwdMaps { CUtensorMap m[6]; };
+template <bool DROP>     // compile-time: the inference / p = 0 instantiation carries no dropout code or registers
 __global__ void __launch_bounds__(AT)
 attn_fwd_mma_kernel(const __grid_constant__ FwdMaps maps, int qcol, int kcol, int vcol,
                     const float* __restrict__ mask, int heads, int Sq, int Sk, bf16* ctx_hi, bf16* ctx_lo,
-                    float* ctx_f32, int ld_ctx, float* probs) {
+                    float* ctx_f32, int ld_ctx, float* probs, const DropSite drop) {
   extern __shared__ uint8_t smem_attn_raw[];
   __shared__ __align__(8) uint64_t bar;
   bf16* Qh = reinterpret_cast<bf16*>(smem_attn_raw + ((1024u - (smem_u32(smem_attn_raw) & 1023u)) & 1023u));
@@ -189,6 +190,12 @@ attn_fwd_mma_kernel(const __grid_constant__ FwdMaps maps, int qcol, int kcol, in
         if (i0 < Sq) { if (j < Sk) pr[i0 * Sk + j] = s[nt][0]; if (j + 1 < Sk) pr[i0 * Sk + j + 1] = s[nt][1]; }
         if (i1 < Sq) { if (j < Sk) pr[i1 * Sk + j] = s[nt][2]; if (j + 1 < Sk) pr[i1 * Sk + j + 1] = s[nt][3]; }
       }
+      if (DROP) {   // dropout(attention_probs) (HF:262-266): P·V below sees P ∘ mask / (1 − p)
+        const int j = nt * 8 + 2 * t;
+        const size_t rbase = (static_cast<size_t>(b) * heads + h) * Sq;
+        const float2 m0 = drop_prob2(drop, rbase + i0, Sk, j), m1 = drop_prob2(drop, rbase + i1, Sk, j);
+        s[nt][0] *= m0.x; s[nt][1] *= m0.y; s[nt][2] *= m1.x; s[nt][3] *= m1.y;
+      }
     }
   }
   // O = P·V: the score accumulators of two adjacent n-tiles are exactly one A fragment of the next product
@@ -249,10 +256,11 @@ attn_fwd_mma_kernel(const __grid_constant__ FwdMaps maps, int qcol, int kcol, in
 // dP = dO·Vᵀ;  dS = P ∘ (dP − rowsum(P ∘ dP)) / 8;  dQ = dS·K;  dV = Pᵀ·dO;  dK = dSᵀ·Q.
 // maps: Q, K, V, dO (hi, lo each)
 struct BwdMaps { CUtensorMap m[8]; };
+template <bool DROP>
 __global__ void __launch_bounds__(AT)
 attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, int vcol, int ocol,
                     const float* __restrict__ probs, int heads, int Sq, int Sk, bf16* dq_hi, bf16* dq_lo, bf16* dk_hi,
-                    bf16* dk_lo, bf16* dv_hi, bf16* dv_lo, int ld_d) {
+                    bf16* dk_lo, bf16* dv_hi, bf16* dv_lo, int ld_d, const DropSite drop) {
   extern __shared__ uint8_t smem_attn_raw[];
   __shared__ __align__(8) uint64_t bar;
   bf16* Qh = reinterpret_cast<bf16*>(smem_attn_raw + ((1024u - (smem_u32(smem_attn_raw) & 1023u)) & 1023u));
@@ -287,10 +295,12 @@ attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, in
 
   // phase 1 (warp = 16 query rows): dP = dO·Vᵀ, dS, dQ = dS·K, all in registers
   float dp[8][4], p[8][4];
+  float pm[DROP ? 8 : 1][4];      // P ∘ dropout mask
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
     p[nt][0] = p[nt][1] = p[nt][2] = p[nt][3] = 0.f;
+    if (DROP) pm[DROP ? nt : 0][0] = pm[DROP ? nt : 0][1] = pm[DROP ? nt : 0][2] = pm[DROP ? nt : 0][3] = 0.f;
   }
   const bool rows_live = r0 < 16 * nq16;
   if (rows_live) {
@@ -319,6 +329,20 @@ attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, in
           const int j = nt * 8 + 2 * t + e;
           p[nt][e] = (i0 < Sq && j < Sk) ? __ldg(pr + i0 * Sk + j) : 0.f;
           p[nt][2 + e] = (i1 < Sq && j < Sk) ? __ldg(pr + i1 * Sk + j) : 0.f;
+        }
+        if (DROP) {
+          // forward: ctx = (P ∘ m)·V with m = mask / (1 − p).  dp holds d(P ∘ m) = dO·Vᵀ → dP = dp ∘ m; the P tile
+          // phase 2 contracts with dO (dV = (P ∘ m)ᵀ·dO) is the dropped one: pm below.
+          const int j = nt * 8 + 2 * t;
+          const size_t rbase = (static_cast<size_t>(b) * heads + h) * Sq;
+          const float2 m0 = drop_prob2(drop, rbase + i0, Sk, j), m1 = drop_prob2(drop, rbase + i1, Sk, j);
+          dp[nt][0] *= m0.x; dp[nt][1] *= m0.y; dp[nt][2] *= m1.x; dp[nt][3] *= m1.y;
+          constexpr int kD = DROP ? 1 : 0;
+          pm[nt * kD][0] = p[nt][0] * m0.x; pm[nt * kD][1] = p[nt][1] * m0.y;
+          pm[nt * kD][2] = p[nt][2] * m1.x; pm[nt * kD][3] = p[nt][3] * m1.y;
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
           dot0 += p[nt][e] * dp[nt][e];
           dot1 += p[nt][2 + e] * dp[nt][2 + e];
         }
@@ -379,9 +403,10 @@ attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, in
       if (nt < 2 * nk16) {
         const int j = nt * 8 + 2 * t;
         uint32_t hi, lo;
-        split2(p[nt][0], p[nt][1], hi, lo);
+        constexpr int kD = DROP ? 1 : 0;
+        split2(DROP ? pm[nt * kD][0] : p[nt][0], DROP ? pm[nt * kD][1] : p[nt][1], hi, lo);
         *reinterpret_cast<uint32_t*>(Ph + swz(i0, j)) = hi; *reinterpret_cast<uint32_t*>(Pl + swz(i0, j)) = lo;
-        split2(p[nt][2], p[nt][3], hi, lo);
+        split2(DROP ? pm[nt * kD][2] : p[nt][2], DROP ? pm[nt * kD][3] : p[nt][3], hi, lo);
         *reinterpret_cast<uint32_t*>(Ph + swz(i1, j)) = hi; *reinterpret_cast<uint32_t*>(Pl + swz(i1, j)) = lo;
         split2(dp[nt][0], dp[nt][1], hi, lo);
         *reinterpret_cast<uint32_t*>(Sh + swz(i0, j)) = hi; *reinterpret_cast<uint32_t*>(Sl + swz(i0, j)) = lo;
@@ -456,15 +481,17 @@ bool operand_ok(const AttnOperand& o) {
 }  // namespace
 
 int attention_fwd(AttnOperand q, AttnOperand k, AttnOperand v, const float* mask, int B, int heads, int Sq, int Sk,
-                  Split ctx, float* ctx_f32, int ld_ctx, float* probs, cudaStream_t s) {
+                  Split ctx, float* ctx_f32, int ld_ctx, float* probs, cudaStream_t s, DropSite drop) {
   if (Sq < 1 || Sk < 1 || Sq > 64 || Sk > 64) return -5;
   if (!operand_ok(q) || !operand_ok(k) || !operand_ok(v) || (ld_ctx % 8)) return -2;
   if (!B) return 0;
   constexpr size_t smem = 6 * TT * sizeof(bf16) + 1024;
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
     set = true;
   }
@@ -473,23 +500,29 @@ int attention_fwd(AttnOperand q, AttnOperand k, AttnOperand v, const float* mask
   if ((rc = operand_maps(&maps.m[0], &maps.m[1], q))) return rc;
   if ((rc = operand_maps(&maps.m[2], &maps.m[3], k))) return rc;
   if ((rc = operand_maps(&maps.m[4], &maps.m[5], v))) return rc;
-  launch_pdl(attn_fwd_mma_kernel, dim3(heads, B), dim3(AT), smem, s, maps, q.col, k.col, v.col, mask, heads, Sq, Sk, ctx.hi, ctx.lo,
-                                                       ctx_f32, ld_ctx, probs);
+  if (drop.threshold)
+    launch_pdl(attn_fwd_mma_kernel<true>, dim3(heads, B), dim3(AT), smem, s, maps, q.col, k.col, v.col, mask, heads, Sq, Sk,
+               ctx.hi, ctx.lo, ctx_f32, ld_ctx, probs, drop);
+  else
+    launch_pdl(attn_fwd_mma_kernel<false>, dim3(heads, B), dim3(AT), smem, s, maps, q.col, k.col, v.col, mask, heads, Sq, Sk,
+               ctx.hi, ctx.lo, ctx_f32, ld_ctx, probs, drop);
   count_aux_launch();
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }
 
 int attention_bwd(AttnOperand dctx, AttnOperand q, AttnOperand k, AttnOperand v, const float* probs, int B, int heads,
-                  int Sq, int Sk, Split dq, Split dk, Split dv, int ld_d, cudaStream_t s) {
+                  int Sq, int Sk, Split dq, Split dk, Split dv, int ld_d, cudaStream_t s, DropSite drop) {
   if (Sq < 1 || Sk < 1 || Sq > 64 || Sk > 64) return -5;
   if (!operand_ok(q) || !operand_ok(k) || !operand_ok(v) || !operand_ok(dctx) || (ld_d % 2)) return -2;
   if (!B) return 0;
   constexpr size_t smem = 8 * TT * sizeof(bf16) + 1024;
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
     set = true;
   }
@@ -499,8 +532,12 @@ int attention_bwd(AttnOperand dctx, AttnOperand q, AttnOperand k, AttnOperand v,
   if ((rc = operand_maps(&maps.m[2], &maps.m[3], k))) return rc;
   if ((rc = operand_maps(&maps.m[4], &maps.m[5], v))) return rc;
   if ((rc = operand_maps(&maps.m[6], &maps.m[7], dctx))) return rc;
-  launch_pdl(attn_bwd_mma_kernel, dim3(heads, B), dim3(AT), smem, s, maps, q.col, k.col, v.col, dctx.col, probs, heads, Sq, Sk, dq.hi,
-                                                       dq.lo, dk.hi, dk.lo, dv.hi, dv.lo, ld_d);
+  if (drop.threshold)
+    launch_pdl(attn_bwd_mma_kernel<true>, dim3(heads, B), dim3(AT), smem, s, maps, q.col, k.col, v.col, dctx.col, probs, heads,
+               Sq, Sk, dq.hi, dq.lo, dk.hi, dk.lo, dv.hi, dv.lo, ld_d, drop);
+  else
+    launch_pdl(attn_bwd_mma_kernel<false>, dim3(heads, B), dim3(AT), smem, s, maps, q.col, k.col, v.col, dctx.col, probs, heads,
+               Sq, Sk, dq.hi, dq.lo, dk.hi, dk.lo, dv.hi, dv.lo, ld_d, drop);
   count_aux_launch();
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);

@@ -118,6 +118,7 @@ struct FfnSave {
 };
 struct BwdScratch {
   Split dy_s;                // LayerNorm-input gradient [M, H]: GEMM operand and residual-path addend
+  Split dy_m;                // the same gradient ∘ dropout mask of the dense output (training with dropout): GEMM operand
   Split dqkv, du, dctx;
   float* part = nullptr;     // partial column sums (bias / LayerNorm-affine gradients)
   float* splitk = nullptr;   // split-K partial sums of the weight-gradient GEMMs
@@ -267,6 +268,7 @@ Plan make_plan(const xlx_dims* d, int B, int L, int V, bool training, void* base
       const size_t M = i ? Ml : Mt;
       c.dctx = b.split(M * H);
       c.dy_s = b.split(M * H);
+      c.dy_m = b.split(M * H);
       c.dqkv = b.split(M * 3 * H);
       c.du = b.split((i ? Ml : Mmax) * I);
       c.splitk = b.f32(gemm_splitk_ws_floats());
@@ -287,6 +289,10 @@ struct Run {
   cudaStream_t st;
   const float* lmask;
   const float* vmask;
+  DropoutCfg drop;     // all-zero unless a training forward / its backward was given an xlx_dropout
+  int n_att = 0;       // attention blocks in the plan (site numbering)
+  DropSite hidden_site(uint32_t site) const { return make_site(drop.seed, site, drop.p_hidden); }
+  DropSite probs_site(int blk, int dir) const { return make_site(drop.seed, site_probs(blk, dir), drop.p_attn); }
 };
 
 int linear(const Run& r, Split x, int M, int K, Split w, int N, const GemmEpilogue& e) {
@@ -330,10 +336,11 @@ int att_self_fwd(const Run& r, int blk, int S, const float* mask, float* out_f32
   e.bias = w.bqkv; e.out_hi = a.qkv.hi; e.out_lo = a.qkv.lo; e.ld_split = 3 * H;
   XLX_TRY(linear(r, a.in, M, H, w.wqkv, 3 * H, e));
   XLX_TRY(attention_fwd(qkv_op(a.qkv, M, H, 0), qkv_op(a.qkv, M, H, 1), qkv_op(a.qkv, M, H, 2), mask, p.B, p.heads, S, S,
-                        a.ctx, nullptr, H, a.probs, r.st));
+                        a.ctx, nullptr, H, a.probs, r.st, r.probs_site(blk, 0)));
   GemmEpilogue o;
   o.bias = P(r, s0 + 7); o.addend_hi = a.in.hi; o.addend_lo = a.in.lo; o.ld_addend = H;
   o.out_f32 = a.y; o.ld_out = H;
+  o.drop = r.hidden_site(site_att_out(blk));
   XLX_TRY(linear(r, a.ctx, M, H, w.wo, H, o));
   return ln_tail(r, a.y, M, P(r, s0 + 8), P(r, s0 + 9), a.out, out_f32, a.mean, a.rstd);
 }
@@ -351,13 +358,14 @@ int att_cross_fwd(const Run& r, int blk) {
   const Split ql = a.qkv, qv = rows(a.qkv, p.Ml, H3);     // language rows / vision rows
   // language queries over vision keys/values (mask = visual attention mask, normally none)
   XLX_TRY(attention_fwd(qkv_op(ql, p.Ml, H, 0), qkv_op(qv, p.Mv, H, 1), qkv_op(qv, p.Mv, H, 2), r.vmask, p.B, p.heads,
-                        p.L, p.V, a.ctx, nullptr, H, a.probs, r.st));
+                        p.L, p.V, a.ctx, nullptr, H, a.probs, r.st, r.probs_site(blk, 0)));
   // vision queries over language keys/values (mask = language attention mask)
   XLX_TRY(attention_fwd(qkv_op(qv, p.Mv, H, 0), qkv_op(ql, p.Ml, H, 1), qkv_op(ql, p.Ml, H, 2), r.lmask, p.B, p.heads,
-                        p.V, p.L, rows(a.ctx, p.Ml, H), nullptr, H, a.probs2, r.st));
+                        p.V, p.L, rows(a.ctx, p.Ml, H), nullptr, H, a.probs2, r.st, r.probs_site(blk, 1)));
   GemmEpilogue o;
   o.bias = P(r, s0 + 7); o.addend_hi = a.in.hi; o.addend_lo = a.in.lo; o.ld_addend = H;
   o.out_f32 = a.y; o.ld_out = H;
+  o.drop = r.hidden_site(site_att_out(blk));
   XLX_TRY(linear(r, a.ctx, p.Mt, H, w.wo, H, o));
   return ln_tail(r, a.y, p.Mt, P(r, s0 + 8), P(r, s0 + 9), a.out, nullptr, a.mean, a.rstd);
 }
@@ -374,6 +382,7 @@ int ffn_fwd(const Run& r, int blk, float* out_f32) {
   GemmEpilogue o;
   o.bias = P(r, s0 + 3); o.addend_hi = f.in.hi; o.addend_lo = f.in.lo; o.ld_addend = H;
   o.out_f32 = f.y; o.ld_out = H;
+  o.drop = r.hidden_site(site_ffn_out(r.n_att, blk));
   XLX_TRY(linear(r, f.h, M, I, w.w2, H, o));
   return ln_tail(r, f.y, M, P(r, s0 + 4), P(r, s0 + 5), f.out, out_f32, f.mean, f.rstd);
 }
@@ -391,11 +400,16 @@ struct Bwd {
 
 // LayerNorm backward of a "dense → +residual → LayerNorm" tail; also yields the dense bias gradient (slot_g − 1),
 // which is the column sum of the LayerNorm-input gradient.
+// With dropout on the dense output (`site`), dy_s keeps the plain gradient (residual path) and bw.sc->dy_m receives
+// dy ∘ mask — the operand of the dense layer's weight / input gradients; *dense_dy tells the caller which one to use.
 int ln_tail_bwd(const Bwd& bw, const float* dout, const float* y, int slot_g, const float* mean, const float* rstd,
-                int M, float* dy, Split dy_s) {
+                int M, float* dy, Split dy_s, uint32_t site, Split* dense_dy) {
   const Run& r = *bw.r;
   int nblk = 0;
-  XLX_TRY(layernorm_bwd(dout, 1.0f, y, P(r, slot_g), mean, rstd, M, r.plan.H, dy, dy_s, bw.sc->part, &nblk, r.st));
+  const DropSite ds = r.hidden_site(site);
+  *dense_dy = ds.threshold ? bw.sc->dy_m : dy_s;
+  XLX_TRY(layernorm_bwd(dout, 1.0f, y, P(r, slot_g), mean, rstd, M, r.plan.H, dy, dy_s, bw.sc->part, &nblk, r.st,
+                        DropSite(), ds, bw.sc->dy_m));
   float* outs[3] = {bw.G(slot_g), bw.G(slot_g + 1), bw.G(slot_g - 1)};
   return colsum_finish(bw.sc->part, 3, nblk, r.plan.H, outs, 0, r.st);
 }
@@ -407,12 +421,13 @@ int ffn_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
   const FfnSave& f = p.ffn[blk];
   const FfnW& w = r.prep.ffn[blk];
   const int s0 = ffn_slot(r.d, blk), H = p.H, I = p.I, M = f.M;
-  XLX_TRY(ln_tail_bwd(bw, dout, f.y, s0 + 4, f.mean, f.rstd, M, nullptr, c.dy_s));    // also dense bias grad (s0 + 3)
-  XLX_TRY(wgrad(r, c.splitk, c.dy_s, M, H, f.h, I, bw.G(s0 + 2)));
+  Split dyd;    // gradient wrt the dense output (= dy, or dy ∘ dropout mask)
+  XLX_TRY(ln_tail_bwd(bw, dout, f.y, s0 + 4, f.mean, f.rstd, M, nullptr, c.dy_s, site_ffn_out(r.n_att, blk), &dyd));  // + bias grad (s0 + 3)
+  XLX_TRY(wgrad(r, c.splitk, dyd, M, H, f.h, I, bw.G(s0 + 2)));
   GemmEpilogue e;   // du = (dy · W2) ∘ gelu'(u), the derivative was saved by the forward
   e.flags = EPI_MUL; e.u_in = f.u; e.ld_u = I; e.out_hi = c.du.hi; e.out_lo = c.du.lo; e.ld_split = I;
   e.colsum_part = c.part;   // the intermediate bias gradient = column sums of du, gathered by the same epilogue
-  XLX_TRY(dgrad(r, c.dy_s, M, H, w.w2_t, I, e));
+  XLX_TRY(dgrad(r, dyd, M, H, w.w2_t, I, e));
   {
     float* outs[1] = {bw.G(s0 + 1)};
     XLX_TRY(colsum_finish(c.part, 1, (M + 31) / 32, I, outs, 0, r.st));
@@ -432,11 +447,12 @@ int att_bwd_head(const Bwd& bw, int blk, const float* dout) {
   const AttSave& a = p.att[blk];
   const AttW& w = r.prep.att[blk];
   const int s0 = att_slot(r.d, blk), H = p.H, M = a.M;
-  XLX_TRY(ln_tail_bwd(bw, dout, a.y, s0 + 8, a.mean, a.rstd, M, nullptr, c.dy_s));    // also dense bias grad (s0 + 7)
-  XLX_TRY(wgrad(r, c.splitk, c.dy_s, M, H, a.ctx, H, bw.G(s0 + 6)));
+  Split dyd;
+  XLX_TRY(ln_tail_bwd(bw, dout, a.y, s0 + 8, a.mean, a.rstd, M, nullptr, c.dy_s, site_att_out(blk), &dyd));   // + bias grad (s0 + 7)
+  XLX_TRY(wgrad(r, c.splitk, dyd, M, H, a.ctx, H, bw.G(s0 + 6)));
   GemmEpilogue e;
   e.out_hi = c.dctx.hi; e.out_lo = c.dctx.lo; e.ld_split = H;
-  return dgrad(r, c.dy_s, M, H, w.wo_t, H, e);
+  return dgrad(r, dyd, M, H, w.wo_t, H, e);
 }
 int att_bwd_tail(const Bwd& bw, int blk, float* din) {
   const Run& r = *bw.r;
@@ -462,7 +478,7 @@ int att_self_bwd(const Bwd& bw, int blk, int S, const float* dout, float* din) {
   Split dq = c.dqkv, dk = c.dqkv, dv = c.dqkv;
   dk.hi += H; dk.lo += H; dv.hi += 2 * H; dv.lo += 2 * H;
   XLX_TRY(attention_bwd(mat_op(c.dctx, a.M, H), qkv_op(a.qkv, a.M, H, 0), qkv_op(a.qkv, a.M, H, 1),
-                        qkv_op(a.qkv, a.M, H, 2), a.probs, p.B, p.heads, S, S, dq, dk, dv, 3 * H, r.st));
+                        qkv_op(a.qkv, a.M, H, 2), a.probs, p.B, p.heads, S, S, dq, dk, dv, 3 * H, r.st, r.probs_site(blk, 0)));
   return att_bwd_tail(bw, blk, din);
 }
 int att_cross_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
@@ -478,11 +494,12 @@ int att_cross_bwd(const Bwd& bw, int blk, const float* dout, float* din) {
   auto col = [](Split s, int c) { s.hi += c; s.lo += c; return s; };
   // language queries: dQ → language rows, dK/dV → vision rows
   XLX_TRY(attention_bwd(mat_op(c.dctx, p.Ml, H), qkv_op(ql, p.Ml, H, 0), qkv_op(qv, p.Mv, H, 1), qkv_op(qv, p.Mv, H, 2),
-                        a.probs, p.B, p.heads, p.L, p.V, col(dl, 0), col(dvv, H), col(dvv, 2 * H), 3 * H, r.st));
+                        a.probs, p.B, p.heads, p.L, p.V, col(dl, 0), col(dvv, H), col(dvv, 2 * H), 3 * H, r.st,
+                        r.probs_site(blk, 0)));
   // vision queries: dQ → vision rows, dK/dV → language rows
   XLX_TRY(attention_bwd(mat_op(rows(c.dctx, p.Ml, H), p.Mv, H), qkv_op(qv, p.Mv, H, 0), qkv_op(ql, p.Ml, H, 1),
                         qkv_op(ql, p.Ml, H, 2), a.probs2, p.B, p.heads, p.V, p.L, col(dvv, 0), col(dl, H),
-                        col(dl, 2 * H), 3 * H, r.st));
+                        col(dl, 2 * H), 3 * H, r.st, r.probs_site(blk, 1)));
   return att_bwd_tail(bw, blk, din);
 }
 
@@ -566,6 +583,31 @@ const char* xlx_strerror(int32_t code) {
   }
 }
 
+int32_t xlx_dropout_mask(uint64_t seed, uint32_t site, float p, int32_t kind, int64_t rows, int32_t cols, float* out,
+                         void* stream) {
+  if (!out) return -24;
+  if (rows < 1 || cols < 1 || !(p >= 0.f && p < 1.f)) return -21;
+  XLX_TRY(ensure_device(out));
+  DropSite d = make_site(seed, site, p);
+  if (!d.threshold) { d.scale = 1.f; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return kind == 0 ? dropout_mask_hidden(d, static_cast<size_t>(rows), cols, out, st)
+                   : dropout_mask_probs(d, static_cast<size_t>(rows), cols, out, st);
+}
+int32_t xlx_dropout_site(const xlx_dims* d, int32_t what, int32_t block, int32_t direction) {
+  if (!dims_ok(d)) return -20;
+  const int n_att = d->l_layers + d->r_layers + 3 * d->x_layers, n_ffn = d->l_layers + d->r_layers + 2 * d->x_layers;
+  if (what == 0 || what == 1) {
+    if (block < 0 || block >= n_att || direction < 0 || direction > 1) return -1;
+    return static_cast<int32_t>(what == 0 ? site_probs(block, direction) : site_att_out(block));
+  }
+  if (what == 2) {
+    if (block < 0 || block >= n_ffn) return -1;
+    return static_cast<int32_t>(site_ffn_out(n_att, block));
+  }
+  return -1;
+}
+
 int64_t xlx_launch_count(void) { return gemm_launch_count() + aux_launch_count() + xlx_generator_launch_count() + xlx_optim_launch_count(); }
 int64_t xlx_gemm_launch_count(void) { return gemm_launch_count(); }
 void xlx_profile_gemm_begin(void) { gemm_timing_begin(); }
@@ -635,7 +677,7 @@ int32_t xlx_encoder_fwd(const xlx_dims* d, const float* const* params, const voi
                         int32_t V, const float* lang_in, const float* lang_mask, const float* visual_feats,
                         const float* visual_pos, const float* vis_mask, float* lang_out, float* vis_out,
                         float* lang_hidden, float* vis_hidden, void* workspace, size_t workspace_bytes,
-                        int32_t training, int32_t passes, void* stream) {
+                        int32_t training, int32_t passes, const xlx_dropout* dropout, void* stream) {
   XLX_TRY(check_common(d, B, L, V));
   if (!params || !prep || !lang_in || !visual_feats || !visual_pos || !lang_out || !vis_out || !workspace) return -24;
   if (passes != 1 && passes != 3) return -1;
@@ -643,6 +685,12 @@ int32_t xlx_encoder_fwd(const xlx_dims* d, const float* const* params, const voi
   Run r;
   r.d = d; r.params = params; r.passes = passes; r.st = static_cast<cudaStream_t>(stream);
   r.lmask = lang_mask; r.vmask = vis_mask;
+  if (dropout) {
+    if (!(dropout->p_hidden >= 0.f && dropout->p_hidden < 1.f && dropout->p_attn >= 0.f && dropout->p_attn < 1.f)) return -1;
+    if ((dropout->p_hidden > 0.f || dropout->p_attn > 0.f) && !training) return -1;   // the backward must replay it
+    r.drop.p_hidden = dropout->p_hidden; r.drop.p_attn = dropout->p_attn; r.drop.seed = dropout->seed;
+  }
+  r.n_att = d->l_layers + d->r_layers + 3 * d->x_layers;
   r.prep = prep_layout(d, const_cast<void*>(prep));
   r.plan = make_plan(d, B, L, V, training != 0, workspace);
   const Plan& p = r.plan;
@@ -670,7 +718,8 @@ int32_t xlx_encoder_fwd(const xlx_dims* d, const float* const* params, const voi
     XLX_TRY(layernorm_fwd(p.y2, P(r, 6), P(r, 7), d->ln_eps, Mv, H, 0.5f, nullptr, Split(), p.tbox,
                           p.training ? p.vstats + 2 * Mv : nullptr, p.training ? p.vstats + 3 * Mv : nullptr, r.st));
     XLX_TRY(layernorm_fwd(p.y1, P(r, 2), P(r, 3), d->ln_eps, Mv, H, 0.5f, p.tbox, p.vis0, nullptr,
-                          p.training ? p.vstats : nullptr, p.training ? p.vstats + Mv : nullptr, r.st));
+                          p.training ? p.vstats : nullptr, p.training ? p.vstats + Mv : nullptr, r.st,
+                          r.hidden_site(DROP_SITE_VISN)));      // dropout((x + y) / 2), HF:482
   }
   XLX_TRY(split_f32(lang_in, p.lang0, lh, rl.st));
 
@@ -714,7 +763,7 @@ int32_t xlx_encoder_fwd(const xlx_dims* d, const float* const* params, const voi
 int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const void* prep, int32_t B, int32_t L,
                         int32_t V, const float* visual_pos, const float* d_lang_out, const float* d_vis_out,
                         float* d_lang_in, float* d_visual_feats, float* grads, void* workspace,
-                        size_t workspace_bytes, int32_t passes, int32_t stages, void* stream) {
+                        size_t workspace_bytes, int32_t passes, int32_t stages, const xlx_dropout* dropout, void* stream) {
   XLX_TRY(check_common(d, B, L, V));
   if (!params || !prep || !visual_pos || !d_lang_in || !grads || !workspace) return -24;
   if (passes != 1 && passes != 3) return -1;
@@ -723,6 +772,11 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
   Run r;
   r.d = d; r.params = params; r.passes = passes; r.st = static_cast<cudaStream_t>(stream);
   r.lmask = nullptr; r.vmask = nullptr;
+  if (dropout) {
+    if (!(dropout->p_hidden >= 0.f && dropout->p_hidden < 1.f && dropout->p_attn >= 0.f && dropout->p_attn < 1.f)) return -1;
+    r.drop.p_hidden = dropout->p_hidden; r.drop.p_attn = dropout->p_attn; r.drop.seed = dropout->seed;
+  }
+  r.n_att = d->l_layers + d->r_layers + 3 * d->x_layers;
   r.prep = prep_layout(d, const_cast<void*>(prep));
   r.plan = make_plan(d, B, L, V, true, workspace);
   const Plan& p = r.plan;
@@ -799,13 +853,15 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
     const BwdScratch& c = p.sc[0];
     int nblk = 0;
     // box branch: d(0.5·LN_b(y2))
+    const DropSite vdrop = r.hidden_site(DROP_SITE_VISN);   // the forward dropped (x + y) / 2: both branches see dvis ∘ mask
     XLX_TRY(layernorm_bwd(dvis, 0.5f, p.y2, P(r, 6), p.vstats + 2 * Mv, p.vstats + 3 * Mv, Mv, H, p.dy2, Split(),
-                          c.part, &nblk, r.st));
+                          c.part, &nblk, r.st, vdrop));
     float* o2[2] = {bw.G(6), bw.G(7)};
     XLX_TRY(colsum_finish(c.part, 2, nblk, H, o2, 0, r.st));
     XLX_TRY(box_linear_bwd(p.dy2, visual_pos, Mv, H, c.part, bw.G(4), bw.G(5), r.st));
     // feature branch: d(0.5·LN_v(y1))
-    XLX_TRY(layernorm_bwd(dvis, 0.5f, p.y1, P(r, 2), p.vstats, p.vstats + Mv, Mv, H, nullptr, c.dy_s, c.part, &nblk, r.st));
+    XLX_TRY(layernorm_bwd(dvis, 0.5f, p.y1, P(r, 2), p.vstats, p.vstats + Mv, Mv, H, nullptr, c.dy_s, c.part, &nblk, r.st,
+                          vdrop));
     float* o1[3] = {bw.G(2), bw.G(3), bw.G(1)};      // LN affine grads + visn_fc bias grad (Σ_rows of the LN-input grad)
     XLX_TRY(colsum_finish(c.part, 3, nblk, H, o1, 0, r.st));
     XLX_TRY(wgrad(r, c.splitk, c.dy_s, Mv, H, p.feats, F, bw.G(0)));

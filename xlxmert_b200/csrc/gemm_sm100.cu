@@ -140,6 +140,10 @@ __device__ __forceinline__ float4 epilogue_vec4(const KParams& P, int row, int n
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
   }
+  if (ACT && E.drop.threshold) {
+    const float4 m = drop_hidden4(E.drop, static_cast<size_t>(row), P.N, n);
+    v[0] *= m.x; v[1] *= m.y; v[2] *= m.z; v[3] *= m.w;
+  }
   const bool has_u = (E.flags & (EPI_MUL | EPI_GELU_GRAD)) != 0;
   if (ACT && (E.flags & EPI_GELU_GRAD)) {
     v[0] *= gelu_erf_grad(in.a.x); v[1] *= gelu_erf_grad(in.a.y); v[2] *= gelu_erf_grad(in.a.z); v[3] *= gelu_erf_grad(in.a.w);
@@ -878,7 +882,7 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   // split-K: only for plain fp32-output GEMMs (weight gradients) whose tile count leaves most SMs idle
   P.splits = 1; P.kb_per_split = nkb; P.part = nullptr;
   const bool plain = p.epi.out_f32 && !p.epi.bias && !p.epi.addend && !p.epi.addend_hi && !p.epi.out_hi &&
-                     !p.epi.out_u && !(p.epi.flags & ~EPI_ACCUM) && p.epi.alpha == 1.0f;
+                     !p.epi.out_u && !(p.epi.flags & ~EPI_ACCUM) && p.epi.alpha == 1.0f && !p.epi.drop.threshold;
   static const int splitk_on = env_int("XLX_GEMM_SPLITK", 1);
   if (splitk_on && plain && p.splitk_ws && num_tiles * cta_per_item < num_sms) {
     // pick the split count whose work items fill whole waves of SMs best (ties → fewer splits)
@@ -926,7 +930,7 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     cudaEventRecord(tl.e0, stream);
   }
   {
-    const bool act = (p.epi.flags & (EPI_GELU | EPI_TANH | EPI_RELU | EPI_GELU_GRAD)) != 0;
+    const bool act = (p.epi.flags & (EPI_GELU | EPI_TANH | EPI_RELU | EPI_GELU_GRAD)) != 0 || p.epi.drop.threshold != 0;
     const int v = (P.a_mn ? 4 : 0) | (P.b_mn ? 2 : 0) | (P.nparts == 2 ? 1 : 0);
     int lrc = 0;
 #define XLX_LAUNCH(A, B, N)                                                                                   \
@@ -1025,7 +1029,9 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream) {
       ((E.out_u || E.u_in || E.out_u16 || E.u_in16) && (E.ld_u % 4)))
     return -2;
   if ((E.flags & EPI_GELU_GRAD) && !E.u_in) return -1;
-  if (E.colsum_part && ((E.flags & (EPI_GELU | EPI_TANH | EPI_RELU | EPI_GELU_GRAD)) || p.splitk_ws)) return -1;
+  if (E.colsum_part && ((E.flags & (EPI_GELU | EPI_TANH | EPI_RELU | EPI_GELU_GRAD)) || p.splitk_ws || E.drop.threshold))
+    return -1;
+  if (E.drop.threshold && (E.rowstat || p.conv.enabled)) return -1;
   if ((E.flags & EPI_MUL) && !E.u_in && !E.u_in16) return -1;
   if (E.addend_hi && !E.addend_lo) return -1;
   if (E.rowstat && (E.out_f32 || E.out_hi || E.out_u || E.out_u16 || E.colsum_part || p.splitk_ws || E.flags ||

@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dropout.cuh"
+
 namespace xlx {
 
 enum EpiFlags : int {
@@ -58,6 +60,10 @@ struct GemmEpilogue {
   // slots = gemm_rowstat_slots(N).  Columns ≥ rowstat_cols (padding) are ignored.  Finish with rowstat_merge().
   float* rowstat = nullptr;
   int rowstat_cols = 0;
+  // Optional dropout of the value after bias / activation and BEFORE the addends (LxmertAttentionOutput / LxmertOutput:
+  // dropout(dense(x)) + residual, HF:282-287,344-349).  The GEMM must span the whole [M, N] matrix the site covers
+  // (element index = row·N + col).  drop.threshold == 0: off.
+  DropSite drop;
   int ld_addend = 0, ld_u = 0, ld_out = 0, ld_split = 0;
   int flags = 0;
   float alpha = 1.0f;               // v = alpha * acc before bias

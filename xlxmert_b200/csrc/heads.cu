@@ -236,7 +236,7 @@ size_t xlx_embeddings_scratch_bytes(const xlx_dims* d, int32_t B, int32_t L) {
 
 int32_t xlx_embeddings_fwd(const xlx_dims* d, int32_t B, int32_t L, const int64_t* input_ids,
                            const int64_t* token_type_ids, const float* const* params, float* out, void* save,
-                           void* stream) {
+                           const xlx_dropout* dropout, void* stream) {
   if (!hidden_ok(d)) return -20;
   if (B < 1 || L < 1) return -21;
   if (!input_ids || !params || !out) return -24;
@@ -247,14 +247,19 @@ int32_t xlx_embeddings_fwd(const xlx_dims* d, int32_t B, int32_t L, const int64_
   EmbSave s = emb_layout(d, M, save);
   float* y = save ? s.y : out;
   XLX_TRY(embed_sum(input_ids, token_type_ids, params[0], params[1], params[2], M, L, H, y, st));
+  DropSite drop;
+  if (dropout && dropout->p_hidden > 0.f) {
+    if (!(dropout->p_hidden < 1.f) || !save) return -1;      // dropout is a training-forward thing
+    drop = make_site(dropout->seed, DROP_SITE_EMB, dropout->p_hidden);
+  }
   return layernorm_fwd(y, params[3], params[4], d->ln_eps, M, H, 1.0f, nullptr, Split(), out, save ? s.mean : nullptr,
-                       save ? s.rstd : nullptr, st);
+                       save ? s.rstd : nullptr, st, drop);
 }
 
 int32_t xlx_embeddings_bwd(const xlx_dims* d, int32_t B, int32_t L, int32_t vocab, int32_t max_pos,
                            int32_t type_vocab, const int64_t* input_ids, const int64_t* token_type_ids,
                            const float* const* params, const void* save, const float* d_out, float* const* grads,
-                           void* scratch, size_t scratch_bytes, void* stream) {
+                           void* scratch, size_t scratch_bytes, const xlx_dropout* dropout, void* stream) {
   if (!hidden_ok(d)) return -20;
   if (B < 1 || L < 1 || L > max_pos) return -21;
   if (!input_ids || !params || !save || !d_out || !grads || !scratch) return -24;
@@ -267,7 +272,9 @@ int32_t xlx_embeddings_bwd(const xlx_dims* d, int32_t B, int32_t L, int32_t voca
   float* dy = b.f32(static_cast<size_t>(M) * H);
   float* part = b.f32(3 * static_cast<size_t>(reduce_max_blocks()) * H);
   int nblk = 0;
-  XLX_TRY(layernorm_bwd(d_out, 1.0f, s.y, params[3], s.mean, s.rstd, M, H, dy, Split(), part, &nblk, st));
+  DropSite drop;
+  if (dropout && dropout->p_hidden > 0.f) drop = make_site(dropout->seed, DROP_SITE_EMB, dropout->p_hidden);
+  XLX_TRY(layernorm_bwd(d_out, 1.0f, s.y, params[3], s.mean, s.rstd, M, H, dy, Split(), part, &nblk, st, drop));
   float* o[2] = {grads[3], grads[4]};
   XLX_TRY(colsum_finish(part, 2, nblk, H, o, 0, st));
   XLX_CUDA(cudaMemsetAsync(grads[0], 0, static_cast<size_t>(vocab) * H * 4, st));

@@ -403,7 +403,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
               int M, float out_scale, const float* __restrict__ addend, bf16* hi, bf16* lo, float* out_f32,
-              float* mean, float* rstd) {
+              float* mean, float* rstd, const DropSite drop) {
   pdl_trigger();
   pdl_wait();
   constexpr int H = NV * 128;
@@ -444,6 +444,10 @@ ln_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma, cons
       const float4 a = __ldg(reinterpret_cast<const float4*>(addend + idx));
       o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
     }
+    if (drop.threshold) {     // dropout on the module output (embeddings HF:212, visual feature encoder HF:482)
+      const float4 m = drop_hidden4(drop, static_cast<size_t>(row), H, c4 * 4);
+      o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
+    }
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + idx) = o;
     if (hi) store_split4(hi, lo, idx, o);
   }
@@ -455,7 +459,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ dy, float dy_scale, const float* __restrict__ y,
               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, int M,
-              float* dx, bf16* dx_hi, bf16* dx_lo, float* part) {
+              float* dx, bf16* dx_hi, bf16* dx_lo, float* part, const DropSite drop_in, const DropSite drop_out,
+              bf16* dxm_hi, bf16* dxm_lo) {
   pdl_trigger();
   pdl_wait();
   constexpr int H = NV * 128;
@@ -478,6 +483,10 @@ ln_bwd_kernel(const float* __restrict__ dy, float dy_scale, const float* __restr
       const float4 yv = __ldg(py + c4);
       float4 d = pd[c4];
       d.x *= dy_scale; d.y *= dy_scale; d.z *= dy_scale; d.w *= dy_scale;
+      if (drop_in.threshold) {   // the forward dropped this LayerNorm's OUTPUT: the same mask gates its gradient
+        const float4 m = drop_hidden4(drop_in, static_cast<size_t>(row), H, c4 * 4);
+        d.x *= m.x; d.y *= m.y; d.z *= m.z; d.w *= m.w;
+      }
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
       xh[k] = make_float4((yv.x - mu) * r, (yv.y - mu) * r, (yv.z - mu) * r, (yv.w - mu) * r);
       dxh[k] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
@@ -496,6 +505,13 @@ ln_bwd_kernel(const float* __restrict__ dy, float dy_scale, const float* __restr
       const size_t idx = static_cast<size_t>(row) * H + (lane + 32 * k) * 4;
       if (dx) *reinterpret_cast<float4*>(dx + idx) = o;
       if (dx_hi) store_split4(dx_hi, dx_lo, idx, o);
+      if (drop_out.threshold) {
+        // the LayerNorm input was dropout(dense(x)) + residual: the residual path takes dx as is (above), the dense
+        // path — its weight / input gradients and its bias gradient (the column sums below) — takes dx ∘ mask
+        const float4 m = drop_hidden4(drop_out, static_cast<size_t>(row), H, (lane + 32 * k) * 4);
+        o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
+        if (dxm_hi) store_split4(dxm_hi, dxm_lo, idx, o);
+      }
       ds[k].x += o.x; ds[k].y += o.y; ds[k].z += o.z; ds[k].w += o.w;
     }
   }
@@ -839,21 +855,56 @@ int small_linear_bwd(const float* dy, const float* x, const float* W, int M, int
   }
 
 int layernorm_fwd(const float* y, const float* gamma, const float* beta, float eps, int M, int H, float out_scale,
-                  const float* addend, Split out, float* out_f32, float* mean, float* rstd, cudaStream_t s) {
+                  const float* addend, Split out, float* out_f32, float* mean, float* rstd, cudaStream_t s,
+                  DropSite drop) {
   if (!M) return 0;
   const int grid = (M + 7) / 8;
   XLX_LN_DISPATCH(ln_fwd_kernel, H, grid, y, gamma, beta, eps, M, out_scale, addend, out.hi, out.lo, out_f32, mean,
-                  rstd);
+                  rstd, drop);
   return launch_rc();
 }
 int layernorm_bwd(const float* dy, float dy_scale, const float* y, const float* gamma, const float* mean,
                   const float* rstd, int M, int H, float* dx, Split dx_split, float* part, int* nblk_out,
-                  cudaStream_t s) {
+                  cudaStream_t s, DropSite drop_in, DropSite drop_out, Split dx_masked) {
   int grid = (M + 7) / 8;
   if (grid > kMaxBlocks) grid = kMaxBlocks;
   if (grid < 1) grid = 1;
   *nblk_out = grid;
-  XLX_LN_DISPATCH(ln_bwd_kernel, H, grid, dy, dy_scale, y, gamma, mean, rstd, M, dx, dx_split.hi, dx_split.lo, part);
+  if (drop_out.threshold && !dx_masked.hi) return -24;
+  XLX_LN_DISPATCH(ln_bwd_kernel, H, grid, dy, dy_scale, y, gamma, mean, rstd, M, dx, dx_split.hi, dx_split.lo, part,
+                  drop_in, drop_out, dx_masked.hi, dx_masked.lo);
+  return launch_rc();
+}
+
+// ---- materialised dropout masks (test / debugging aid: the product kernels regenerate them on the fly) -----------
+__global__ void drop_mask_hidden_kernel(const DropSite d, size_t rows, int H, float* out) {
+  const size_t n4 = rows * H / 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t e = i * 4;
+    reinterpret_cast<float4*>(out)[i] = drop_hidden4(d, e / H, H, static_cast<int>(e % H));
+  }
+}
+__global__ void drop_mask_probs_kernel(const DropSite d, size_t rows, int Sk, float* out) {
+  const int pairs = (Sk + 1) >> 1;
+  const size_t n = rows * pairs;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / pairs;
+    const int j = static_cast<int>(i % pairs) * 2;
+    const float2 m = drop_prob2(d, r, Sk, j);
+    out[r * Sk + j] = m.x;
+    if (j + 1 < Sk) out[r * Sk + j + 1] = m.y;
+  }
+}
+int dropout_mask_hidden(DropSite d, size_t rows, int H, float* out, cudaStream_t s) {
+  if (!rows || H % 4) return -2;
+  drop_mask_hidden_kernel<<<grid_for(rows * H / 4, 256), 256, 0, s>>>(d, rows, H, out);
+  return launch_rc();
+}
+int dropout_mask_probs(DropSite d, size_t rows, int Sk, float* out, cudaStream_t s) {
+  if (!rows || Sk < 1) return -21;
+  drop_mask_probs_kernel<<<grid_for(rows * ((Sk + 1) / 2), 256), 256, 0, s>>>(d, rows, Sk, out);
   return launch_rc();
 }
 int colsum_finish(const float* part, int nvec, int nblk, int H, float* const* outs, int accumulate, cudaStream_t s) {

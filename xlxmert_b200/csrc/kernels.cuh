@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dropout.cuh"
 #include "pdl.cuh"
 
 namespace xlx {
@@ -97,13 +98,23 @@ int small_linear_bwd(const float* dy, const float* x, const float* W, int M, int
 
 // LayerNorm over the last axis (biased variance; HF modeling_lxmert.py:188,281,343 use eps 1e-12):
 //   o = out_scale · LN(y) + addend;   y [M,H] fp32 → split out and/or fp32 out; optionally saves mean / rstd.
+//   `drop` (optional): dropout applied to o (after the addend) — LxmertEmbeddings / LxmertVisualFeatureEncoder outputs.
 int layernorm_fwd(const float* y, const float* gamma, const float* beta, float eps, int M, int H, float out_scale,
-                  const float* addend, Split out, float* out_f32, float* mean, float* rstd, cudaStream_t s);
+                  const float* addend, Split out, float* out_f32, float* mean, float* rstd, cudaStream_t s,
+                  DropSite drop = DropSite());
 // dy [M,H]: upstream grad wrt the LN output (scaled by dy_scale); y: saved LN input; → dx fp32 and/or split,
 // plus partial column sums part[3, nblk, H] (dgamma, dbeta, Σ_rows dx); finish with colsum_finish.  dx may alias dy.
+// Dropout (training): `drop_in` gates the incoming dy with the mask the forward applied to this LayerNorm's output;
+// `drop_out` is the mask of a dropout(dense(x)) + residual producer of the LayerNorm INPUT: dx / dx_split keep the plain
+// gradient (residual path), dx_masked receives dx ∘ mask (the dense path's GEMM operand) and the third partial column
+// sum becomes Σ_rows dx ∘ mask (the dense bias gradient).
 int layernorm_bwd(const float* dy, float dy_scale, const float* y, const float* gamma, const float* mean,
                   const float* rstd, int M, int H, float* dx, Split dx_split, float* part, int* nblk_out,
-                  cudaStream_t s);
+                  cudaStream_t s, DropSite drop_in = DropSite(), DropSite drop_out = DropSite(),
+                  Split dx_masked = Split());
+// out[rows, H] / out[rows, Sk] = the multipliers (0 or 1/(1−p)) the fused kernels apply at a site (tests).
+int dropout_mask_hidden(DropSite d, size_t rows, int H, float* out, cudaStream_t s);
+int dropout_mask_probs(DropSite d, size_t rows, int Sk, float* out, cudaStream_t s);
 int reduce_max_blocks();  // upper bound on nblk for every partial-sum kernel here
 // out_v[H] = Σ_blk part[v, blk, H] for v < nvec (outs[v] may be null to skip); accumulate: out += instead of =
 int colsum_finish(const float* part, int nvec, int nblk, int H, float* const* outs, int accumulate, cudaStream_t s);
@@ -128,12 +139,13 @@ struct AttnOperand {
 };
 // mask: additive fp32 [B, Sk] or null.  Sq, Sk ≤ 64.  ctx: split and/or fp32 rows [b·Sq + i, h·64 + d] with leading
 // dimension ld_ctx.  probs (optional) [B, heads, Sq, Sk] fp32.
+// `drop` (training): dropout on the probabilities before P·V (HF:262-266); `probs` always receives the UNdropped P.
 int attention_fwd(AttnOperand q, AttnOperand k, AttnOperand v, const float* mask, int B, int heads, int Sq, int Sk,
-                  Split ctx, float* ctx_f32, int ld_ctx, float* probs, cudaStream_t s);
+                  Split ctx, float* ctx_f32, int ld_ctx, float* probs, cudaStream_t s, DropSite drop = DropSite());
 // Backward: dctx = gradient wrt ctx (an operand like q); writes dq (rows b·Sq + i), dk / dv (rows b·Sk + j), columns
 // h·64 + d, as split matrices with leading dimension ld_d.
 int attention_bwd(AttnOperand dctx, AttnOperand q, AttnOperand k, AttnOperand v, const float* probs, int B, int heads,
-                  int Sq, int Sk, Split dq, Split dk, Split dv, int ld_d, cudaStream_t s);
+                  int Sq, int Sk, Split dq, Split dk, Split dv, int ld_d, cudaStream_t s, DropSite drop = DropSite());
 // Row compaction for the masked-prediction losses (CrossEntropyLoss ignores label −100, lxrt/modeling.py:99,253-256):
 // rows[0..count) = ascending indices m with labels[m] != ignore.  rows has room for M entries.
 int labelled_rows(const int64_t* labels, int M, int64_t ignore, int64_t* rows, int32_t* count, cudaStream_t s);

@@ -25,7 +25,9 @@ def dims_from_hf_config(cfg) -> LxmertDims:
                       intermediate=cfg.intermediate_size, feat_dim=cfg.visual_feat_dim,
                       pos_dim=cfg.visual_pos_dim, l_layers=cfg.l_layers, r_layers=cfg.r_layers,
                       x_layers=cfg.x_layers, vocab=cfg.vocab_size, max_pos=cfg.max_position_embeddings,
-                      type_vocab=cfg.type_vocab_size, ln_eps=1e-12)
+                      type_vocab=cfg.type_vocab_size, ln_eps=1e-12,
+                      hidden_dropout=float(getattr(cfg, "hidden_dropout_prob", 0.0)),
+                      attention_dropout=float(getattr(cfg, "attention_probs_dropout_prob", 0.0)))
 
 
 # ---- a parameter skeleton with the HF names (used when no HF module is at hand) --------------------
@@ -127,7 +129,7 @@ class _EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc: "B200LxmertEncoder", lang_mask, visual_pos, vis_mask, want_hidden: bool, training: bool,
-                lang_in, visual_feats, *params):
+                drop, lang_in, visual_feats, *params):
         lib = _lib.load()
         d = enc.dims
         B, L, H = lang_in.shape
@@ -151,8 +153,10 @@ class _EncoderFn(torch.autograd.Function):
         rc = lib.xlx_encoder_fwd(C.byref(enc._cdims), parr, prep.data_ptr(), B, L, V, lang_in.data_ptr(),
                                  _ptr(lang_mask), visual_feats.data_ptr(), visual_pos.data_ptr(), _ptr(vis_mask),
                                  lang_out.data_ptr(), vis_out.data_ptr(), _ptr(lang_hidden), _ptr(vis_hidden),
-                                 ws.data_ptr(), ws_bytes, int(training), enc.passes, _stream_ptr())
+                                 ws.data_ptr(), ws_bytes, int(training), enc.passes,
+                                 None if drop is None else C.byref(drop), _stream_ptr())
         _lib.check("xlx_encoder_fwd", rc)
+        ctx.drop = drop
         # an output the loss does not read must arrive in backward as None (not as a tensor of zeros): it decides which
         # blocks of the last cross-modality layer are part of the graph at all
         ctx.set_materialize_grads(False)
@@ -190,7 +194,8 @@ class _EncoderFn(torch.autograd.Function):
             rc = lib.xlx_encoder_bwd(C.byref(enc._cdims), ctx.parr, ctx.prep.data_ptr(), B, L, V,
                                      ctx.visual_pos.data_ptr(), _ptr(d_lang_out), _ptr(d_vis_out),
                                      d_lang_in.data_ptr(), _ptr(d_feats), grads.data_ptr(), ctx.ws.data_ptr(),
-                                     ctx.ws_bytes, enc.passes, stages, _stream_ptr())
+                                     ctx.ws_bytes, enc.passes, stages,
+                                     None if ctx.drop is None else C.byref(ctx.drop), _stream_ptr())
             _lib.check("xlx_encoder_bwd", rc)
 
         group = enc.grad_sync_group
@@ -222,7 +227,7 @@ class _EncoderFn(torch.autograd.Function):
         for i, (p, (off, n)) in enumerate(zip(ctx.params, enc._grad_slices)):
             pgrads.append(grads[off:off + n].view(p.shape) if (p.requires_grad and i not in unused) else None)
         ctx.ws = None
-        return (None, None, None, None, None, None, d_lang_in, d_feats, *pgrads)
+        return (None, None, None, None, None, None, None, d_lang_in, d_feats, *pgrads)
 
 
 class B200LxmertEncoder(nn.Module):
@@ -449,8 +454,12 @@ class B200LxmertEncoder(nn.Module):
         params = self._param_list()
         training = torch.is_grad_enabled() and (lang_feats.requires_grad or visual_feats.requires_grad
                                                 or any(p.requires_grad for p in params))
+        # nn.Dropout follows module.training, not grad mode (HF:474,282,344,236): a train()-mode forward drops even
+        # under no_grad, and takes the training plan for it
+        drop = _lib.step_dropout(self, self.dims)
+        training = training or drop is not None
         lang_out, vis_out, lh, vh = _EncoderFn.apply(self, lmask, visual_pos, vmask, self.output_hidden_states,
-                                                     training, lang_feats, visual_feats, *params)
+                                                     training, drop, lang_feats, visual_feats, *params)
         if self.output_hidden_states:
             n_l, n_v = lh.shape[0], vh.shape[0]
             lang_states = tuple(lh[i] for i in range(n_l - 1)) + (lang_out,)
