@@ -28,6 +28,7 @@ constexpr int EPI_COLS = 16;       // accumulator columns per epilogue step (one
 constexpr int STAGE_BYTES = EPI_WARPS * 32 * EPI_COLS * 4;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA on sm_100
+constexpr size_t kSplitkCounters = 1024;   // words at the end of a split-K workspace holding the per-tile counters
 
 struct KParams {
   int M, N, K;
@@ -41,6 +42,7 @@ struct KParams {
   int splits;          // split-K factor (1 = none); work item = (tile, split)
   int kb_per_split;    // k-blocks per split (last split may be shorter)
   float* part;         // [splits][M][N] fp32 partial sums when splits > 1
+  int* tile_counter;   // split-K: arrivals per output tile; the last arrival reduces the tile (nullptr: reduce kernel)
   int conv, conv_H, conv_W, conv_taps, conv_kb_per_tap;   // implicit-GEMM convolution (see ConvGeometry)
   // conv == 2 ("row halo", 3×3, W % 128 == 0): a k-block is (filter row dy, 32-channel block); its A stage is ONE haloed
   // image row segment of 130 pixels, and the three dx taps are three UMMA descriptor views of it shifted by one pixel
@@ -196,6 +198,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bar_tmem_full[2];
   __shared__ __align__(8) uint64_t bar_tmem_empty[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ int splitk_last;     // split-K: did this CTA store the last partial of the tile?
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -544,6 +547,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
         }
         __syncwarp();
       }
+      if (P.splits > 1 && P.tile_counter) {
+        // Split-K without a second kernel: when every epilogue warp of this CTA has stored its partial sums of
+        // (tile, split), one thread counts the arrival; the CTA that arrives last re-reads all the tile's partials
+        // (L2-resident, written moments ago) in split order and writes the final values.
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        if (e == 0 && lane == 0) {
+          const int t = item % P.tiles_per_split;
+          int* ctr = P.tile_counter + (P.cluster == 2 ? 2 * t + crank : t);
+          const int old = atomicAdd(ctr, 1);
+          const int last = (old == P.splits - 1);
+          if (last) *ctr = 0;                      // ready for the next launch on this workspace
+          splitk_last = last;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        if (*reinterpret_cast<volatile int*>(&splitk_last)) {
+          __threadfence();
+          const size_t mn = static_cast<size_t>(P.M) * P.N;
+          for (int c = half; c <= last_c; c += EPI_WARPS / 4) {
+            const int n = n0 + c * EPI_COLS + cq * 4;
+            if (n >= P.N) continue;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int row = m0 + q * 32 + it * 8 + sub;
+              if (row >= P.M) continue;
+              const float* src = P.part + static_cast<size_t>(row) * P.N + n;
+              float4 a = __ldcg(reinterpret_cast<const float4*>(src));
+              for (int sp = 1; sp < P.splits; ++sp) {
+                const float4 b = __ldcg(reinterpret_cast<const float4*>(src + sp * mn));
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+              }
+              float4* dst = reinterpret_cast<float4*>(P.epi.out_f32 + static_cast<size_t>(row) * P.epi.ld_out + n);
+              if (P.epi.flags & EPI_ACCUM) {
+                const float4 o = *dst;
+                a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+              }
+              *dst = a;
+            }
+          }
+        }
+      }
       if (P.epi.rowstat) {
         const int row = m0 + q * 32 + lane;
         if (row < P.M) {
@@ -891,7 +935,8 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     if (maxS > 16) maxS = 16;
     int best = 1;
     double best_eff = 0.0;
-    for (int S = 1; S <= maxS && need * S <= p.splitk_ws_floats; ++S) {
+    const size_t ws_data = p.splitk_ws_floats > kSplitkCounters ? p.splitk_ws_floats - kSplitkCounters : 0;
+    for (int S = 1; S <= maxS && need * S <= ws_data; ++S) {
       const int items = num_tiles * S * cta_per_item;
       const int waves = (items + num_sms - 1) / num_sms;
       const double eff = static_cast<double>(items) / (static_cast<double>(waves) * num_sms);
@@ -901,6 +946,9 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
       P.kb_per_split = (nkb + best - 1) / best;
       P.splits = (nkb + P.kb_per_split - 1) / P.kb_per_split;
       P.part = p.splitk_ws;
+      static const int fold_on = env_int("XLX_GEMM_SPLITK_FOLD", 0);
+      if (fold_on && num_tiles * cta_per_item <= kSplitkCounters)
+        P.tile_counter = reinterpret_cast<int*>(p.splitk_ws + (p.splitk_ws_floats - kSplitkCounters));
     }
   }
   // plain fp32 output (no split-K partials): TMA store from the staging buffers
@@ -949,7 +997,7 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
 #undef XLX_LAUNCH
     if (lrc) return lrc;
   }
-  if (P.splits > 1) {
+  if (P.splits > 1 && !P.tile_counter) {
     const size_t mn4 = static_cast<size_t>(p.M) * p.N / 4;
     size_t blocks = (mn4 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
@@ -983,7 +1031,12 @@ int gemm_rowstat_slots(int N) {
   return ((N + BN - 1) / BN) * (EPI_WARPS / 4);
 }
 // splits · tiles ≤ 2 · #SMs and every tile is ≤ 128 × 256 outputs
-size_t gemm_splitk_ws_floats() { return static_cast<size_t>(2 * 148) * BM * 256; }
+size_t gemm_splitk_ws_floats() { return static_cast<size_t>(2 * 148) * BM * 256 + kSplitkCounters; }
+int gemm_splitk_ws_reset(float* splitk_ws, cudaStream_t stream) {
+  if (!splitk_ws) return 0;
+  cudaError_t e = cudaMemsetAsync(splitk_ws + (gemm_splitk_ws_floats() - kSplitkCounters), 0, kSplitkCounters * 4, stream);
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
 
 bool gemm_timing_active() { return g_timing; }
 void gemm_timing_begin() {

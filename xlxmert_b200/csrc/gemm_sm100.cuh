@@ -101,6 +101,11 @@ struct GemmProblem {
   size_t splitk_ws_floats = 0;
 };
 size_t gemm_splitk_ws_floats();
+// The last 1024 words of a split-K workspace are per-tile arrival counters: the CTA that stores the LAST partial sum of
+// an output tile adds the tile's partials up (fixed order: deterministic) and writes the result — no second kernel.
+// The counters return to zero by themselves; a workspace must be reset once before its first use (and after an
+// aborted launch): encoder / head backward calls do it once per call.
+int gemm_splitk_ws_reset(float* splitk_ws, cudaStream_t stream);
 // number of partial (max, sumexp, argmax) triples per row a rowstat epilogue writes for an N-column GEMM
 int gemm_rowstat_slots(int N);
 // Cached 2-D TMA descriptor of a row-major bf16 matrix [outer, inner] with leading dimension ld (elements) and a

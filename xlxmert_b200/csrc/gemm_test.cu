@@ -96,13 +96,23 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(dout, out0.data(), nmn * 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&dws, gemm_splitk_ws_floats() * 4));
     CK(cudaMemset(dws, 0xff, gemm_splitk_ws_floats() * 4));   // NaN-fill: a partial sum that is read before written shows
+    if (gemm_splitk_ws_reset(dws, 0)) { printf("gemm_splitk_ws_reset failed\n"); return 3; }
     p.splitk_ws = dws; p.splitk_ws_floats = gemm_splitk_ws_floats();
   }
   long long launches0 = gemm_launch_count();
   int rc = gemm_launch(p, 0);
   if (rc) { printf("gemm_launch rc=%d\n", rc); return 3; }
   CK(cudaDeviceSynchronize());
-  const bool splitk_engaged = (gemm_launch_count() - launches0) > 1;   // main kernel + reduce kernel
+  bool splitk_engaged = (gemm_launch_count() - launches0) > 1;   // main kernel + reduce kernel (XLX_GEMM_SPLITK_FOLD=0)
+  if (epi & 256) {   // folded split-K leaves no second launch: the NaN-filled partial region has been overwritten instead
+    float probe = 0;
+    CK(cudaMemcpy(&probe, dws, 4, cudaMemcpyDeviceToHost));
+    splitk_engaged = splitk_engaged || probe == probe;
+    // run it a second time on the same workspace: the arrival counters must have returned to zero
+    CK(cudaMemcpy(dout, out0.data(), nmn * 4, cudaMemcpyHostToDevice));
+    if (gemm_launch(p, 0)) { printf("second split-K launch failed\n"); return 3; }
+    CK(cudaDeviceSynchronize());
+  }
   std::vector<float> out(nmn), usave(nmn);
   std::vector<__nv_bfloat16> ohi(nmn), olo(nmn);
   CK(cudaMemcpy(out.data(), dout, nmn * 4, cudaMemcpyDeviceToHost));

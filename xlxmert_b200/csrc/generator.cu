@@ -89,6 +89,16 @@ __global__ void prep_conv_kernel(const float* __restrict__ w, const float* __res
   const size_t d = static_cast<size_t>(row0 + co) * ld + static_cast<size_t>(tap) * ctot + col0 + ci;
   hi[d] = h; lo[d] = l;
 }
+// w [HID, CH, 3, 3] → dst[(tap·HID + co)·CH + ci] as split bf16 (tap-major rows: one GEMM gives all nine W_t·y)
+__global__ void prep_tapmajor_kernel(const float* __restrict__ w, int Co, int Ci, bf16* hi, bf16* lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Co * Ci * 9) return;
+  const int tap = i % 9, ci = (i / 9) % Ci, co = i / (9 * Ci);
+  bf16 h, l;
+  split_bf16(w[i], h, l);
+  const size_t d = (static_cast<size_t>(tap) * Co + co) * Ci + ci;
+  hi[d] = h; lo[d] = l;
+}
 __global__ void repeat_bias_kernel(const float* b, int n, float* dst, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) dst[i] = b[i % n];
@@ -174,6 +184,85 @@ __global__ void resize_split_kernel(const float* __restrict__ x, int ld, int Hi,
   o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
   o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
   store_split(hi, lo, p * CH + c4 * 4, o);
+}
+
+// ---- SPADE hidden map without its convolution --------------------------------------------------------------
+// layers.py:33-47: actv = ReLU(conv3×3(bilinear(y → R×R))) with y the 8×8×32 style map.  Both the resize and the
+// convolution are LINEAR in y, so the 32 → 128 convolution never has to run at R×R (73.7 kFLOP per pixel, 2.8 ms of the
+// B = 128 forward at 256² alone): with Z_t = W_t·y computed once at 8×8 for the nine taps t (one small tcgen05 GEMM),
+//     u(p) = b + Σ_t bilinear(Z_t)(p + t)            (zero outside the image = the conv padding)
+// and the bilinear sample separates into a row stage and a column stage:
+//     Ry[b, py, tx, c]   = Σ_ty Σ_a  wy_a(py + ty) · Z_(ty,tx)[b, ya(py + ty), c]          (≤ 6 terms; per image ROW)
+//     u(py, px)          = b + Σ_tx Σ_a  wx_a(px + tx) · Ry[b, py, tx, xa(px + tx)]          (≤ 6 terms; per pixel)
+// — exact (same products, different summation order), 768 FMA per pixel instead of 36 864, HBM-bound on writing the
+// split-bf16 hidden map the γ/β convolution reads.
+// Z: [B·64, 9·HID] fp32, column (tap·HID + ch), tap = ty·3 + tx;  Ry: [B, R, 3, 8, HID] fp32.
+__global__ void __launch_bounds__(256)
+spade_rows_kernel(const float* __restrict__ Z, int R, size_t n, float* __restrict__ Ry) {
+  const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (t >= n) return;                                   // n = B·R·3·8·(HID/4)
+  const int c4 = static_cast<int>(t & (HID / 4 - 1));
+  size_t q = t >> 5;
+  const int c = static_cast<int>(q & 7); q >>= 3;
+  const int tx = static_cast<int>(q % 3); q /= 3;
+  const int lg = 31 - __clz(R);
+  const int py = static_cast<int>(q & (R - 1));
+  const size_t b = q >> lg;
+  const float scale = static_cast<float>(R0) / static_cast<float>(R);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int ty = 0; ty < 3; ++ty) {
+    const int qy = py + ty - 1;
+    if (qy < 0 || qy >= R) continue;
+    int y0, y1;
+    float l0, l1;
+    bilinear_src(qy, scale, R0, y0, y1, l0, l1);
+    const size_t col = static_cast<size_t>(ty * 3 + tx) * HID + c4 * 4;
+    const float4 z0 = __ldg(reinterpret_cast<const float4*>(Z + ((b * 64 + y0 * 8 + c) * 9 * HID + col)));
+    const float4 z1 = __ldg(reinterpret_cast<const float4*>(Z + ((b * 64 + y1 * 8 + c) * 9 * HID + col)));
+    acc.x += l0 * z0.x + l1 * z1.x; acc.y += l0 * z0.y + l1 * z1.y;
+    acc.z += l0 * z0.z + l1 * z1.z; acc.w += l0 * z0.w + l1 * z1.w;
+  }
+  reinterpret_cast<float4*>(Ry)[t] = acc;
+}
+// actv[b, py, px, :] = ReLU(bias + column stage) → split bf16 [B·R², HID].  A warp = the 128 channels (lane = channel
+// quad) of PXW consecutive pixels: the two source columns a tap reads change at most once per 8/R0·R pixels, so their Ry
+// rows stay in registers across the run and every pixel costs 6 FMAs per channel plus its 512 B of stores.
+constexpr int PXW = 8;
+__global__ void __launch_bounds__(256)
+spade_hidden_kernel(const float* __restrict__ Ry, const float* __restrict__ bias, int R, size_t n_groups, bf16* hi,
+                    bf16* lo) {
+  const size_t grp = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (grp >= n_groups) return;                          // n_groups = B·R²/PXW (R ≥ 8: a group never leaves its row)
+  const int c4 = threadIdx.x & 31;
+  const size_t p0 = grp * PXW;
+  const int lg = 31 - __clz(R);
+  const int px0 = static_cast<int>(p0 & (R - 1));
+  const size_t row = p0 >> lg;                          // b·R + py
+  const float scale = static_cast<float>(R0) / static_cast<float>(R);
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+  const float* ry = Ry + row * (3 * 8 * HID) + c4 * 4;
+  float4 r0[3], r1[3];
+  int cx0[3] = {-1, -1, -1}, cx1[3] = {-1, -1, -1};
+#pragma unroll
+  for (int k = 0; k < PXW; ++k) {
+    const int px = px0 + k;
+    float4 acc = bv;
+#pragma unroll
+    for (int tx = 0; tx < 3; ++tx) {
+      const int qx = px + tx - 1;
+      if (qx < 0 || qx >= R) continue;
+      int x0, x1;
+      float l0, l1;
+      bilinear_src(qx, scale, R0, x0, x1, l0, l1);
+      if (x0 != cx0[tx]) { r0[tx] = __ldg(reinterpret_cast<const float4*>(ry + (tx * 8 + x0) * HID)); cx0[tx] = x0; }
+      if (x1 != cx1[tx]) { r1[tx] = __ldg(reinterpret_cast<const float4*>(ry + (tx * 8 + x1) * HID)); cx1[tx] = x1; }
+      acc.x += l0 * r0[tx].x + l1 * r1[tx].x; acc.y += l0 * r0[tx].y + l1 * r1[tx].y;
+      acc.z += l0 * r0[tx].z + l1 * r1[tx].z; acc.w += l0 * r0[tx].w + l1 * r1[tx].w;
+    }
+    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+    store_split(hi, lo, (p0 + k) * HID + c4 * 4, acc);
+  }
 }
 
 // SPADE modulation + noise + LeakyReLU(0.2) at one source pixel (layers.py:33-47, 56-62, 97-100):
@@ -339,7 +428,9 @@ __global__ void rgb_accumulate_kernel(const float* __restrict__ rgb, int r, int 
 inline int blk(int i) { return 10 + 26 * i; }
 inline int rgb_slot(int i) { return 10 + 26 * NBLK + 2 * i; }
 
-struct SpadeW { Split shared, gb; float* gb_bias; };
+// shared: [HID, 9·CH] conv layout (XLX_SPADE_ANALYTIC=0 path); shared_z: [9·HID, CH], row (tap·HID + co) — the B operand
+// of Z = y·W_tᵀ (see spade_rows_kernel)
+struct SpadeW { Split shared, shared_z, gb; float* gb_bias; };
 struct Prep {
   Split bott, init;          // [256, 2048]; [64, 9·256] (rows 0-31 learned_init, 32-63 style_init)
   float* init_bias;          // [64]
@@ -363,6 +454,7 @@ Prep prep_layout(void* base) {
   for (int i = 0; i < NBLK; ++i) {
     for (int j = 0; j < 2; ++j) {
       p.sp[i][j].shared = b.split(static_cast<size_t>(HID) * 9 * CH);
+      p.sp[i][j].shared_z = b.split(static_cast<size_t>(9) * HID * CH);
       p.sp[i][j].gb = b.split(static_cast<size_t>(2 * CH) * 9 * HID);
       p.sp[i][j].gb_bias = b.f32(2 * CH);
     }
@@ -380,7 +472,7 @@ Prep prep_layout(void* base) {
 
 struct Ws {
   Split emb, code, yup[NBLK + 1], actv, a, xu, os;
-  float *hy, *gb, *h1, *of[2], *rgb, *acc, *mean, *rstd;
+  float *hy, *gb, *h1, *of[2], *rgb, *acc, *mean, *rstd, *z;
   double* stat;
   size_t bytes;
 };
@@ -391,6 +483,7 @@ Ws ws_layout(int B, void* base) {
   w.emb = b.split(n * 64 * EMB);
   w.code = b.split(n * 64 * CODE);
   w.hy = b.f32(n * 64 * 64);
+  w.z = b.f32(n * 64 * 9 * HID);          // Z_t = W_t·y at 8×8 for the nine taps (spade_rows_kernel)
   for (int i = 0; i <= NBLK; ++i) w.yup[i] = b.split(n * (static_cast<size_t>(R0 << i) * (R0 << i)) * CH);
   w.actv = b.split(n * top * HID);
   w.gb = b.f32(n * top * 2 * CH);
@@ -472,6 +565,9 @@ int32_t xlx_generator_prepare(const float* const* P, void* prep, void* stream) {
     for (int j = 0; j < 2; ++j) {
       const int q = s + 6 * j;
       XLX_TRY(prep_w(P[q], nullptr, HID, CH, 9, CH, 0, 0, p.sp[i][j].shared));
+      prep_tapmajor_kernel<<<(HID * CH * 9 + 255) / 256, 256, 0, st>>>(P[q], HID, CH, p.sp[i][j].shared_z.hi,
+                                                                      p.sp[i][j].shared_z.lo);
+      XLX_TRY(krc());
       XLX_TRY(prep_w(P[q + 2], nullptr, CH, HID, 9, HID, 0, 0, p.sp[i][j].gb));       // γ rows 0-31
       XLX_TRY(prep_w(P[q + 4], nullptr, CH, HID, 9, HID, 0, CH, p.sp[i][j].gb));      // β rows 32-63
       concat_bias_kernel<<<1, 64, 0, st>>>(P[q + 3], CH, P[q + 5], CH, p.sp[i][j].gb_bias, 2 * CH);
@@ -521,8 +617,10 @@ int32_t xlx_generator_fwd(const float* const* P, const void* prep, int32_t B, co
     XLX_TRY(conv(passes, st, w.code, B, R0, CODE, 9, p.init, 64, 64, e));
   }
   const float* y = w.hy + CH;
-  // style map resized to every resolution once (SPADE resizes y to x's size, layers.py:40)
-  for (int i = 0; i <= NBLK; ++i) {
+  // style map resized to every resolution once (SPADE resizes y to x's size, layers.py:40); the analytic hidden map
+  // (default) only needs the 8×8 original as a split GEMM operand
+  static const bool analytic = [] { const char* e = getenv("XLX_SPADE_ANALYTIC"); return !(e && e[0] == '0'); }();
+  for (int i = 0; i <= (analytic ? 0 : NBLK); ++i) {
     const int R = R0 << i;
     const size_t npix = static_cast<size_t>(B) * R * R;
     resize_split_kernel<<<blocks_for(npix * (CH / 4)), 256, 0, st>>>(y, 64, R0, R, npix, w.yup[i].hi, w.yup[i].lo);
@@ -531,9 +629,23 @@ int32_t xlx_generator_fwd(const float* const* P, const void* prep, int32_t B, co
   // SPADE parameter maps at resolution index ri for SPADE instance (i, j): gb = [γ | β] fp32 [B,R,R,64]
   auto spade_params = [&](int i, int j, int ri) -> int {
     const int R = R0 << ri;
-    GemmEpilogue e;
-    e.bias = P[blk(i) + 6 * j + 1]; e.flags = EPI_RELU; e.out_hi = w.actv.hi; e.out_lo = w.actv.lo; e.ld_split = HID;
-    XLX_TRY(conv(passes, st, w.yup[ri], B, R, CH, 9, p.sp[i][j].shared, HID, HID, e));
+    if (analytic) {
+      // Z = y·W_tᵀ for all taps (one GEMM at 8×8), row stage, column stage + ReLU → actv; Ry borrows the γ/β buffer,
+      // which is only written by the convolution below
+      GemmEpilogue z;
+      z.out_f32 = w.z; z.ld_out = 9 * HID;
+      XLX_TRY(gemm_linear(passes, st, w.yup[0], M0, CH, p.sp[i][j].shared_z, 9 * HID, z));
+      const size_t nr = static_cast<size_t>(B) * R * 3 * 8 * (HID / 4), ngrp = static_cast<size_t>(B) * R * R / PXW;
+      spade_rows_kernel<<<blocks_for(nr), 256, 0, st>>>(w.z, R, nr, w.gb);
+      XLX_TRY(krc());
+      spade_hidden_kernel<<<static_cast<unsigned>((ngrp + 7) / 8), 256, 0, st>>>(w.gb, P[blk(i) + 6 * j + 1], R, ngrp,
+                                                                                 w.actv.hi, w.actv.lo);
+      XLX_TRY(krc());
+    } else {
+      GemmEpilogue e;
+      e.bias = P[blk(i) + 6 * j + 1]; e.flags = EPI_RELU; e.out_hi = w.actv.hi; e.out_lo = w.actv.lo; e.ld_split = HID;
+      XLX_TRY(conv(passes, st, w.yup[ri], B, R, CH, 9, p.sp[i][j].shared, HID, HID, e));
+    }
     GemmEpilogue g;
     g.bias = p.sp[i][j].gb_bias; g.out_f32 = w.gb; g.ld_out = 2 * CH;
     return conv(passes, st, w.actv, B, R, HID, 9, p.sp[i][j].gb, 2 * CH, 2 * CH, g);

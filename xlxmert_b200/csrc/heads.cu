@@ -165,6 +165,7 @@ int head_bwd(const HeadDims& h, const float* const* params, const void* prep_bas
   HeadWs w = head_ws_layout(h, M, ws_base);
   if (w.bytes > ws_bytes) return -23;
   const int H = h.H, F = h.F, C = h.C, Cp = h.Cp;
+  XLX_TRY(gemm_splitk_ws_reset(w.splitk, st));
   XLX_TRY(ce_bwd(w.logits, Cp, M, C, Cp, labels, -100, w.lse, w.stats, d_loss, w.dlogits, st));
   // class bias: column sums over the padded width into scratch, first C entries are the gradient
   XLX_TRY(colsum(nullptr, w.dlogits, M, Cp, Cp, w.part, w.dbc, st));

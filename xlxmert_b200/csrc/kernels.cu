@@ -565,6 +565,37 @@ colsum_finish_kernel(const float* __restrict__ part, int nblk, int H, float* o0,
   }
 }
 
+// Batched variant: the job table travels as a kernel parameter; CTA → (job, vector, 32-column block)
+struct FinishBatch { FinishJob j[64]; int n; };
+__global__ void __launch_bounds__(256) colsum_finish_batched_kernel(const __grid_constant__ FinishBatch b) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[8][33];
+  int ji = 0;
+  while (ji + 1 < b.n && static_cast<int>(blockIdx.x) >= b.j[ji + 1].block0) ++ji;
+  const FinishJob& job = b.j[ji];
+  const int local = blockIdx.x - job.block0, hb = (job.H + 31) / 32;
+  const int v = local / hb, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int h = (local % hb) * 32 + tx, H = job.H, nblk = job.nblk;
+  float* out = job.out[v];
+  if (!out) return;
+  float a0 = 0.f, a1 = 0.f;
+  if (h < H) {     // same summation order as colsum_finish_kernel
+    const float* p = job.part + static_cast<size_t>(v) * nblk * H + h;
+    int k = ty;
+    for (; k + 8 < nblk; k += 16) { a0 += __ldg(p + static_cast<size_t>(k) * H); a1 += __ldg(p + static_cast<size_t>(k + 8) * H); }
+    if (k < nblk) a0 += __ldg(p + static_cast<size_t>(k) * H);
+  }
+  red[ty][tx] = a0 + a1;
+  __syncthreads();
+  if (ty == 0 && h < H) {
+    float sum = red[0][tx];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) sum += red[w][tx];
+    out[h] = sum;
+  }
+}
+
 // Column sums: CTA = 32 column quads (128 columns) × 8 row lanes; grid (ceil(N/128), nblk).
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ xf, const bf16* __restrict__ xh, const bf16* __restrict__ xl, int M, int N,
@@ -913,6 +944,34 @@ int colsum_finish(const float* part, int nvec, int nblk, int H, float* const* ou
   for (int v = 0; v < nvec; ++v) o[v] = outs[v];
   launch_pdl(colsum_finish_kernel, dim3((H + 31) / 32, nvec), dim3(256), 0, s, part, nblk, H, o[0], o[1], o[2], o[3],
              o[4], accumulate);
+  return launch_rc();
+}
+int colsum_finish_batched(FinishJob* jobs, int njobs, cudaStream_t s) {
+  for (int j0 = 0; j0 < njobs; j0 += 64) {
+    FinishBatch b;
+    b.n = njobs - j0 < 64 ? njobs - j0 : 64;
+    int blocks = 0;
+    for (int i = 0; i < b.n; ++i) {
+      FinishJob j = jobs[j0 + i];
+      if (j.nvec < 1 || j.nvec > 3 || j.nblk < 1 || j.H < 1) return -1;
+      j.block0 = blocks;
+      blocks += ((j.H + 31) / 32) * j.nvec;
+      b.j[i] = j;
+    }
+    launch_pdl(colsum_finish_batched_kernel, dim3(blocks), dim3(256), 0, s, b);
+    int rc = launch_rc();
+    if (rc) return rc;
+  }
+  return 0;
+}
+int colsum_partial(const float* x_f32, Split x, int M, int N, int ld, float* part, int* nblk_out, cudaStream_t s,
+                   const uint8_t* rowmask) {
+  if ((N % 4) || (ld % 4)) return -2;
+  int nblk = (M + 63) / 64;
+  if (nblk > 128) nblk = 128;
+  if (nblk < 1) nblk = 1;
+  *nblk_out = nblk;
+  launch_pdl(colsum_kernel, dim3((N + 127) / 128, nblk), dim3(256), 0, s, x_f32, x.hi, x.lo, M, N, ld, part, rowmask);
   return launch_rc();
 }
 int colsum(const float* x_f32, Split x, int M, int N, int ld, float* scratch, float* out, cudaStream_t s,

@@ -119,6 +119,21 @@ int reduce_max_blocks();  // upper bound on nblk for every partial-sum kernel he
 // out_v[H] = Σ_blk part[v, blk, H] for v < nvec (outs[v] may be null to skip); accumulate: out += instead of =
 int colsum_finish(const float* part, int nvec, int nblk, int H, float* const* outs, int accumulate, cudaStream_t s);
 
+// Deferred, batched finish of partial column sums: a backward pass produces one small reduction per block (LayerNorm
+// affine + dense-bias gradients, intermediate-bias and Q/K/V-bias gradients) — ≈ 140 nine-microsecond launches per
+// step when finished one by one.  The partials stay where their producers wrote them (each in its own piece of a
+// scratch arena) and ONE launch per 64 jobs finishes them all at the end of the pass, in the same fixed order.
+struct FinishJob {
+  const float* part;   // [nvec, nblk, H]
+  float* out[3];       // out[v][h] = Σ_blk part[v, blk, h]   (nullptr to skip a vector)
+  int nvec, nblk, H;
+  int block0;          // first CTA of this job (prefix sum, filled by colsum_finish_batched)
+};
+int colsum_finish_batched(FinishJob* jobs, int njobs, cudaStream_t s);
+// first phase of colsum(): partial sums [nblk, N] into `part`; *nblk_out = rows of partials written
+int colsum_partial(const float* x_f32, Split x, int M, int N, int ld, float* part, int* nblk_out, cudaStream_t s,
+                   const uint8_t* rowmask = nullptr);
+
 // column sums: out[N] = Σ_m x[m, n]  (bias gradients) of an fp32 or split matrix with leading dimension ld.
 // scratch: [128, N] floats.  rowmask (optional, one byte per row): only rows with a non-zero byte are summed.
 int colsum(const float* x_f32, Split x, int M, int N, int ld, float* scratch, float* out, cudaStream_t s,
