@@ -47,6 +47,14 @@ struct KParams {
   // conv == 2 ("row halo", 3×3, W % 128 == 0): a k-block is (filter row dy, 32-channel block); its A stage is ONE haloed
   // image row segment of 130 pixels, and the three dx taps are three UMMA descriptor views of it shifted by one pixel
   // (64 bytes) each — every activation byte crosses L2→SM 3 times instead of 9.
+  // conv == 3 ("row group", halo geometry): a work item is G vertically adjacent 128-pixel tiles with G accumulators in
+  // TMEM.  Per 32-channel block the producer streams the G + 2 haloed image rows ONCE (each feeds up to three
+  // (tile, filter-row) pairs) and the three filter-row weight groups ONCE (each serves G tiles) through a second,
+  // longer-lived ring — 2.8× fewer bytes from L2 per pixel than conv == 2 and 54 instead of 18 MMAs per A stage.
+  int conv_G;            // tiles per item (4 for BN ≤ 64)
+  uint32_t b_group_bytes; // one weight group: 3 dx taps × BN rows × 32 channels, per part
+  uint32_t b_ring_off;   // byte offset of the weight ring behind the A ring
+  int b_slots;           // weight-ring slots
   uint32_t stage_tx;   // bytes one stage receives by TMA (= stage_bytes except in halo mode, whose A box is 130 rows)
   int conv_tapbox;     // halo mode: the B maps are rank-3 (channel, row, dx) and one box fetches all three dx taps
   int cluster;         // 1, or 2 = CTA pairs on adjacent m-tiles sharing the B tile by TMA multicast
@@ -199,6 +207,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bar_tmem_empty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ int splitk_last;     // split-K: did this CTA store the last partial of the tile?
+  __shared__ __align__(8) uint64_t bar_bfull[4];    // conv == 3: weight-group ring
+  __shared__ __align__(8) uint64_t bar_bempty[4];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -234,6 +244,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
       mbar_init(smem_u32(&bar_tmem_full[b]), 1);
       mbar_init(smem_u32(&bar_tmem_empty[b]), EPI_WARPS);  // one arrival per epilogue warp
     }
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(smem_u32(&bar_bfull[b]), 1);
+      mbar_init(smem_u32(&bar_bempty[b]), 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -249,7 +263,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
   pdl_trigger();
   pdl_wait();
 
-  if (warp == 0) {
+  // conv == 3: item → (image, first row of the G-row group, first pixel of the 128-pixel column block)
+  auto decode_group = [&](int item, int& img, int& y0, int& x0) {
+    const int xt = P.conv_W / BM, yg = P.conv_H / P.conv_G;
+    x0 = (item % xt) * BM;
+    y0 = ((item / xt) % yg) * P.conv_G;
+    img = item / (xt * yg);
+  };
+  if (warp == 0 && !A_MN && !B_MN && P.conv == 3) {
+    // ===================== TMA producer, row-group convolution =====================
+    if (lane == 0) {
+      int s = 0, bs = 0;
+      uint32_t ph = 0, bph = 0;
+      const uint32_t a_box = (BM + 2) * BK * 2;
+      for (int item = item0; item < num_items; item += istride) {
+        int img, y0, x0;
+        decode_group(item, img, y0, x0);
+        for (int cb = 0; cb < P.conv_kb_per_tap; ++cb) {
+          for (int r = 0; r < P.conv_G + 2; ++r) {
+            if (r < 3) {     // weight group (cb, filter row r): needed from image row r on
+              mbar_wait(smem_u32(&bar_bempty[bs]), bph ^ 1);
+              const uint32_t bfull = smem_u32(&bar_bfull[bs]);
+              mbar_arrive_expect_tx(bfull, NPARTS * P.b_group_bytes);
+              const uint32_t dB = smem_base + P.b_ring_off + bs * NPARTS * P.b_group_bytes;
+#pragma unroll
+              for (int part = 0; part < NPARTS; ++part)
+                tma_load_3d(dB + part * P.b_group_bytes, part ? &mapBlo : &mapBhi, bfull,
+                            (r * 3 * P.conv_kb_per_tap + cb) * BK, 0, 0);
+              if (++bs == P.b_slots) { bs = 0; bph ^= 1; }
+            }
+            mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+            const uint32_t full = smem_u32(&bar_full[s]);
+            mbar_arrive_expect_tx(full, NPARTS * a_box);
+            const uint32_t sA = smem_base + s * P.stage_bytes;
+#pragma unroll
+            for (int part = 0; part < NPARTS; ++part)
+              tma_load_4d(sA + part * P.a_part_bytes, part ? &mapAlo : &mapAhi, full, cb * BK, x0 - 1, y0 + r - 1, img);
+            if (++s == P.num_stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer (one thread) =====================
     if (lane == 0) {
       int s = 0;
@@ -340,6 +395,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
     int s = 0;
     uint32_t ph = 0;
     int local = 0;
+    if (!A_MN && !B_MN && P.conv == 3) {
+      // row-group convolution: A stage = (channel block cb, image row r of the group's G + 2 haloed rows); it feeds the
+      // tiles g = r − dy for the filter rows dy whose tile exists, each with the three dx taps as shifted views
+      const int G = P.conv_G, kbpt = P.conv_kb_per_tap;
+      const uint32_t b_tap = (P.BN * BK * 2) >> 4;
+      uint32_t q = 0;                       // running index of the weight group (cb, dy = 0) of the current item
+      for (int item = item0; item < num_items; item += istride, ++local) {
+        const int buf = local & 1;
+        const uint32_t acc_ph = (local >> 1) & 1;
+        mbar_wait(smem_u32(&bar_tmem_empty[buf]), acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_item = tmem_base + buf * (G * P.BN);
+        for (int cb = 0; cb < kbpt; ++cb, q += 3) {
+          for (int r = 0; r < G + 2; ++r) {
+            if (r < 3) {                    // first use of weight group (cb, dy = r)
+              const uint32_t qi = q + r;
+              mbar_wait(smem_u32(&bar_bfull[qi % P.b_slots]), (qi / P.b_slots) & 1);
+            }
+            mbar_wait(smem_u32(&bar_full[s]), ph);
+            tc_fence_after();
+            const uint32_t sA = (smem_base + s * P.stage_bytes) & 0x3FFFFu;
+            const uint32_t a0 = loA | (sA >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy) {
+                const int g = r - dy;
+                if (g < 0 || g >= G) continue;
+                const uint32_t qi = q + dy;
+                const uint32_t sB = (smem_base + P.b_ring_off + (qi % P.b_slots) * NPARTS * P.b_group_bytes) & 0x3FFFFu;
+                const uint32_t b0 = loB | (sB >> 4);
+                const uint32_t tmem_d = tmem_item + g * P.BN;
+#pragma unroll
+                for (int dxi = 0; dxi < 3; ++dxi) {
+#pragma unroll
+                  for (int kk = 0; kk < BK / 16; ++kk) {
+                    const uint32_t acc = (cb > 0 || dy > 0 || dxi > 0 || kk > 0) ? 1u : 0u;
+                    const uint32_t ah = a0 + dxi * ((BK * 2) >> 4) + kk * stepA, bh = b0 + dxi * b_tap + kk * stepB;
+                    if (NPARTS == 2) {
+                      umma_bf16(tmem_d, umma_desc(hiA, ah + a_part), umma_desc(hiB, bh), idesc, acc);
+                      umma_bf16(tmem_d, umma_desc(hiA, ah), umma_desc(hiB, bh + (P.b_group_bytes >> 4)), idesc, 1u);
+                      umma_bf16(tmem_d, umma_desc(hiA, ah), umma_desc(hiB, bh), idesc, 1u);
+                    } else {
+                      umma_bf16(tmem_d, umma_desc(hiA, ah), umma_desc(hiB, bh), idesc, acc);
+                    }
+                  }
+                }
+                if (g == G - 1) umma_commit(smem_u32(&bar_bempty[qi % P.b_slots]));   // last tile served by this group
+              }
+              umma_commit(smem_u32(&bar_empty[s]));
+              if (cb == kbpt - 1 && r == G + 1) umma_commit(smem_u32(&bar_tmem_full[buf]));
+            }
+            __syncwarp();
+            if (++s == P.num_stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    } else
     for (int item = item0; item < num_items; item += istride, ++local) {
       const int split = item / P.tiles_per_split;
       const int kb0 = split * P.kb_per_split, kb1 = min(nkb, kb0 + P.kb_per_split);
@@ -412,18 +524,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int e = warp - 2;                 // epilogue warp index 0 … EPI_WARPS-1
     const int half = e >> 2;                // which of the EPI_WARPS/4 warps of the quadrant
-    float* stage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + P.num_stages * P.stage_bytes) +
+    float* stage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + P.num_stages * P.stage_bytes +
+                                            (P.conv == 3 ? P.b_slots * P.nparts * P.b_group_bytes : 0u)) +
                    e * 32 * EPI_COLS;
     const int sub = lane >> 2, cq = lane & 3;
     int local = 0;
     for (int item = item0; item < num_items; item += istride, ++local) {
       int m0, n0, split;
-      decode(item, m0, n0, split);
+      // conv == 3: the item holds ngrp accumulators, one per image row of the group (tiles W pixels apart)
+      const int ngrp = (P.conv == 3) ? P.conv_G : 1;
+      if (P.conv == 3) {
+        int img, y0, x0;
+        decode_group(item, img, y0, x0);
+        m0 = (img * P.conv_H + y0) * P.conv_W + x0; n0 = 0; split = 0;
+      } else {
+        decode(item, m0, n0, split);
+      }
+      const int m0_item = m0;
       const int buf = local & 1;
       const uint32_t acc_ph = (local >> 1) & 1;
       mbar_wait(smem_u32(&bar_tmem_full[buf]), acc_ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * P.BN;
       const int nchunks = P.BN / EPI_COLS;
       // last chunk this warp will read (chunks beyond N are skipped)
       int last_c = -1;
@@ -437,11 +558,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
       // row-statistics epilogue state (thread = row domain): running max, Σ exp(x − max), first index of the max
       float rs_m = -INFINITY, rs_s = 0.f;
       int rs_arg = 0x7fffffff;
+      for (int grp = 0; grp < ngrp; ++grp) {
+      m0 = m0_item + grp * P.conv_W;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (ngrp * P.BN) + grp * P.BN;
       for (int c = half; c <= last_c; c += EPI_WARPS / 4) {
         uint32_t r[EPI_COLS];
         tmem_ld_32x16(taddr + c * EPI_COLS, r);
         tmem_ld_wait();
-        if (c == last_c) {  // accumulator fully read by this warp: release before the global traffic
+        if (c == last_c && grp == ngrp - 1) {  // accumulator(s) fully read by this warp: release before the global traffic
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
@@ -547,6 +671,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
         }
         __syncwarp();
       }
+      }   // grp
       if (P.splits > 1 && P.tile_counter) {
         // Split-K without a second kernel: when every epilogue warp of this CTA has stored its partial sums of
         // (tile, split), one thread counts the arrival; the CTA that arrives last re-reads all the tile's partials
@@ -827,6 +952,17 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   P.M = p.M; P.N = p.N; P.K = p.K;
   int BN = 256;
   if (p.N <= 64) BN = 64; else if (p.N <= 128) BN = 128;
+  // narrow convolutions (32 → 32, ToRGB): an N = 64 instruction would spend half of its tensor-pipe time on padding
+  static const int conv_bn32 = env_int("XLX_CONV_BN32", 1);
+  if (conv_bn32 && p.conv.enabled && p.N <= 32) BN = 32;
+  // Small-M GEMMs (inference at sampling batch sizes: M = 2048 rows → 48 tiles of 128 × 256 on 148 SMs): narrower tiles
+  // put more SMs to work; one output element's accumulation order does not depend on the tile width, so results are
+  // bit-identical.  Only when the wide tiling leaves more than 40 % of the SMs without a tile.
+  static const int narrow_on = env_int("XLX_GEMM_NARROW_SMALL_M", 1);
+  if (narrow_on && !p.conv.enabled && !p.epi.rowstat && !p.splitk_ws) {
+    const int tm = (p.M + BM - 1) / BM;
+    while (BN > 64 && tm * ((p.N + BN - 1) / BN) * 10 < num_sms * 6) BN >>= 1;
+  }
   int force_bn = env_int("XLX_GEMM_BN", 0);
   if (force_bn) BN = force_bn;
   P.BN = BN;
@@ -883,6 +1019,7 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     if (P.nparts == 2) { if ((rc = make_map4(&mAlo, p.a.lo, nimg, g.H, g.W, g.C, BK, bw, bh, bb, swzK))) return rc; }
     else mAlo = mAhi;
     P.conv = halo ? 2 : 1; P.conv_H = g.H; P.conv_W = g.W; P.conv_taps = g.taps; P.conv_kb_per_tap = g.C / BK;
+    P.conv_G = 1;
     if (halo) {
       const uint32_t a_box = (BM + 2) * BK * 2;                       // 130 pixel rows of 64 bytes
       P.a_part_bytes = (a_box + 1023u) & ~1023u;                      // parts stay 1024-byte aligned
@@ -919,8 +1056,38 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
       P.conv_tapbox = 1;
     }
   }
-  // tiles per split: single tiles, or pairs of m-tiles (an odd last m-tile gets an idle partner)
-  const int num_tiles = P.cluster == 2 ? ((P.tiles_m + 1) / 2) * P.tiles_n : P.tiles_m * P.tiles_n;
+  // row-group mode: G tiles per item share the weight groups and the haloed rows (needs the rank-3 weight box, a
+  // single n-tile and a plain enough epilogue that the G accumulators can be drained one after the other)
+  static const int rowgroup_on = env_int("XLX_CONV_ROWGROUP", 1);
+  if (P.conv == 2 && P.conv_tapbox && rowgroup_on && P.tiles_n == 1 && BN <= 64 && p.conv.H % 4 == 0 && !p.epi.rowstat &&
+      !p.epi.colsum_part) {
+    P.conv = 3;
+    P.conv_G = 4;
+    P.b_group_bytes = 3 * BN * BK * 2;
+    P.b_slots = 4;
+    P.stage_bytes = P.nparts * P.a_part_bytes;                    // the A ring carries the haloed rows only
+    const int fixed = 2048 + 1024 + STAGE_BYTES + P.b_slots * P.nparts * static_cast<int>(P.b_group_bytes);
+    stages = (SMEM_LIMIT - fixed) / static_cast<int>(P.stage_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 3) { P.conv = 2; P.conv_G = 1; }                  // does not fit: keep the one-tile halo mode
+    else {
+      P.num_stages = stages;
+      P.b_ring_off = stages * P.stage_bytes;
+      uint32_t cols = 32;
+      while (cols < static_cast<uint32_t>(2 * P.conv_G * BN)) cols <<= 1;
+      P.tmem_cols = cols;
+    }
+    if (P.conv == 2) {   // restore the halo-mode stage geometry
+      P.stage_bytes = P.nparts * (P.a_part_bytes + 3 * BN * BK * 2);
+      stages = (SMEM_LIMIT - 2048 - 1024 - STAGE_BYTES) / static_cast<int>(P.stage_bytes);
+      if (stages > MAX_STAGES) stages = MAX_STAGES;
+      P.num_stages = stages;
+    }
+  }
+  // tiles per split: single tiles, or pairs of m-tiles (an odd last m-tile gets an idle partner); row-group
+  // convolution: groups of conv_G vertically adjacent tiles
+  const int num_tiles = P.conv == 3 ? P.tiles_m / P.conv_G
+                        : P.cluster == 2 ? ((P.tiles_m + 1) / 2) * P.tiles_n : P.tiles_m * P.tiles_n;
   const int cta_per_item = P.cluster;
   const int nkb = (P.conv == 2) ? 3 * P.conv_kb_per_tap : (p.K + BK - 1) / BK;
   // split-K: only for plain fp32-output GEMMs (weight gradients) whose tile count leaves most SMs idle
@@ -965,7 +1132,8 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   P.num_items = num_items;
   int grid = num_items * cta_per_item < num_sms ? num_items * cta_per_item : num_sms;
   if (P.cluster == 2) grid &= ~1;
-  const size_t smem = static_cast<size_t>(stages) * P.stage_bytes + 1024 + STAGE_BYTES;
+  const size_t smem = static_cast<size_t>(P.num_stages) * P.stage_bytes + 1024 + STAGE_BYTES +
+                      (P.conv == 3 ? static_cast<size_t>(P.b_slots) * P.nparts * P.b_group_bytes : 0);
   TimedLaunch tl{};
   if (g_timing) {
     cudaEventCreate(&tl.e0);
