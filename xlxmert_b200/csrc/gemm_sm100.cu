@@ -953,7 +953,7 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   int BN = 256;
   if (p.N <= 64) BN = 64; else if (p.N <= 128) BN = 128;
   // narrow convolutions (32 → 32, ToRGB): an N = 64 instruction would spend half of its tensor-pipe time on padding
-  static const int conv_bn32 = env_int("XLX_CONV_BN32", 1);
+  static const int conv_bn32 = env_int("XLX_CONV_BN32", 0);
   if (conv_bn32 && p.conv.enabled && p.N <= 32) BN = 32;
   // Small-M GEMMs (inference at sampling batch sizes: M = 2048 rows → 48 tiles of 128 × 256 on 148 SMs): narrower tiles
   // put more SMs to work; one output element's accumulation order does not depend on the tile width, so results are

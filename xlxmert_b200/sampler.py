@@ -137,6 +137,16 @@ class B200ImggenModel(nn.Module):
         mf = self.mask_feat.detach()
         return mf if (mf.dtype == torch.float32 and mf.is_contiguous()) else mf.float().contiguous()
 
+    def _visual_pos(self, B, grid_size, dev):
+        """``box_position(grid_size)`` expanded to the batch (imggen_model.py:195), cached on the device: building it
+        from numpy on every call costs a pageable host→device copy and a synchronisation."""
+        key = (B, grid_size, str(dev))
+        cache = self.__dict__.setdefault("_vpos_cache", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = torch.from_numpy(box_position(grid_size)).unsqueeze(0).expand(B, -1, -1).contiguous().to(dev)
+        return cache[key]
+
     def _check_device(self, input_ids):
         if not input_ids.is_cuda or self.vis_emb is None or not self.vis_emb.weight.is_cuda:
             raise RuntimeError("B200ImggenModel samples on CUDA (sm_100a) only — move the model and its visual "
@@ -157,7 +167,7 @@ class B200ImggenModel(nn.Module):
         n_grids = grid_size ** 2
         if n_steps is None:
             n_steps = n_grids
-        visual_pos = torch.from_numpy(box_position(grid_size)).unsqueeze(0).expand(B, -1, -1).contiguous().to(dev)
+        visual_pos = self._visual_pos(B, grid_size, dev)
         intermediate_imgs = []
         pred_prob = pred_code_id = None
         lang = self.bert.language_stack(input_ids, input_ids > 0) if cache_language else None
@@ -198,7 +208,7 @@ class B200ImggenModel(nn.Module):
         n_grids = grid_size ** 2
         if n_steps is None:
             n_steps = n_grids
-        visual_pos = torch.from_numpy(box_position(grid_size)).unsqueeze(0).expand(B, -1, -1).contiguous().to(dev)
+        visual_pos = self._visual_pos(B, grid_size, dev)
         intermediate_imgs = []
         if position_random:
             positions = list(range(n_grids))
