@@ -195,11 +195,18 @@ __device__ __forceinline__ float4 epilogue_vec4(const KParams& P, int row, int n
 // the single MMA-issuing thread's loop is a handful of integer adds per tcgen05.mma (it is the critical path).
 // ACT: the epilogue may contain an activation (GeLU / tanh / ReLU / gelu-grad); kept out of the other instantiations so
 // that their code stays small — the epilogue warps share the instruction cache with the MMA-issuing warp.
-template <int BK, int A_MN, int B_MN, int NPARTS, bool ACT>
+// EPI: 0 = load-bound epilogues (the common case), 1 = ACT, 2 = row statistics (soft-max / arg-max of the sampler's
+// logits GEMM, K-major operands only), 3 = split-K with the reduction folded into the last-arriving CTA (weight-gradient
+// layout only; XLX_GEMM_SPLITK_FOLD=1).  The rare modes are separate instantiations so that their state (16 extra live
+// registers for the row statistics, the extra barriers of the fold) cannot push the hot variant into spilling.
+template <int BK, int A_MN, int B_MN, int NPARTS, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
             const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
             const __grid_constant__ CUtensorMap mapOut, const KParams P) {
+  constexpr bool ACT = (EPI == 1);
+  constexpr bool ROWSTAT = (EPI == 2);
+  constexpr bool FOLD = (EPI == 3);
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
@@ -571,7 +578,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
           if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
         }
         if (P.debug & 1) continue;
-        if (P.epi.rowstat) {
+        if (ROWSTAT) {
           // this thread holds columns nb … nb+15 of its own row: fold them into the running statistics
           const int nb = n0 + c * EPI_COLS;
           float v[EPI_COLS];
@@ -672,7 +679,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
         __syncwarp();
       }
       }   // grp
-      if (P.splits > 1 && P.tile_counter) {
+      if (FOLD && P.splits > 1) {
         // Split-K without a second kernel: when every epilogue warp of this CTA has stored its partial sums of
         // (tile, split), one thread counts the arrival; the CTA that arrives last re-reads all the tile's partials
         // (L2-resident, written moments ago) in split order and writes the final values.
@@ -713,7 +720,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
           }
         }
       }
-      if (P.epi.rowstat) {
+      if (ROWSTAT) {
         const int row = m0 + q * 32 + lane;
         if (row < P.M) {
           const int slots = P.tiles_n * (EPI_WARPS / 4);
@@ -910,12 +917,12 @@ int env_int(const char* name, int dflt) {
   return s ? atoi(s) : dflt;
 }
 
-template <int BK, int A_MN, int B_MN, int NPARTS, bool ACT>
+template <int BK, int A_MN, int B_MN, int NPARTS, int EPI>
 int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& mAhi, const CUtensorMap& mAlo,
                    const CUtensorMap& mBhi, const CUtensorMap& mBlo, const CUtensorMap& mOut, const KParams& P) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BK, A_MN, B_MN, NPARTS, ACT>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BK, A_MN, B_MN, NPARTS, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
@@ -935,7 +942,7 @@ int launch_variant(int grid, size_t smem, cudaStream_t stream, const CUtensorMap
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BK, A_MN, B_MN, NPARTS, ACT>, mAhi, mAlo, mBhi, mBlo, mOut, P);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BK, A_MN, B_MN, NPARTS, EPI>, mAhi, mAlo, mBhi, mBlo, mOut, P);
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }
 
@@ -1114,7 +1121,7 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
       P.splits = (nkb + P.kb_per_split - 1) / P.kb_per_split;
       P.part = p.splitk_ws;
       static const int fold_on = env_int("XLX_GEMM_SPLITK_FOLD", 0);
-      if (fold_on && num_tiles * cta_per_item <= kSplitkCounters)
+      if (fold_on && P.a_mn && P.b_mn && num_tiles * cta_per_item <= kSplitkCounters)
         P.tile_counter = reinterpret_cast<int*>(p.splitk_ws + (p.splitk_ws_floats - kSplitkCounters));
     }
   }
@@ -1150,8 +1157,15 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     const int v = (P.a_mn ? 4 : 0) | (P.b_mn ? 2 : 0) | (P.nparts == 2 ? 1 : 0);
     int lrc = 0;
 #define XLX_LAUNCH(A, B, N)                                                                                   \
-  lrc = act ? launch_variant<BK, A, B, N, true>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)          \
-            : launch_variant<BK, A, B, N, false>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)
+  lrc = act ? launch_variant<BK, A, B, N, 1>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)             \
+            : launch_variant<BK, A, B, N, 0>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)
+    if (p.epi.rowstat) {                       // K-major operands only (checked by gemm_launch)
+      lrc = P.nparts == 2 ? launch_variant<BK, 0, 0, 2, 2>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)
+                          : launch_variant<BK, 0, 0, 1, 2>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
+    } else if (P.tile_counter) {               // folded split-K: weight-gradient layout only (see below)
+      lrc = P.nparts == 2 ? launch_variant<BK, 1, 1, 2, 3>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)
+                          : launch_variant<BK, 1, 1, 1, 3>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
+    } else
     switch (v) {
       case 0: XLX_LAUNCH(0, 0, 1); break;
       case 1: XLX_LAUNCH(0, 0, 2); break;
@@ -1255,7 +1269,7 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream) {
   if (E.drop.threshold && (E.rowstat || p.conv.enabled)) return -1;
   if ((E.flags & EPI_MUL) && !E.u_in && !E.u_in16) return -1;
   if (E.addend_hi && !E.addend_lo) return -1;
-  if (E.rowstat && (E.out_f32 || E.out_hi || E.out_u || E.out_u16 || E.colsum_part || p.splitk_ws || E.flags ||
+  if (E.rowstat && (p.a.mn_major || p.b.mn_major || E.out_f32 || E.out_hi || E.out_u || E.out_u16 || E.colsum_part || p.splitk_ws || E.flags ||
                     E.rowstat_cols < 1 || E.rowstat_cols > p.N || getenv("XLX_GEMM_BN")))
     return -1;
   return launch_bk<32>(p, stream);
