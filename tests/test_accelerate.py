@@ -98,3 +98,37 @@ def test_accelerated_hf_model_matches_unswapped_hf_on_cpu():
     assert len(h.language_hidden_states) == 14 and len(h.vision_hidden_states) == 10
     for a, b in zip(h.language_hidden_states + h.vision_hidden_states, hr.language_hidden_states + hr.vision_hidden_states):
         assert rel_err(a.cpu(), b) < 1e-4
+
+
+@pytest.mark.gpu
+def test_output_attentions_match_hf():
+    """``output_attentions=True`` (a1 / a13 boundary): language_attentions (9), vision_attentions (5) and
+    cross_encoder_attentions (5, language queries over vision keys) equal HF's in eval mode — through an accelerated HF
+    ``LxmertModel`` and through ``B200LxmertModel``."""
+    from xlxmert_b200 import synth
+    from xlxmert_b200.config import DEFAULT_DIMS as D
+    from xlxmert_b200.encoder import accelerate, dims_from_hf_config
+    from xlxmert_b200.lxmert import B200LxmertModel
+    ref = _hf_model(seed=4).eval()
+    fast = accelerate(copy.deepcopy(ref).cuda()).eval()
+    B, L, V = 2, 13, 36
+    batch = synth.make_batch(D, B, L, V, seed=8)
+    feats = synth.visual_feats_from(synth.centroid_table(D), batch["cluster_ids"])
+    kw = dict(input_ids=batch["input_ids"], visual_feats=feats, visual_pos=batch["visual_pos"],
+              attention_mask=batch["attention_mask"], return_dict=True, output_attentions=True)
+    with torch.no_grad():
+        o = ref(**kw)
+        g = fast(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()})
+        native = B200LxmertModel(dims_from_hf_config(ref.config), source=copy.deepcopy(ref).cuda()).eval()
+        n = native(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()})
+    for got in (g, n):
+        assert len(got.language_attentions) == 9 and len(got.vision_attentions) == 5 and len(got.cross_encoder_attentions) == 5
+        for a, b in zip(got.language_attentions + got.vision_attentions + got.cross_encoder_attentions,
+                        o.language_attentions + o.vision_attentions + o.cross_encoder_attentions):
+            assert a.shape == b.shape
+            assert float((a.cpu() - b).abs().max()) < 1e-5          # probabilities in [0, 1]: absolute error
+        assert rel_err(got.language_output.cpu() if hasattr(got, "language_output") else got[0].cpu(), o.language_output) < 1e-4
+    # without the flag nothing is exported (and the small inference plan is used)
+    with torch.no_grad():
+        plain = native(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items() if k != "output_attentions"})
+    assert plain.language_attentions is None and torch.equal(plain[0], n[0])

@@ -939,6 +939,18 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
   return 0;
 }
 
+// Byte offset, inside a TRAINING workspace, of the soft-max probabilities attention block `att_block` (plan order)
+// saved for the backward: [B, heads, Sq, Sk] fp32, before dropout.  second = 1: the vision-query half of a cross block.
+// This is what HF returns as language_attentions / vision_attentions / cross_encoder_attentions (HF:506-565) in eval mode.
+int64_t xlx_encoder_probs_offset(const xlx_dims* d, int32_t B, int32_t L, int32_t V, int32_t att_block, int32_t second) {
+  if (check_common(d, B, L, V)) return -1;
+  Plan p = make_plan(d, B, L, V, true, nullptr);
+  if (att_block < 0 || att_block >= static_cast<int>(p.att.size())) return -1;
+  const float* ptr = second ? p.att[att_block].probs2 : p.att[att_block].probs;
+  if (!ptr) return -1;
+  return static_cast<int64_t>(reinterpret_cast<const char*>(ptr) - static_cast<const char*>(nullptr));
+}
+
 // Element range [*offset, *offset + *elems) of the gradient arena completed by one backward stage.
 int32_t xlx_encoder_grad_stage_range(const xlx_dims* d, int32_t stage, int64_t* offset, int64_t* elems) {
   if (!dims_ok(d)) return -20;

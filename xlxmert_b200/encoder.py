@@ -129,7 +129,7 @@ class _EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc: "B200LxmertEncoder", lang_mask, visual_pos, vis_mask, want_hidden: bool, training: bool,
-                drop, lang_in, visual_feats, *params):
+                drop, want_attn: bool, lang_in, visual_feats, *params):
         lib = _lib.load()
         d = enc.dims
         B, L, H = lang_in.shape
@@ -171,10 +171,28 @@ class _EncoderFn(torch.autograd.Function):
             outs += [lang_hidden, vis_hidden]
         else:
             outs += [None, None]
+        if want_attn:
+            # HF:506-565 — language_attentions (layer.*), vision_attentions (r_layers.*), cross_encoder_attentions (the
+            # language-query half of every x_layer's cross attention): copies of the probabilities the training plan
+            # saves for its backward
+            def probs(blk, Sq, Sk):
+                off = lib.xlx_encoder_probs_offset(C.byref(enc._cdims), B, L, V, blk, 0)
+                if off < 0:
+                    raise _lib.XlxError("xlx_encoder_probs_offset", -1)
+                n = B * d.heads * Sq * Sk
+                return ws[off:off + 4 * n].view(torch.float32).view(B, d.heads, Sq, Sk).clone()
+            la = [probs(i, L, L) for i in range(d.l_layers)]
+            va = [probs(d.l_layers + i, V, V) for i in range(d.r_layers)]
+            xa = [probs(d.l_layers + d.r_layers + 3 * k, L, V) for k in range(d.x_layers)]
+            ctx.mark_non_differentiable(*la, *va, *xa)
+            ctx.n_attn = len(la) + len(va) + len(xa)
+            outs += la + va + xa
+        else:
+            ctx.n_attn = 0
         return tuple(outs)
 
     @staticmethod
-    def backward(ctx, d_lang_out, d_vis_out, _dlh, _dvh):
+    def backward(ctx, d_lang_out, d_vis_out, _dlh, _dvh, *_dattn):
         lib = _lib.load()
         enc = ctx.enc
         B, L, V = ctx.shape
@@ -227,7 +245,7 @@ class _EncoderFn(torch.autograd.Function):
         for i, (p, (off, n)) in enumerate(zip(ctx.params, enc._grad_slices)):
             pgrads.append(grads[off:off + n].view(p.shape) if (p.requires_grad and i not in unused) else None)
         ctx.ws = None
-        return (None, None, None, None, None, None, None, d_lang_in, d_feats, *pgrads)
+        return (None, None, None, None, None, None, None, None, d_lang_in, d_feats, *pgrads)
 
 
 class B200LxmertEncoder(nn.Module):
@@ -437,8 +455,6 @@ class B200LxmertEncoder(nn.Module):
                 raise RuntimeError("language_stack= is an inference-only shortcut; wrap the call in torch.no_grad()")
             return self._subpass("rest")(language_stack, lang_attention_mask, visual_feats, visual_pos,
                                          visual_attention_mask)
-        if output_attentions:
-            raise NotImplementedError("attention probabilities are not exported by the fused path")
         if not lang_feats.is_cuda:
             raise RuntimeError("B200LxmertEncoder runs on CUDA (sm_100a) only; there is no CPU fallback")
         B, L, _ = lang_feats.shape
@@ -457,16 +473,25 @@ class B200LxmertEncoder(nn.Module):
         # nn.Dropout follows module.training, not grad mode (HF:474,282,344,236): a train()-mode forward drops even
         # under no_grad, and takes the training plan for it
         drop = _lib.step_dropout(self, self.dims)
-        training = training or drop is not None
-        lang_out, vis_out, lh, vh = _EncoderFn.apply(self, lmask, visual_pos, vmask, self.output_hidden_states,
-                                                     training, drop, lang_feats, visual_feats, *params)
+        want_attn = bool(output_attentions)
+        # the probabilities only exist in the training plan (saved for the backward); note that HF returns them AFTER
+        # dropout in train() mode (HF:262-274) — here they are always the undropped soft-max
+        training = training or drop is not None or want_attn
+        res = _EncoderFn.apply(self, lmask, visual_pos, vmask, self.output_hidden_states, training, drop, want_attn,
+                               lang_feats, visual_feats, *params)
+        lang_out, vis_out, lh, vh = res[:4]
         if self.output_hidden_states:
             n_l, n_v = lh.shape[0], vh.shape[0]
             lang_states = tuple(lh[i] for i in range(n_l - 1)) + (lang_out,)
             vis_states = tuple(vh[i] for i in range(n_v - 1)) + (vis_out,)
         else:
             lang_states, vis_states = (lang_out,), (vis_out,)
-        return ((vis_states, None), (lang_states, None), None)
+        if not want_attn:
+            return ((vis_states, None), (lang_states, None), None)
+        d = self.dims
+        att = res[4:]
+        la, va, xa = att[:d.l_layers], att[d.l_layers:d.l_layers + d.r_layers], att[d.l_layers + d.r_layers:]
+        return ((vis_states, tuple(va)), (lang_states, tuple(la)), tuple(xa))
 
 
 def accelerate(model: nn.Module, passes: int = 3, output_hidden_states: bool = False) -> nn.Module:

@@ -29,6 +29,10 @@ class LxmertOutput(tuple):
         self.language_attentions = self.vision_attentions = self.cross_encoder_attentions = None
         return self
 
+    def with_attentions(self, lang_att, vis_att, cross_att):
+        self.language_attentions, self.vision_attentions, self.cross_encoder_attentions = lang_att, vis_att, cross_att
+        return self
+
 
 class B200LxmertModel(nn.Module):
     def __init__(self, dims: LxmertDims, passes: int = 3, source: Optional[nn.Module] = None):
@@ -64,8 +68,6 @@ class B200LxmertModel(nn.Module):
     def forward(self, input_ids=None, visual_feats=None, visual_pos=None, attention_mask=None,
                 visual_attention_mask=None, token_type_ids=None, inputs_embeds=None, output_attentions=None,
                 output_hidden_states=None, return_dict=None, language_stack=None, **kw):
-        if output_attentions:
-            raise NotImplementedError("attention probabilities are not exported by the fused path")
         if visual_feats is None or visual_pos is None:
             raise ValueError("`visual_feats` and `visual_pos` cannot be `None`")           # HF:746-749
         if input_ids is None and inputs_embeds is None:
@@ -86,9 +88,10 @@ class B200LxmertModel(nn.Module):
             V = visual_feats.shape[1]
             vmask = ((1.0 - visual_attention_mask.to(torch.float32)) * fmin).view(B, 1, 1, V)
         want_hidden = bool(output_hidden_states)
+        vis_att = lang_att = cross_att = None
         if language_stack is not None:
-            if want_hidden:
-                raise NotImplementedError("output_hidden_states with a cached language stack")
+            if want_hidden or output_attentions:
+                raise NotImplementedError("output_hidden_states / output_attentions with a cached language stack")
             (vis_states, _), (lang_states, _), _ = self.encoder(None, lmask, visual_feats, visual_pos, vmask,
                                                                  language_stack=language_stack)
         else:
@@ -96,10 +99,14 @@ class B200LxmertModel(nn.Module):
             prev = self.encoder.output_hidden_states
             self.encoder.output_hidden_states = want_hidden
             try:
-                (vis_states, _), (lang_states, _), _ = self.encoder(emb, lmask, visual_feats, visual_pos, vmask)
+                (vis_states, vis_att), (lang_states, lang_att), cross_att = self.encoder(
+                    emb, lmask, visual_feats, visual_pos, vmask, output_attentions=output_attentions)
             finally:
                 self.encoder.output_hidden_states = prev
         lang, vis = lang_states[-1], vis_states[-1]
         pooled = self.pooler(lang)
-        return LxmertOutput(lang, vis, pooled, lang_states if want_hidden else None,
-                            vis_states if want_hidden else None)
+        out = LxmertOutput(lang, vis, pooled, lang_states if want_hidden else None,
+                           vis_states if want_hidden else None)
+        if output_attentions:
+            out.with_attentions(lang_att, vis_att, cross_att)
+        return out
