@@ -132,3 +132,38 @@ def test_output_attentions_match_hf():
     with torch.no_grad():
         plain = native(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items() if k != "output_attentions"})
     assert plain.language_attentions is None and torch.equal(plain[0], n[0])
+
+
+@pytest.mark.gpu
+def test_inputs_embeds_path_matches_hf():
+    """``inputs_embeds`` instead of ``input_ids`` (HF:199-203,737-742): same outputs as the id path bit for bit when the
+    embeddings are the table rows, and the gradient with respect to ``inputs_embeds`` equals HF's."""
+    from xlxmert_b200 import synth
+    from xlxmert_b200.config import DEFAULT_DIMS as D
+    from xlxmert_b200.encoder import dims_from_hf_config
+    from xlxmert_b200.lxmert import B200LxmertModel
+    ref = _hf_model(seed=6, l_layers=2, r_layers=1, x_layers=1).train()
+    native = B200LxmertModel(dims_from_hf_config(ref.config), source=copy.deepcopy(ref).cuda()).train()
+    B, L, V = 2, 20, 64
+    batch = synth.make_batch(D, B, L, V, seed=4)
+    feats = synth.visual_feats_from(synth.centroid_table(D), batch["cluster_ids"])
+    ids = batch["input_ids"]
+    e_ref = ref.embeddings.word_embeddings.weight[ids].detach().clone().requires_grad_(True)
+    o = ref(inputs_embeds=e_ref, visual_feats=feats, visual_pos=batch["visual_pos"], attention_mask=batch["attention_mask"],
+            return_dict=True)
+    pl, pv = probes([o.language_output.shape, o.vision_output.shape], seed=2)
+    ((o.language_output * pl).sum() + (o.vision_output * pv).sum()).backward()
+    e_gpu = e_ref.detach().clone().cuda().requires_grad_(True)
+    kw = dict(visual_feats=feats.cuda(), visual_pos=batch["visual_pos"].cuda(), attention_mask=batch["attention_mask"].cuda())
+    g = native(inputs_embeds=e_gpu, **kw)
+    assert rel_err(g[0].detach().cpu(), o.language_output.detach()) < 1e-4
+    ((g[0] * pl.cuda()).sum() + (g[1] * pv.cuda()).sum()).backward()
+    assert rel_err(e_gpu.grad.cpu(), e_ref.grad) < 1e-3
+    assert native.embeddings.word_embeddings.weight.grad is None           # the table took no part
+    assert rel_err(native.embeddings.position_embeddings.weight.grad.cpu(), ref.embeddings.position_embeddings.weight.grad) < 1e-3
+    with torch.no_grad():
+        by_id = native(input_ids=ids.cuda(), **kw)
+        by_emb = native(inputs_embeds=e_gpu.detach(), **kw)
+    assert torch.equal(by_id[0], by_emb[0]) and torch.equal(by_id[1], by_emb[1])
+    with pytest.raises(ValueError):
+        native(input_ids=ids.cuda(), inputs_embeds=e_gpu.detach(), **kw)

@@ -93,9 +93,9 @@ def _sig(lib):
     lib.xlx_embeddings_scratch_bytes.restype = SZ
     lib.xlx_embeddings_scratch_bytes.argtypes = [D, I32, I32]
     lib.xlx_embeddings_fwd.restype = I32
-    lib.xlx_embeddings_fwd.argtypes = [D, I32, I32, P, P, PP, P, P, DR, P]
+    lib.xlx_embeddings_fwd.argtypes = [D, I32, I32, P, P, P, PP, P, P, DR, P]
     lib.xlx_embeddings_bwd.restype = I32
-    lib.xlx_embeddings_bwd.argtypes = [D, I32, I32, I32, I32, I32, P, P, PP, P, P, PP, P, SZ, DR, P]
+    lib.xlx_embeddings_bwd.argtypes = [D, I32, I32, I32, I32, I32, P, P, PP, P, P, PP, P, P, SZ, DR, P]
     lib.xlx_pooler_workspace_bytes.restype = SZ
     lib.xlx_pooler_workspace_bytes.argtypes = [D, I32]
     lib.xlx_pooler_fwd.restype = I32

@@ -236,18 +236,18 @@ size_t xlx_embeddings_scratch_bytes(const xlx_dims* d, int32_t B, int32_t L) {
 }
 
 int32_t xlx_embeddings_fwd(const xlx_dims* d, int32_t B, int32_t L, const int64_t* input_ids,
-                           const int64_t* token_type_ids, const float* const* params, float* out, void* save,
-                           const xlx_dropout* dropout, void* stream) {
+                           const float* inputs_embeds, const int64_t* token_type_ids, const float* const* params,
+                           float* out, void* save, const xlx_dropout* dropout, void* stream) {
   if (!hidden_ok(d)) return -20;
   if (B < 1 || L < 1) return -21;
-  if (!input_ids || !params || !out) return -24;
+  if ((!input_ids == !inputs_embeds) || !params || !out) return -24;     // exactly one of the two (HF:739-742)
   XLX_TRY(ensure_device(out));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int M = B * L, H = d->hidden;
   // without a save buffer (inference) the pre-LayerNorm sum goes through `out` itself, normalised in place
   EmbSave s = emb_layout(d, M, save);
   float* y = save ? s.y : out;
-  XLX_TRY(embed_sum(input_ids, token_type_ids, params[0], params[1], params[2], M, L, H, y, st));
+  XLX_TRY(embed_sum(input_ids, token_type_ids, input_ids ? params[0] : inputs_embeds, params[1], params[2], M, L, H, y, st));
   DropSite drop;
   if (dropout && dropout->p_hidden > 0.f) {
     if (!(dropout->p_hidden < 1.f) || !save) return -1;      // dropout is a training-forward thing
@@ -260,10 +260,11 @@ int32_t xlx_embeddings_fwd(const xlx_dims* d, int32_t B, int32_t L, const int64_
 int32_t xlx_embeddings_bwd(const xlx_dims* d, int32_t B, int32_t L, int32_t vocab, int32_t max_pos,
                            int32_t type_vocab, const int64_t* input_ids, const int64_t* token_type_ids,
                            const float* const* params, const void* save, const float* d_out, float* const* grads,
-                           void* scratch, size_t scratch_bytes, const xlx_dropout* dropout, void* stream) {
+                           float* d_inputs_embeds, void* scratch, size_t scratch_bytes, const xlx_dropout* dropout,
+                           void* stream) {
   if (!hidden_ok(d)) return -20;
   if (B < 1 || L < 1 || L > max_pos) return -21;
-  if (!input_ids || !params || !save || !d_out || !grads || !scratch) return -24;
+  if ((!input_ids == !d_inputs_embeds) || !params || !save || !d_out || !grads || !scratch) return -24;
   if (scratch_bytes < xlx_embeddings_scratch_bytes(d, B, L)) return -23;
   XLX_TRY(ensure_device(scratch));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -278,7 +279,10 @@ int32_t xlx_embeddings_bwd(const xlx_dims* d, int32_t B, int32_t L, int32_t voca
   XLX_TRY(layernorm_bwd(d_out, 1.0f, s.y, params[3], s.mean, s.rstd, M, H, dy, Split(), part, &nblk, st, drop));
   float* o[2] = {grads[3], grads[4]};
   XLX_TRY(colsum_finish(part, 2, nblk, H, o, 0, st));
-  XLX_CUDA(cudaMemsetAsync(grads[0], 0, static_cast<size_t>(vocab) * H * 4, st));
+  if (d_inputs_embeds)      // gradient wrt inputs_embeds = the LayerNorm-input gradient itself
+    XLX_CUDA(cudaMemcpyAsync(d_inputs_embeds, dy, static_cast<size_t>(M) * H * 4, cudaMemcpyDeviceToDevice, st));
+  else
+    XLX_CUDA(cudaMemsetAsync(grads[0], 0, static_cast<size_t>(vocab) * H * 4, st));
   XLX_CUDA(cudaMemsetAsync(grads[1], 0, static_cast<size_t>(max_pos) * H * 4, st));
   XLX_CUDA(cudaMemsetAsync(grads[2], 0, static_cast<size_t>(type_vocab) * H * 4, st));
   return embed_scatter(input_ids, token_type_ids, dy, M, L, H, grads[0], grads[1], grads[2], st);

@@ -102,7 +102,8 @@ __global__ void embed_sum_kernel(const int64_t* __restrict__ ids, const int64_t*
                                  const float* __restrict__ word, const float* __restrict__ pos,
                                  const float* __restrict__ type, int L, int H, float* y) {
   const int r = blockIdx.x;
-  const float4* w = reinterpret_cast<const float4*>(word + static_cast<size_t>(ids[r]) * H);
+  // ids == nullptr: `word` is an inputs_embeds matrix [rows, H] instead of the table (HF:199-203)
+  const float4* w = reinterpret_cast<const float4*>(word + static_cast<size_t>(ids ? ids[r] : r) * H);
   const float4* p = reinterpret_cast<const float4*>(pos + static_cast<size_t>(r % L) * H);
   const float4* t = reinterpret_cast<const float4*>(type + static_cast<size_t>(tt ? tt[r] : 0) * H);
   for (int c = threadIdx.x; c < H / 4; c += blockDim.x) {
@@ -116,7 +117,7 @@ __global__ void embed_scatter_kernel(const int64_t* __restrict__ ids, const int6
                                      const float* __restrict__ dy, int L, int H, float* dword, float* dpos,
                                      float* dtype) {
   const int r = blockIdx.x;
-  const int64_t id = ids[r], ty = tt ? tt[r] : 0;
+  const int64_t id = ids ? ids[r] : 0, ty = tt ? tt[r] : 0;     // no ids (inputs_embeds): the word table gets no gradient
   const int l = r % L;
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
     const float g = __ldg(dy + static_cast<size_t>(r) * H + c);

@@ -70,6 +70,8 @@ class B200LxmertModel(nn.Module):
                 output_hidden_states=None, return_dict=None, language_stack=None, **kw):
         if visual_feats is None or visual_pos is None:
             raise ValueError("`visual_feats` and `visual_pos` cannot be `None`")           # HF:746-749
+        if input_ids is not None and inputs_embeds is not None:
+            raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")   # HF:737-738
         if input_ids is None and inputs_embeds is None:
             raise ValueError("You have to specify either input_ids or inputs_embeds")      # HF:741-742
         ref = input_ids if input_ids is not None else inputs_embeds
