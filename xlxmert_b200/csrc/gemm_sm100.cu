@@ -197,7 +197,7 @@ __device__ __forceinline__ float4 epilogue_vec4(const KParams& P, int row, int n
 // that their code stays small — the epilogue warps share the instruction cache with the MMA-issuing warp.
 // EPI: 0 = load-bound epilogues (the common case), 1 = ACT, 2 = row statistics (soft-max / arg-max of the sampler's
 // logits GEMM, K-major operands only), 3 = split-K with the reduction folded into the last-arriving CTA (weight-gradient
-// layout only; XLX_GEMM_SPLITK_FOLD=1).  The rare modes are separate instantiations so that their state (16 extra live
+// layout only; XLX_GEMM_SPLITK_FOLD=1), 4 = SPADE modulation (the generator's γ/β convolution, K-major, N = BN = 64).  The rare modes are separate instantiations so that their state (16 extra live
 // registers for the row statistics, the extra barriers of the fold) cannot push the hot variant into spilling.
 template <int BK, int A_MN, int B_MN, int NPARTS, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -207,6 +207,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
   constexpr bool ACT = (EPI == 1);
   constexpr bool ROWSTAT = (EPI == 2);
   constexpr bool FOLD = (EPI == 3);
+  constexpr bool SPADE = (EPI == 4);
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
@@ -557,7 +558,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
       int last_c = -1;
       for (int c = half; c < nchunks; c += EPI_WARPS / 4)
         if (n0 + c * EPI_COLS < P.N) last_c = c;
-      if (last_c < 0) {   // nothing to read from this accumulator: hand it back right away
+      if (!SPADE && last_c < 0) {   // nothing to read from this accumulator: hand it back right away
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
@@ -568,6 +569,66 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
       for (int grp = 0; grp < ngrp; ++grp) {
       m0 = m0_item + grp * P.conv_W;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (ngrp * P.BN) + grp * P.BN;
+      if (SPADE) {
+        // thread = pixel row; the warps with half < 2 take channels half·16 … +15: their γ (columns c0 …) and β
+        // (columns 32 + c0 …) accumulators, the other two warps of the quadrant only hand the accumulator back
+        uint32_t rg[EPI_COLS], rb[EPI_COLS];
+        if (half < 2) {
+          tmem_ld_32x16(taddr + half * EPI_COLS, rg);
+          tmem_ld_32x16(taddr + 32 + half * EPI_COLS, rb);
+          tmem_ld_wait();
+        }
+        if (grp == ngrp - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
+        }
+        if (half < 2 && !(P.debug & 1)) {
+          const GemmEpilogue& E = P.epi;
+          const int row = m0 + q * 32 + lane, c0 = half * EPI_COLS;
+          if (row < P.M) {
+            const size_t b = static_cast<size_t>(row) >> E.spade_hw_log2;
+            const float* xr = E.spade_x + static_cast<size_t>(row) * E.spade_ldx + c0;
+            const float* mu = E.spade_mean + b * 32 + c0;
+            const float* rs = E.spade_rstd + b * 32 + c0;
+            const float nz = (E.spade_noise && E.spade_noise_w) ? __ldg(E.spade_noise_w) * __ldg(E.spade_noise + row) : 0.f;
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int j4 = 0; j4 < EPI_COLS / 4; ++j4) {
+              const float4 xv = __ldg(reinterpret_cast<const float4*>(xr) + j4);
+              const float4 m4 = __ldg(reinterpret_cast<const float4*>(mu) + j4);
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(rs) + j4);
+              const float4 bg = __ldg(reinterpret_cast<const float4*>(E.bias + c0) + j4);
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(E.bias + 32 + c0) + j4);
+              const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ms[4] = {m4.x, m4.y, m4.z, m4.w};
+              const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, gs[4] = {bg.x, bg.y, bg.z, bg.w}, bs[4] = {bb.x, bb.y, bb.z, bb.w};
+              float o[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float g = __uint_as_float(rg[j4 * 4 + k]) * E.alpha + gs[k];
+                const float bt = __uint_as_float(rb[j4 * 4 + k]) * E.alpha + bs[k];
+                const float t = ((xs[k] - ms[k]) * rr[k]) * (1.f + g) + bt + nz;      // same association as spade_pixel()
+                o[k] = t > 0.f ? t : 0.2f * t;
+              }
+              if (E.out_f32)
+                *reinterpret_cast<float4*>(E.out_f32 + static_cast<size_t>(row) * E.ld_out + c0 + j4 * 4) =
+                    make_float4(o[0], o[1], o[2], o[3]);
+              if (E.out_hi) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(o[0], h0, l0); split_bf16(o[1], h1, l1);
+                hw[(j4 & 1) * 2] = pack_bf16x2(h0, h1); lw[(j4 & 1) * 2] = pack_bf16x2(l0, l1);
+                split_bf16(o[2], h0, l0); split_bf16(o[3], h1, l1);
+                hw[(j4 & 1) * 2 + 1] = pack_bf16x2(h0, h1); lw[(j4 & 1) * 2 + 1] = pack_bf16x2(l0, l1);
+                if (j4 & 1) {      // eight channels ready: one 16-byte store per part
+                  const size_t idx = static_cast<size_t>(row) * E.ld_split + c0 + (j4 >> 1) * 8;
+                  *reinterpret_cast<uint4*>(E.out_hi + idx) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                  *reinterpret_cast<uint4*>(E.out_lo + idx) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+              }
+            }
+          }
+        }
+      } else
       for (int c = half; c <= last_c; c += EPI_WARPS / 4) {
         uint32_t r[EPI_COLS];
         tmem_ld_32x16(taddr + c * EPI_COLS, r);
@@ -1100,7 +1161,8 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   // split-K: only for plain fp32-output GEMMs (weight gradients) whose tile count leaves most SMs idle
   P.splits = 1; P.kb_per_split = nkb; P.part = nullptr;
   const bool plain = p.epi.out_f32 && !p.epi.bias && !p.epi.addend && !p.epi.addend_hi && !p.epi.out_hi &&
-                     !p.epi.out_u && !(p.epi.flags & ~EPI_ACCUM) && p.epi.alpha == 1.0f && !p.epi.drop.threshold;
+                     !p.epi.out_u && !(p.epi.flags & ~EPI_ACCUM) && p.epi.alpha == 1.0f && !p.epi.drop.threshold &&
+                     !p.epi.spade_x;
   static const int splitk_on = env_int("XLX_GEMM_SPLITK", 1);
   if (splitk_on && plain && p.splitk_ws && num_tiles * cta_per_item < num_sms) {
     // pick the split count whose work items fill whole waves of SMs best (ties → fewer splits)
@@ -1159,7 +1221,10 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
 #define XLX_LAUNCH(A, B, N)                                                                                   \
   lrc = act ? launch_variant<BK, A, B, N, 1>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)             \
             : launch_variant<BK, A, B, N, 0>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)
-    if (p.epi.rowstat) {                       // K-major operands only (checked by gemm_launch)
+    if (p.epi.spade_x) {                       // γ/β convolution of the generator (checked by gemm_launch)
+      lrc = P.nparts == 2 ? launch_variant<BK, 0, 0, 2, 4>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)
+                          : launch_variant<BK, 0, 0, 1, 4>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
+    } else if (p.epi.rowstat) {                // K-major operands only (checked by gemm_launch)
       lrc = P.nparts == 2 ? launch_variant<BK, 0, 0, 2, 2>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)
                           : launch_variant<BK, 0, 0, 1, 2>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
     } else if (P.tile_counter) {               // folded split-K: weight-gradient layout only (see below)
@@ -1267,6 +1332,13 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream) {
   if (E.colsum_part && ((E.flags & (EPI_GELU | EPI_TANH | EPI_RELU | EPI_GELU_GRAD)) || p.splitk_ws || E.drop.threshold))
     return -1;
   if (E.drop.threshold && (E.rowstat || p.conv.enabled)) return -1;
+  if (E.spade_x) {
+    if (p.a.mn_major || p.b.mn_major || p.N != 64 || !E.bias || !E.spade_mean || !E.spade_rstd || E.flags || E.rowstat ||
+        E.addend || E.addend_hi || E.out_u || E.colsum_part || E.drop.threshold || p.splitk_ws || (!E.out_f32 && !E.out_hi) ||
+        (E.out_hi && !E.out_lo) || (E.spade_ldx % 4) || (E.out_f32 && (E.ld_out % 4)) || (E.out_hi && (E.ld_split % 8)) ||
+        getenv("XLX_GEMM_BN"))
+      return -1;
+  }
   if ((E.flags & EPI_MUL) && !E.u_in && !E.u_in16) return -1;
   if (E.addend_hi && !E.addend_lo) return -1;
   if (E.rowstat && (p.a.mn_major || p.b.mn_major || E.out_f32 || E.out_hi || E.out_u || E.out_u16 || E.colsum_part || p.splitk_ws || E.flags ||

@@ -60,6 +60,16 @@ struct GemmEpilogue {
   // slots = gemm_rowstat_slots(N).  Columns ≥ rowstat_cols (padding) are ignored.  Finish with rowstat_merge().
   float* rowstat = nullptr;
   int rowstat_cols = 0;
+  // SPADE modulation epilogue (image_generator/src/layers.py:33-47,93-107) for the γ/β convolution (N = 64: columns
+  // 0-31 = γ, 32-63 = β of the same 32 channels): instead of writing γ|β, the epilogue reads the block input x and writes
+  //   out[p, c] = LeakyReLU_0.2( ((x[p, c] − mean[b, c])·rstd[b, c])·(1 + γ[p, c]) + β[p, c] + noise_w·noise[p] )
+  // as fp32 (out_f32, ld_out) and/or split bf16 (out_hi/out_lo, ld_split) — γ|β never reach memory.  b = p >> hw_log2.
+  const float* spade_x = nullptr;       // [pixels, spade_ldx] fp32, first 32 channels
+  const float* spade_mean = nullptr;    // [B, 32] InstanceNorm statistics
+  const float* spade_rstd = nullptr;
+  const float* spade_noise = nullptr;   // [pixels] or null
+  const float* spade_noise_w = nullptr; // device scalar (NoiseInjection.weight) or null
+  int spade_ldx = 0, spade_hw_log2 = 0;
   // Optional dropout of the value after bias / activation and BEFORE the addends (LxmertAttentionOutput / LxmertOutput:
   // dropout(dense(x)) + residual, HF:282-287,344-349).  The GEMM must span the whole [M, N] matrix the site covers
   // (element index = row·N + col).  drop.threshold == 0: off.

@@ -626,8 +626,12 @@ int32_t xlx_generator_fwd(const float* const* P, const void* prep, int32_t B, co
     resize_split_kernel<<<blocks_for(npix * (CH / 4)), 256, 0, st>>>(y, 64, R0, R, npix, w.yup[i].hi, w.yup[i].lo);
     XLX_TRY(krc());
   }
-  // SPADE parameter maps at resolution index ri for SPADE instance (i, j): gb = [γ | β] fp32 [B,R,R,64]
-  auto spade_params = [&](int i, int j, int ri) -> int {
+  // SPADE parameter maps at resolution index ri for SPADE instance (i, j): gb = [γ | β] fp32 [B,R,R,64] — or, with
+  // `mod` given, the modulated + activated block input itself straight out of the γ/β convolution's epilogue (γ|β never
+  // written): split bf16 into w.a (up = 1) or fp32 [B,R,R,32] into w.gb for the ×2 bilinear kernel (up = 2)
+  struct Modulate { const float* x; int ldx; const float* noise; const float* noise_w; int up; };
+  static const bool spade_epi = [] { const char* e = getenv("XLX_SPADE_EPILOGUE"); return !(e && e[0] == '0'); }();
+  auto spade_params = [&](int i, int j, int ri, const Modulate* mod) -> int {
     const int R = R0 << ri;
     if (analytic) {
       // Z = y·W_tᵀ for all taps (one GEMM at 8×8), row stage, column stage + ReLU → actv; Ry borrows the γ/β buffer,
@@ -647,7 +651,16 @@ int32_t xlx_generator_fwd(const float* const* P, const void* prep, int32_t B, co
       XLX_TRY(conv(passes, st, w.yup[ri], B, R, CH, 9, p.sp[i][j].shared, HID, HID, e));
     }
     GemmEpilogue g;
-    g.bias = p.sp[i][j].gb_bias; g.out_f32 = w.gb; g.ld_out = 2 * CH;
+    g.bias = p.sp[i][j].gb_bias;
+    if (mod) {
+      g.spade_x = mod->x; g.spade_ldx = mod->ldx; g.spade_mean = w.mean; g.spade_rstd = w.rstd;
+      g.spade_noise = mod->noise; g.spade_noise_w = mod->noise_w;
+      g.spade_hw_log2 = 2 * (31 - __builtin_clz(static_cast<unsigned>(R)));
+      if (mod->up == 1) { g.out_hi = w.a.hi; g.out_lo = w.a.lo; g.ld_split = CH; }
+      else { g.out_f32 = w.gb; g.ld_out = CH; }
+    } else {
+      g.out_f32 = w.gb; g.ld_out = 2 * CH;
+    }
     return conv(passes, st, w.actv, B, R, HID, 9, p.sp[i][j].gb, 2 * CH, 2 * CH, g);
   };
 
@@ -660,10 +673,17 @@ int32_t xlx_generator_fwd(const float* const* P, const void* prep, int32_t B, co
     const float* n2 = noise ? noise[2 * i + 1] : nullptr;
     // cbn1 → noise1 → LeakyReLU → ×2 bilinear (layers.py:96-101)
     XLX_TRY(instance_stats(x, ldx, B, R * R, w, st));
-    XLX_TRY(spade_params(i, 0, i));
     const size_t npix1 = npix2 / 4;
-    spade_up2_kernel<<<blocks_for(npix1 * (CH / 4)), 256, 0, st>>>(x, ldx, w.mean, w.rstd, w.gb, n1, P[s + 24], R, npix1,
-                                                                   w.a.hi, w.a.lo);
+    if (spade_epi) {
+      const Modulate m1{x, ldx, n1, P[s + 24], 2};
+      XLX_TRY(spade_params(i, 0, i, &m1));          // w.gb ← lrelu(spade(x)) at R×R, fp32 [B,R,R,32]
+      spade_up2_kernel<<<blocks_for(npix1 * (CH / 4)), 256, 0, st>>>(w.gb, CH, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                     R, npix1, w.a.hi, w.a.lo);
+    } else {
+      XLX_TRY(spade_params(i, 0, i, nullptr));
+      spade_up2_kernel<<<blocks_for(npix1 * (CH / 4)), 256, 0, st>>>(x, ldx, w.mean, w.rstd, w.gb, n1, P[s + 24], R, npix1,
+                                                                     w.a.hi, w.a.lo);
+    }
     XLX_TRY(krc());
     // residual branch input: ×2 bilinear of x (layers.py:88-91)
     spade_up2_kernel<<<blocks_for(npix1 * (CH / 4)), 256, 0, st>>>(x, ldx, nullptr, nullptr, nullptr, nullptr, nullptr, R,
@@ -677,10 +697,15 @@ int32_t xlx_generator_fwd(const float* const* P, const void* prep, int32_t B, co
     }
     // cbn2 → noise2 → LeakyReLU (layers.py:104-107)
     XLX_TRY(instance_stats(w.h1, CH, B, R2 * R2, w, st));
-    XLX_TRY(spade_params(i, 1, i + 1));
-    spade_act_kernel<<<blocks_for(npix2 * (CH / 4)), 256, 0, st>>>(w.h1, CH, w.mean, w.rstd, w.gb, n2, P[s + 25], R2, 1,
-                                                                   npix2, w.a.hi, w.a.lo);
-    XLX_TRY(krc());
+    if (spade_epi) {
+      const Modulate m2{w.h1, CH, n2, P[s + 25], 1};
+      XLX_TRY(spade_params(i, 1, i + 1, &m2));      // w.a ← lrelu(spade(h1)) as split bf16, the operand of conv2
+    } else {
+      XLX_TRY(spade_params(i, 1, i + 1, nullptr));
+      spade_act_kernel<<<blocks_for(npix2 * (CH / 4)), 256, 0, st>>>(w.h1, CH, w.mean, w.rstd, w.gb, n2, P[s + 25], R2, 1,
+                                                                     npix2, w.a.hi, w.a.lo);
+      XLX_TRY(krc());
+    }
     // conv2, then out = h + res_branch(x): the 1×1 conv accumulates onto conv2's output (layers.py:108-112)
     // ping-pong: blocks alternate between the two buffers; the largest (last) block uses the full-size of[0]
     float* of = ((NBLK - 1 - i) & 1) ? w.of[1] : w.of[0];
