@@ -20,3 +20,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _fresh_library():
+    """The tests load ``xlxmert_b200/lib/libxlxmert_b200.so`` as it lies in the tree; rebuild it first whenever the CUDA
+    sources changed since it was built (a no-op when the build stamp matches), so that a stale binary can never be what
+    a green or red result is about."""
+    import __graft_entry__ as entry
+    entry.build()
