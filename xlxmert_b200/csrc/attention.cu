@@ -102,11 +102,15 @@ __device__ __forceinline__ float quad_max(float v) {
 // ---- forward ------------------------------------------------------------------------------------------
 // maps: [0] Q hi, [1] Q lo, [2] K hi, [3] K lo, [4] V hi, [5] V lo — 2-D maps over the split [rows, ld] matrices
 struct FwdMaps { CUtensorMap m[6]; };
-template <bool DROP>     // compile-time: the inference / p = 0 instantiation carries no dropout code or registers
+// PACK (self-attention with S ≤ 32 only): one CTA serves G = 64 / S consecutive samples.  Their rows are contiguous
+// in memory, so the same 64-row TMA boxes bring them in; the score tile is block-diagonal — entries pairing different
+// samples are masked to −inf before the soft-max and contribute exact zeros to P·V.  The language stack's (S ≤ 20)
+// kernels were bound by per-CTA latency, not work: a third of the CTAs do the same job.
+template <bool DROP, bool PACK>   // compile-time: the inference / p = 0 instantiation carries no dropout code or registers
 __global__ void __launch_bounds__(AT)
 attn_fwd_mma_kernel(const __grid_constant__ FwdMaps maps, int qcol, int kcol, int vcol,
                     const float* __restrict__ mask, int heads, int Sq, int Sk, bf16* ctx_hi, bf16* ctx_lo,
-                    float* ctx_f32, int ld_ctx, float* probs, const DropSite drop) {
+                    float* ctx_f32, int ld_ctx, float* probs, const DropSite drop, int nbatch) {
   extern __shared__ uint8_t smem_attn_raw[];
   __shared__ __align__(8) uint64_t bar;
   bf16* Qh = reinterpret_cast<bf16*>(smem_attn_raw + ((1024u - (smem_u32(smem_attn_raw) & 1023u)) & 1023u));
@@ -115,13 +119,16 @@ attn_fwd_mma_kernel(const __grid_constant__ FwdMaps maps, int qcol, int kcol, in
   bf16* Kl = Kh + TT;
   bf16* Vh = Kl + TT;
   bf16* Vl = Vh + TT;
-  const int h = blockIdx.x, b = blockIdx.y;
+  // S1: per-sample sequence length; packed mode turns (Sq, Sk) into the extent of the G samples this CTA serves
+  const int S1 = Sq;
+  const int h = blockIdx.x, b = PACK ? blockIdx.y * (64 / S1) : blockIdx.y;
+  if (PACK) { const int gc = min(64 / S1, nbatch - b); Sq = Sk = gc * S1; }
   pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const size_t qrow0 = static_cast<size_t>(b) * Sq;
+  const size_t qrow0 = static_cast<size_t>(b) * S1;
   {
-    const int qr = b * Sq, kr = b * Sk;
+    const int qr = b * S1, kr = PACK ? b * S1 : b * Sk;
     const TileSrc src[6] = {{&maps.m[0], qcol + h * 64, qr}, {&maps.m[1], qcol + h * 64, qr},
                             {&maps.m[2], kcol + h * 64, kr}, {&maps.m[3], kcol + h * 64, kr},
                             {&maps.m[4], vcol + h * 64, kr}, {&maps.m[5], vcol + h * 64, kr}};
@@ -130,6 +137,9 @@ attn_fwd_mma_kernel(const __grid_constant__ FwdMaps maps, int qcol, int kcol, in
   const int r0 = warp * 16;
   if (r0 >= Sq) return;
   const int nk16 = (Sk + 15) >> 4;     // 16-key steps; score n-tiles = 2·nk16
+  const int i0 = r0 + g, i1 = r0 + g + 8;
+  // packed mode: sample slot and in-sample index of this thread's two query rows
+  const int gi0 = PACK ? i0 / S1 : 0, gi1 = PACK ? i1 / S1 : 0;
 
   // S = Q·Kᵀ
   float s[8][4];
@@ -158,9 +168,16 @@ attn_fwd_mma_kernel(const __grid_constant__ FwdMaps maps, int qcol, int kcol, in
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = nt * 8 + 2 * t + e;
-        const float mk = (j < Sk) ? (mask ? __ldg(mask + static_cast<size_t>(b) * Sk + j) : 0.f) : -INFINITY;
-        s[nt][e] = s[nt][e] * 0.125f + mk;          // scores / sqrt(64) then + mask (HF:255-259)
-        s[nt][2 + e] = s[nt][2 + e] * 0.125f + mk;
+        if (PACK) {
+          const int gj = j / S1;
+          const float mk = (j < Sk) ? (mask ? __ldg(mask + static_cast<size_t>(b + gj) * S1 + (j - gj * S1)) : 0.f) : -INFINITY;
+          s[nt][e] = (gj == gi0) ? s[nt][e] * 0.125f + mk : -INFINITY;         // other samples' keys: not part of this row
+          s[nt][2 + e] = (gj == gi1) ? s[nt][2 + e] * 0.125f + mk : -INFINITY;
+        } else {
+          const float mk = (j < Sk) ? (mask ? __ldg(mask + static_cast<size_t>(b) * Sk + j) : 0.f) : -INFINITY;
+          s[nt][e] = s[nt][e] * 0.125f + mk;          // scores / sqrt(64) then + mask (HF:255-259)
+          s[nt][2 + e] = s[nt][2 + e] * 0.125f + mk;
+        }
         mx0 = fmaxf(mx0, s[nt][e]);
         mx1 = fmaxf(mx1, s[nt][2 + e]);
       }
@@ -179,22 +196,39 @@ attn_fwd_mma_kernel(const __grid_constant__ FwdMaps maps, int qcol, int kcol, in
     }
   }
   const float inv0 = 1.0f / quad_sum(sum0), inv1 = 1.0f / quad_sum(sum1);
-  const int i0 = r0 + g, i1 = r0 + g + 8;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     if (nt < 2 * nk16) {
       s[nt][0] *= inv0; s[nt][1] *= inv0; s[nt][2] *= inv1; s[nt][3] *= inv1;
-      if (probs) {
-        const int j = nt * 8 + 2 * t;
-        float* pr = probs + (static_cast<size_t>(b) * heads + h) * Sq * Sk;
-        if (i0 < Sq) { if (j < Sk) pr[i0 * Sk + j] = s[nt][0]; if (j + 1 < Sk) pr[i0 * Sk + j + 1] = s[nt][1]; }
-        if (i1 < Sq) { if (j < Sk) pr[i1 * Sk + j] = s[nt][2]; if (j + 1 < Sk) pr[i1 * Sk + j + 1] = s[nt][3]; }
-      }
-      if (DROP) {   // dropout(attention_probs) (HF:262-266): P·V below sees P ∘ mask / (1 − p)
-        const int j = nt * 8 + 2 * t;
-        const size_t rbase = (static_cast<size_t>(b) * heads + h) * Sq;
-        const float2 m0 = drop_prob2(drop, rbase + i0, Sk, j), m1 = drop_prob2(drop, rbase + i1, Sk, j);
-        s[nt][0] *= m0.x; s[nt][1] *= m0.y; s[nt][2] *= m1.x; s[nt][3] *= m1.y;
+      if (PACK) {
+        // per element: (sample slot, in-sample key) of column j; only same-sample entries exist in probs / get a mask
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * t + e, gj = j / S1, jj = j - gj * S1;
+          if (probs && j < Sk) {
+            if (i0 < Sq && gj == gi0)
+              probs[((static_cast<size_t>(b + gi0) * heads + h) * S1 + (i0 - gi0 * S1)) * S1 + jj] = s[nt][e];
+            if (i1 < Sq && gj == gi1)
+              probs[((static_cast<size_t>(b + gi1) * heads + h) * S1 + (i1 - gi1 * S1)) * S1 + jj] = s[nt][2 + e];
+          }
+          if (DROP) {
+            if (gj == gi0) s[nt][e] *= drop_prob1(drop, (static_cast<size_t>(b + gi0) * heads + h) * S1 + (i0 - gi0 * S1), S1, jj);
+            if (gj == gi1) s[nt][2 + e] *= drop_prob1(drop, (static_cast<size_t>(b + gi1) * heads + h) * S1 + (i1 - gi1 * S1), S1, jj);
+          }
+        }
+      } else {
+        if (probs) {
+          const int j = nt * 8 + 2 * t;
+          float* pr = probs + (static_cast<size_t>(b) * heads + h) * Sq * Sk;
+          if (i0 < Sq) { if (j < Sk) pr[i0 * Sk + j] = s[nt][0]; if (j + 1 < Sk) pr[i0 * Sk + j + 1] = s[nt][1]; }
+          if (i1 < Sq) { if (j < Sk) pr[i1 * Sk + j] = s[nt][2]; if (j + 1 < Sk) pr[i1 * Sk + j + 1] = s[nt][3]; }
+        }
+        if (DROP) {   // dropout(attention_probs) (HF:262-266): P·V below sees P ∘ mask / (1 − p)
+          const int j = nt * 8 + 2 * t;
+          const size_t rbase = (static_cast<size_t>(b) * heads + h) * Sq;
+          const float2 m0 = drop_prob2(drop, rbase + i0, Sk, j), m1 = drop_prob2(drop, rbase + i1, Sk, j);
+          s[nt][0] *= m0.x; s[nt][1] *= m0.y; s[nt][2] *= m1.x; s[nt][3] *= m1.y;
+        }
       }
     }
   }
@@ -256,11 +290,11 @@ attn_fwd_mma_kernel(const __grid_constant__ FwdMaps maps, int qcol, int kcol, in
 // dP = dO·Vᵀ;  dS = P ∘ (dP − rowsum(P ∘ dP)) / 8;  dQ = dS·K;  dV = Pᵀ·dO;  dK = dSᵀ·Q.
 // maps: Q, K, V, dO (hi, lo each)
 struct BwdMaps { CUtensorMap m[8]; };
-template <bool DROP>
+template <bool DROP, bool PACK>
 __global__ void __launch_bounds__(AT)
 attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, int vcol, int ocol,
                     const float* __restrict__ probs, int heads, int Sq, int Sk, bf16* dq_hi, bf16* dq_lo, bf16* dk_hi,
-                    bf16* dk_lo, bf16* dv_hi, bf16* dv_lo, int ld_d, const DropSite drop) {
+                    bf16* dk_lo, bf16* dv_hi, bf16* dv_lo, int ld_d, const DropSite drop, int nbatch) {
   extern __shared__ uint8_t smem_attn_raw[];
   __shared__ __align__(8) uint64_t bar;
   bf16* Qh = reinterpret_cast<bf16*>(smem_attn_raw + ((1024u - (smem_u32(smem_attn_raw) & 1023u)) & 1023u));
@@ -276,13 +310,15 @@ attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, in
   bf16* Pl = Vl;
   bf16* Sh = Kh;
   bf16* Sl = Kl;
-  const int h = blockIdx.x, b = blockIdx.y;
+  const int S1 = Sq;       // per-sample length; packed mode (see the forward kernel) widens (Sq, Sk) to the CTA's samples
+  const int h = blockIdx.x, b = PACK ? blockIdx.y * (64 / S1) : blockIdx.y;
+  if (PACK) { const int gc = min(64 / S1, nbatch - b); Sq = Sk = gc * S1; }
   pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const size_t qrow0 = static_cast<size_t>(b) * Sq, krow0 = static_cast<size_t>(b) * Sk;
+  const size_t qrow0 = static_cast<size_t>(b) * S1, krow0 = PACK ? qrow0 : static_cast<size_t>(b) * Sk;
   {
-    const int qr = b * Sq, kr = b * Sk;
+    const int qr = b * S1, kr = PACK ? b * S1 : b * Sk;
     const TileSrc src[8] = {{&maps.m[0], qcol + h * 64, qr}, {&maps.m[1], qcol + h * 64, qr},
                             {&maps.m[2], kcol + h * 64, kr}, {&maps.m[3], kcol + h * 64, kr},
                             {&maps.m[4], vcol + h * 64, kr}, {&maps.m[5], vcol + h * 64, kr},
@@ -321,16 +357,33 @@ attn_bwd_mma_kernel(const __grid_constant__ BwdMaps maps, int qcol, int kcol, in
     }
     float dot0 = 0.f, dot1 = 0.f;
     const float* pr = probs + (static_cast<size_t>(b) * heads + h) * Sq * Sk;
+    const int gi0 = PACK ? i0 / S1 : 0, gi1 = PACK ? i1 / S1 : 0;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       if (nt < 2 * nk16) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = nt * 8 + 2 * t + e;
-          p[nt][e] = (i0 < Sq && j < Sk) ? __ldg(pr + i0 * Sk + j) : 0.f;
-          p[nt][2 + e] = (i1 < Sq && j < Sk) ? __ldg(pr + i1 * Sk + j) : 0.f;
+          if (PACK) {
+            // probabilities exist for same-sample pairs only; everything else is an exact zero of the block-diagonal tile
+            const int gj = j / S1, jj = j - gj * S1;
+            const bool ok0 = i0 < Sq && j < Sk && gj == gi0, ok1 = i1 < Sq && j < Sk && gj == gi1;
+            const size_t r0p = (static_cast<size_t>(b + gi0) * heads + h) * S1 + (i0 - gi0 * S1);
+            const size_t r1p = (static_cast<size_t>(b + gi1) * heads + h) * S1 + (i1 - gi1 * S1);
+            p[nt][e] = ok0 ? __ldg(probs + r0p * S1 + jj) : 0.f;
+            p[nt][2 + e] = ok1 ? __ldg(probs + r1p * S1 + jj) : 0.f;
+            if (DROP) {
+              constexpr int kD = DROP ? 1 : 0;
+              const float m0 = ok0 ? drop_prob1(drop, r0p, S1, jj) : 0.f, m1 = ok1 ? drop_prob1(drop, r1p, S1, jj) : 0.f;
+              dp[nt][e] *= m0; dp[nt][2 + e] *= m1;
+              pm[nt * kD][e] = p[nt][e] * m0; pm[nt * kD][2 + e] = p[nt][2 + e] * m1;
+            }
+          } else {
+            p[nt][e] = (i0 < Sq && j < Sk) ? __ldg(pr + i0 * Sk + j) : 0.f;
+            p[nt][2 + e] = (i1 < Sq && j < Sk) ? __ldg(pr + i1 * Sk + j) : 0.f;
+          }
         }
-        if (DROP) {
+        if (DROP && !PACK) {
           // forward: ctx = (P ∘ m)·V with m = mask / (1 − p).  dp holds d(P ∘ m) = dO·Vᵀ → dP = dp ∘ m; the P tile
           // phase 2 contracts with dO (dV = (P ∘ m)ᵀ·dO) is the dropped one: pm below.
           const int j = nt * 8 + 2 * t;
@@ -478,6 +531,17 @@ bool operand_ok(const AttnOperand& o) {
   return o.base.hi && o.base.lo && o.ld % 8 == 0 && o.col % 8 == 0 && o.rows > 0 &&
          !((reinterpret_cast<uintptr_t>(o.base.hi) | reinterpret_cast<uintptr_t>(o.base.lo)) & 15);
 }
+// one CTA per several samples: self-attention (Q, K, V rows of one matrix) with S ≤ 32
+bool pack_self(const AttnOperand& q, const AttnOperand& k, const AttnOperand& v, int Sq, int Sk) {
+  static const bool on = [] { const char* e = getenv("XLX_ATTN_PACK"); return !(e && e[0] == '0'); }();
+  return on && Sq == Sk && Sq <= 32 && q.base.hi == k.base.hi && k.base.hi == v.base.hi && q.rows == k.rows &&
+         k.rows == v.rows && q.ld == k.ld && k.ld == v.ld;
+}
+template <typename K>
+int set_smem(K kernel, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
 }  // namespace
 
 int attention_fwd(AttnOperand q, AttnOperand k, AttnOperand v, const float* mask, int B, int heads, int Sq, int Sk,
@@ -488,11 +552,11 @@ int attention_fwd(AttnOperand q, AttnOperand k, AttnOperand v, const float* mask
   constexpr size_t smem = 6 * TT * sizeof(bf16) + 1024;
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_fwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return static_cast<int>(e);
+    int rc = set_smem(attn_fwd_mma_kernel<false, false>, smem);
+    if (!rc) rc = set_smem(attn_fwd_mma_kernel<true, false>, smem);
+    if (!rc) rc = set_smem(attn_fwd_mma_kernel<false, true>, smem);
+    if (!rc) rc = set_smem(attn_fwd_mma_kernel<true, true>, smem);
+    if (rc) return rc;
     set = true;
   }
   FwdMaps maps;
@@ -500,12 +564,13 @@ int attention_fwd(AttnOperand q, AttnOperand k, AttnOperand v, const float* mask
   if ((rc = operand_maps(&maps.m[0], &maps.m[1], q))) return rc;
   if ((rc = operand_maps(&maps.m[2], &maps.m[3], k))) return rc;
   if ((rc = operand_maps(&maps.m[4], &maps.m[5], v))) return rc;
-  if (drop.threshold)
-    launch_pdl(attn_fwd_mma_kernel<true>, dim3(heads, B), dim3(AT), smem, s, maps, q.col, k.col, v.col, mask, heads, Sq, Sk,
-               ctx.hi, ctx.lo, ctx_f32, ld_ctx, probs, drop);
-  else
-    launch_pdl(attn_fwd_mma_kernel<false>, dim3(heads, B), dim3(AT), smem, s, maps, q.col, k.col, v.col, mask, heads, Sq, Sk,
-               ctx.hi, ctx.lo, ctx_f32, ld_ctx, probs, drop);
+  const bool pack = pack_self(q, k, v, Sq, Sk);
+  const int per = pack ? 64 / Sq : 1;
+  const dim3 grid(heads, (B + per - 1) / per);
+  auto kernel = pack ? (drop.threshold ? attn_fwd_mma_kernel<true, true> : attn_fwd_mma_kernel<false, true>)
+                     : (drop.threshold ? attn_fwd_mma_kernel<true, false> : attn_fwd_mma_kernel<false, false>);
+  launch_pdl(kernel, grid, dim3(AT), smem, s, maps, q.col, k.col, v.col, mask, heads, Sq, Sk, ctx.hi, ctx.lo, ctx_f32, ld_ctx,
+             probs, drop, B);
   count_aux_launch();
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);
@@ -519,11 +584,11 @@ int attention_bwd(AttnOperand dctx, AttnOperand q, AttnOperand k, AttnOperand v,
   constexpr size_t smem = 8 * TT * sizeof(bf16) + 1024;
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_bwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return static_cast<int>(e);
+    int rc = set_smem(attn_bwd_mma_kernel<false, false>, smem);
+    if (!rc) rc = set_smem(attn_bwd_mma_kernel<true, false>, smem);
+    if (!rc) rc = set_smem(attn_bwd_mma_kernel<false, true>, smem);
+    if (!rc) rc = set_smem(attn_bwd_mma_kernel<true, true>, smem);
+    if (rc) return rc;
     set = true;
   }
   BwdMaps maps;
@@ -532,12 +597,13 @@ int attention_bwd(AttnOperand dctx, AttnOperand q, AttnOperand k, AttnOperand v,
   if ((rc = operand_maps(&maps.m[2], &maps.m[3], k))) return rc;
   if ((rc = operand_maps(&maps.m[4], &maps.m[5], v))) return rc;
   if ((rc = operand_maps(&maps.m[6], &maps.m[7], dctx))) return rc;
-  if (drop.threshold)
-    launch_pdl(attn_bwd_mma_kernel<true>, dim3(heads, B), dim3(AT), smem, s, maps, q.col, k.col, v.col, dctx.col, probs, heads,
-               Sq, Sk, dq.hi, dq.lo, dk.hi, dk.lo, dv.hi, dv.lo, ld_d, drop);
-  else
-    launch_pdl(attn_bwd_mma_kernel<false>, dim3(heads, B), dim3(AT), smem, s, maps, q.col, k.col, v.col, dctx.col, probs, heads,
-               Sq, Sk, dq.hi, dq.lo, dk.hi, dk.lo, dv.hi, dv.lo, ld_d, drop);
+  const bool pack = pack_self(q, k, v, Sq, Sk) && dctx.rows == q.rows;
+  const int per = pack ? 64 / Sq : 1;
+  const dim3 grid(heads, (B + per - 1) / per);
+  auto kernel = pack ? (drop.threshold ? attn_bwd_mma_kernel<true, true> : attn_bwd_mma_kernel<false, true>)
+                     : (drop.threshold ? attn_bwd_mma_kernel<true, false> : attn_bwd_mma_kernel<false, false>);
+  launch_pdl(kernel, grid, dim3(AT), smem, s, maps, q.col, k.col, v.col, dctx.col, probs, heads, Sq, Sk, dq.hi, dq.lo, dk.hi,
+             dk.lo, dv.hi, dv.lo, ld_d, drop, B);
   count_aux_launch();
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);

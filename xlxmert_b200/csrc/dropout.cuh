@@ -82,6 +82,11 @@ __device__ __forceinline__ float2 drop_prob2(const DropSite& d, size_t r, int Sk
   const uint4 w = drop_words(d, static_cast<uint64_t>(r) * ((Sk + 1) >> 1) + (j >> 1));
   return make_float2(drop_mul(d, w.x), drop_mul(d, w.y));
 }
+// multiplier of the single probability (r, j) — same value as the matching lane of drop_prob2
+__device__ __forceinline__ float drop_prob1(const DropSite& d, size_t r, int Sk, int j) {
+  const uint4 w = drop_words(d, static_cast<uint64_t>(r) * ((Sk + 1) >> 1) + (j >> 1));
+  return drop_mul(d, (j & 1) ? w.y : w.x);
+}
 #endif
 
 }  // namespace xlx
