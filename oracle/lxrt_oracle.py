@@ -295,6 +295,21 @@ def feat_loss(pred_feat: Tensor, feat_labels: Tensor, vis_mask: Tensor) -> Tenso
     return ((h * m).sum(1) / m.sum(1).clamp(min=1)).mean()
 
 
+def answer_head(sd: SD, pooled: Tensor) -> Tensor:
+    """HF ``LxmertVisualAnswerHead`` (HF modeling_lxmert.py:610-623), the reference's ``answer_head``
+    (x-lxmert/src/lxrt/modeling.py:90,289): ``Linear(H, 2H) → GeLU → LayerNorm(2H, eps 1e-12) → Linear(2H, labels)``
+    on the pooled output.  State-dict keys: ``logit_fc.{0,2,3}.{weight,bias}``."""
+    t = layer_norm(gelu_erf(linear(pooled, sd["logit_fc.0.weight"], sd["logit_fc.0.bias"])),
+                   sd["logit_fc.2.weight"], sd["logit_fc.2.bias"])
+    return linear(t, sd["logit_fc.3.weight"], sd["logit_fc.3.bias"])
+
+
+def qa_loss(sd: SD, pooled: Tensor, qa_labels: Tensor):
+    """``CrossEntropyLoss()(answer_score, ans)`` and ``answer_score.max(1)`` ids (modeling.py:287-299)."""
+    score = answer_head(sd, pooled)
+    return cross_entropy_mean(score, qa_labels.reshape(-1)), score.argmax(dim=1)
+
+
 def lm_head(sd_cls: SD, lang_out: Tensor, pooled: Tensor):
     """``LxmertPreTrainingHeads`` (HF:656-665, 597-607); decoder weight tied to word embeddings."""
     t = head_transform(sub(sd_cls, "predictions.transform"), lang_out)

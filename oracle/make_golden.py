@@ -180,6 +180,85 @@ def golden_pretrain(name, d, B, wseed, bseed):
     save(name, rec)
 
 
+def golden_pretrain_feat_qa(name, d, B, wseed, bseed, n_answers=157):
+    """The reference model AS PUBLISHED: ``visual_losses`` = obj + feat (modeling.py:117-137; the
+    default ``--visualLosses obj,feat``, param.py:123) and ``--taskQA`` (modeling.py:89-90,286-299): the QA loss is
+    added to every task's loss; for ``matched`` the labels of flipped pairs are ignored (lxmert_pretrain.py:184-189)."""
+    model = refshim.build_pretraining_model(
+        num_clusters=d.num_clusters, keep_feat_loss=True, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+        task_qa=True, num_qa_labels=n_answers, visual_attr_loss=False)   # lxmert_pretrain.py:72-74: from --visualLosses
+    sd_bert = P.init_state_dict(P.model_param_specs(d), seed=wseed, randomize_ln_bias=True)
+    sd_head = P.init_state_dict(P.objhead_param_specs(d), seed=wseed + 1, randomize_ln_bias=True)
+    cls_specs = [("predictions.transform.dense.weight", (d.hidden, d.hidden)),
+                 ("predictions.transform.dense.bias", (d.hidden,)),
+                 ("predictions.transform.LayerNorm.weight", (d.hidden,)),
+                 ("predictions.transform.LayerNorm.bias", (d.hidden,)),
+                 ("predictions.bias", (d.vocab,)),
+                 ("seq_relationship.weight", (2, d.hidden)), ("seq_relationship.bias", (2,))]
+    sd_cls = P.init_state_dict(cls_specs, seed=wseed + 2, randomize_ln_bias=True)
+    sd_ans = P.init_state_dict(P.answerhead_param_specs(d, n_answers), seed=wseed + 4, randomize_ln_bias=True)
+    table = synth.centroid_table(d)
+    g = torch.Generator().manual_seed(wseed + 3)
+    mask_feat = 0.05 * torch.randn(d.feat_dim, generator=g)
+    model.set_visual_embedding(table.clone())
+    full = {"bert." + k: v for k, v in sd_bert.items()}
+    full.update({"obj_predict_head." + k: v for k, v in sd_head.items() if k != "out_cluster.weight"})
+    full.update({"cls." + k: v for k, v in sd_cls.items()})
+    full.update({"answer_head." + k: v for k, v in sd_ans.items()})
+    full["mask_feat"] = mask_feat
+    missing, unexpected = model.load_state_dict(full, strict=False)
+    assert not unexpected, unexpected
+    bad = [k for k in missing if not any(s in k for s in ("position_ids", "vis_emb", "out_cluster.weight",
+                                                          "decoder.weight", "decoder.bias"))]
+    assert not bad, bad
+    model.eval()
+    batch = synth.make_batch(d, B, 20, 64, seed=bseed)
+    feat_labels, qa_labels = synth.feat_qa_targets(d, B, bseed, n_answers)
+    rec = dict(meta=np.array([B, 20, 64, wseed, bseed, n_answers]),
+               weights_checksum=torch.tensor(checksum(sd_bert) + checksum(sd_head) + checksum(sd_cls) + checksum(sd_ans),
+                                             dtype=torch.float64),
+               inputs_checksum=torch.tensor(feat_labels.double().abs().sum().item() + qa_labels.sum().item(),
+                                            dtype=torch.float64))
+    common = dict(visual_pos=batch["visual_pos"], attention_mask=batch["attention_mask"],
+                  cluster_ids=batch["cluster_ids"], vis_mask=batch["vis_mask"],
+                  token_type_ids=batch["token_type_ids"], return_dict=True)
+    watch = {"ans0w": "answer_head.logit_fc.0.weight", "ans0b": "answer_head.logit_fc.0.bias",
+             "ans2w": "answer_head.logit_fc.2.weight", "ans2b": "answer_head.logit_fc.2.bias",
+             "ans3w": "answer_head.logit_fc.3.weight", "ans3b": "answer_head.logit_fc.3.bias",
+             "poolw": "bert.pooler.dense.weight", "featw": "obj_predict_head.linear_feat.weight",
+             "featb": "obj_predict_head.linear_feat.bias", "objtw": "obj_predict_head.transform.dense.weight",
+             "clsb": "obj_predict_head.out_cluster.bias", "visnw": "bert.encoder.visn_fc.visn_fc.weight",
+             "maskf": "mask_feat", "l0q": "bert.encoder.layer.0.attention.self.query.weight"}
+    params = dict(model.named_parameters())
+    for task, ids in (("vis_mask", batch["input_ids"]), ("word_mask", batch["masked_input_ids"]),
+                      ("matched", batch["input_ids"])):
+        qa = qa_labels.clone()
+        if task == "matched":
+            qa.masked_fill_(batch["matched_labels"] == 0, -100)        # lxmert_pretrain.py:186-188
+        elif task == "word_mask":
+            qa[0] = -100                                                 # an ignored row outside the matched rule
+        labels = dict(word_labels=batch["word_labels"], obj_labels=batch["obj_labels"],
+                      matched_labels=batch["matched_labels"], feat_labels=feat_labels, qa_labels=qa)
+        model.zero_grad()
+        out = model(input_ids=ids, label_dict=labels, task=task, **common)
+        out["total_loss"].backward()
+        for k, v in out.items():
+            rec[f"{k}_{task}"] = v.detach()
+        rec[f"qa_labels_{task}"] = qa
+        for short, pname in watch.items():
+            gr = params[pname].grad
+            rec[f"gnorm_{short}_{task}"] = torch.tensor(float("nan") if gr is None else gr.norm().item())
+            if gr is not None:
+                rec[f"ghead_{short}_{task}"] = gr.flatten()[:16].clone()
+    with torch.no_grad():
+        feats = synth.visual_feats_from(table, batch["cluster_ids"])
+        o = model.bert(input_ids=batch["input_ids"], visual_feats=feats, visual_pos=batch["visual_pos"],
+                       attention_mask=batch["attention_mask"], return_dict=True)
+        rec["qa_score"] = model.answer_head(o[2])
+        rec["pooled"] = o[2]
+    save(name, rec)
+
+
 def golden_sampler(name, d, B, wseed, bseed, n_steps=4):
     """Reference NAR sampling loop (imggen_model.py:199-243) at the BASELINE batch size of config 5 (B = 32), run with
     the reference's ``XLxmertForPretraining`` sub-modules exactly as ``ImggenModel`` chains them; every step's mask,
@@ -349,7 +428,10 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     d = DEFAULT_DIMS
-    which = sys.argv[1:] or ["model", "ragged", "pretrain", "generator", "sampler", "generator_b16", "generator_noise"]
+    which = sys.argv[1:] or ["model", "ragged", "pretrain", "generator", "sampler", "generator_b16", "generator_noise",
+                             "feat_qa"]
+    if "feat_qa" in which:
+        golden_pretrain_feat_qa("pretrain_feat_qa_b3", d, B=3, wseed=0, bseed=2)
     if "model" in which:
         golden_model("model_b2_l20_v64", d, B=2, L=20, V=64, wseed=0, bseed=0)
     if "ragged" in which:

@@ -55,8 +55,10 @@ def import_lxrt_modeling():
     return modeling
 
 
-def build_pretraining_model(num_clusters: int = 10000, **config_kw):
-    """Reference ``XLxmertForPretraining`` with S3/S4 applied (obj loss only, ``--visualLosses obj``)."""
+def build_pretraining_model(num_clusters: int = 10000, keep_feat_loss: bool = False, **config_kw):
+    """Reference ``XLxmertForPretraining`` with S3/S4 applied (obj loss only, ``--visualLosses obj``).
+    ``keep_feat_loss``: leave the model as published — ``visual_losses`` = obj + feat (the default
+    ``--visualLosses obj,feat`` of ``param.py:123``), so the vis_mask forward needs ``label_dict['feat_labels']``."""
     from transformers import LxmertConfig
 
     modeling = import_lxrt_modeling()
@@ -64,8 +66,9 @@ def build_pretraining_model(num_clusters: int = 10000, **config_kw):
     cfg.num_clusters = num_clusters
     model = modeling.XLxmertForPretraining(cfg, num_clusters=num_clusters)
     model.config.n_centroids = num_clusters                      # S3 (D4)
-    model.visual_losses = {"obj": model.visual_losses["obj"]}    # S4 (D5)
-    model.obj_predict_head.visual_losses = {"obj": model.obj_predict_head.visual_losses["obj"]}
+    if not keep_feat_loss:
+        model.visual_losses = {"obj": model.visual_losses["obj"]}    # S4 (D5)
+        model.obj_predict_head.visual_losses = {"obj": model.obj_predict_head.visual_losses["obj"]}
     return model
 
 

@@ -156,3 +156,56 @@ def test_generator_matches_reference_golden():
         assert rel_err(h[:, :, ::s, ::s], g[f"h{i}_sub"]) < 1e-4, i
     assert rel_err(aux["pre_tanh"][:, :, ::4, ::4], g["pre_tanh_sub"]) < 1e-4
     assert rel_err(img[:, :, ::4, ::4], g["img_sub"]) < 1e-4
+
+
+def _feat_qa_case():
+    g = load_golden("pretrain_feat_qa_b3")
+    B, L, V, wseed, bseed, n_answers = (int(x) for x in g["meta"])
+    sd_bert = P.init_state_dict(P.model_param_specs(D), seed=wseed, randomize_ln_bias=True)
+    sd_head = P.init_state_dict(P.objhead_param_specs(D), seed=wseed + 1, randomize_ln_bias=True)
+    sd_ans = P.init_state_dict(P.answerhead_param_specs(D, n_answers), seed=wseed + 4, randomize_ln_bias=True)
+    table = synth.centroid_table(D)
+    sd_head["out_cluster.weight"] = table
+    mask_feat = 0.05 * torch.randn(D.feat_dim, generator=torch.Generator().manual_seed(wseed + 3))
+    batch = synth.make_batch(D, B, L, V, seed=bseed)
+    feat_labels, qa_labels = synth.feat_qa_targets(D, B, bseed, n_answers)
+    chk = feat_labels.double().abs().sum().item() + qa_labels.sum().item()
+    assert abs(chk - float(g["inputs_checksum"])) < 1e-6 * chk
+    return g, sd_bert, sd_head, sd_ans, table, mask_feat, batch, feat_labels
+
+
+def test_feat_regression_and_qa_losses_match_reference_golden():
+    """modeling.py:270-299 as published (obj + feat visual losses, --taskQA), vis_mask task."""
+    g, sd_bert, sd_head, sd_ans, table, mask_feat, batch, feat_labels = _feat_qa_case()
+    for t in sd_ans.values():
+        t.requires_grad_(True)
+    sd_head["linear_feat.weight"].requires_grad_(True)
+    mask_feat = mask_feat.clone().requires_grad_(True)
+    feats = O.mask_visual_feats(table[batch["cluster_ids"]], batch["vis_mask"], mask_feat)
+    lang, vis, pooled, _, _ = O.lxmert_model(sd_bert, batch["input_ids"], feats, batch["visual_pos"],
+                                             batch["attention_mask"])
+    feat, logits = O.obj_head(sd_head, vis)
+    obj = O.cross_entropy_mean(logits.reshape(-1, logits.shape[-1]), batch["obj_labels"].reshape(-1))
+    fl = O.feat_loss(feat, feat_labels, batch["vis_mask"])
+    qa, pred = O.qa_loss(sd_ans, pooled, torch.as_tensor(g["qa_labels_vis_mask"]))
+    total = obj + fl + qa
+    total.backward()
+    for mine, key in ((obj, "obj_loss"), (fl, "feat_loss"), (qa, "qa_loss"), (obj + fl, "vis_loss"), (total, "total_loss")):
+        ref = float(g[f"{key}_vis_mask"])
+        assert abs(float(mine.detach()) - ref) < 1e-5 * abs(ref), key
+    assert torch.equal(pred, torch.as_tensor(g["qa_pred_vis_mask"]))
+    for short, t in (("ans0w", sd_ans["logit_fc.0.weight"]), ("ans2b", sd_ans["logit_fc.2.bias"]),
+                     ("ans3w", sd_ans["logit_fc.3.weight"]), ("ans3b", sd_ans["logit_fc.3.bias"]),
+                     ("featw", sd_head["linear_feat.weight"]), ("maskf", mask_feat)):
+        ref_n = float(g[f"gnorm_{short}_vis_mask"])
+        assert abs(float(t.grad.norm()) - ref_n) < 1e-3 * ref_n, short
+        assert rel_err(t.grad.flatten()[:16], g[f"ghead_{short}_vis_mask"]) < 1e-3, short
+    with torch.no_grad():
+        feats0 = table[batch["cluster_ids"]]
+        _, _, pooled0, _, _ = O.lxmert_model(sd_bert, batch["input_ids"], feats0, batch["visual_pos"],
+                                             batch["attention_mask"])
+        assert rel_err(pooled0, g["pooled"]) < TOL
+        assert rel_err(O.answer_head(sd_ans, pooled0), g["qa_score"]) < TOL
+        # matched task: the labels of flipped pairs are ignored (lxmert_pretrain.py:186-188)
+        qa_m, _ = O.qa_loss(sd_ans, pooled0, torch.as_tensor(g["qa_labels_matched"]))
+        assert abs(float(qa_m) - float(g["qa_loss_matched"])) < 1e-5 * float(g["qa_loss_matched"])

@@ -82,7 +82,7 @@ def _sig(lib):
     lib.xlx_dropout_site.restype = I32
     lib.xlx_dropout_site.argtypes = [D, I32, I32, I32]
     lib.xlx_encoder_bwd.restype = I32
-    lib.xlx_encoder_bwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, SZ, I32, I32, DR, P]
+    lib.xlx_encoder_bwd.argtypes = [D, P, P, I32, I32, I32, P, P, P, P, P, P, P, SZ, I32, I32, DR, P, P]
     lib.xlx_encoder_probs_offset.restype = I64
     lib.xlx_encoder_probs_offset.argtypes = [D, I32, I32, I32, I32, I32]
     lib.xlx_encoder_grad_stage_range.restype = I32

@@ -411,7 +411,7 @@ int ffn_fwd(const Run& r, int blk, float* out_f32) {
 struct Deferred {
   float* arena = nullptr;
   size_t cap = 0, used = 0;
-  std::vector<FinishJob> jobs;
+  std::vector<FinishJob> jobs[2];      // [0] registered by blocks on the caller's stream, [1] by language-side blocks
   float* take(size_t n) {                      // nullptr when the arena is exhausted (callers then finish right away)
     n = (n + 63) & ~static_cast<size_t>(63);
     if (used + n > cap) return nullptr;
@@ -426,6 +426,7 @@ struct Bwd {
   float* grads;
   SlotTable slots;
   Deferred* def = nullptr; // shared by the two streams' views (host-side bookkeeping only)
+  int lane = 0;            // which of the Deferred job lists this view feeds
   float* G(int slot) const { return grads + slots.offset[slot]; }
 };
 // Finish `part` [nvec, nblk, H] into outs now, or later with the batch when the partials live in the deferred arena.
@@ -434,7 +435,7 @@ int finish_or_defer(const Bwd& bw, const float* part, bool in_arena, int nvec, i
     FinishJob j{};
     j.part = part; j.nvec = nvec; j.nblk = nblk; j.H = H;
     for (int v = 0; v < nvec; ++v) j.out[v] = outs[v];
-    bw.def->jobs.push_back(j);
+    bw.def->jobs[bw.lane].push_back(j);
     return 0;
   }
   return colsum_finish(part, nvec, nblk, H, outs, 0, bw.r->st);
@@ -820,7 +821,8 @@ int32_t xlx_encoder_fwd(const xlx_dims* d, const float* const* params, const voi
 int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const void* prep, int32_t B, int32_t L,
                         int32_t V, const float* visual_pos, const float* d_lang_out, const float* d_vis_out,
                         float* d_lang_in, float* d_visual_feats, float* grads, void* workspace,
-                        size_t workspace_bytes, int32_t passes, int32_t stages, const xlx_dropout* dropout, void* stream) {
+                        size_t workspace_bytes, int32_t passes, int32_t stages, const xlx_dropout* dropout,
+                        void* language_done_event, void* stream) {
   XLX_TRY(check_common(d, B, L, V));
   if (!params || !prep || !visual_pos || !d_lang_in || !grads || !workspace) return -24;
   if (passes != 1 && passes != 3) return -1;
@@ -849,7 +851,7 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
   SideStream* side = side_stream();
   Run rl = r;
   Bwd bwl = bw;
-  if (side) { rl.st = side->st; bwl.r = &rl; bwl.sc = &p.sc[1]; }
+  if (side) { rl.st = side->st; bwl.r = &rl; bwl.sc = &p.sc[1]; bwl.lane = 1; }
   const int H = p.H, F = p.F, Ml = p.Ml, Mv = p.Mv;
   const int nl = d->l_layers, nr = d->r_layers, nx = d->x_layers;
   const size_t lh = static_cast<size_t>(Ml) * H, vh = static_cast<size_t>(Mv) * H;
@@ -902,6 +904,16 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
     }
     // language embedding gradient
     XLX_CUDA(cudaMemcpyAsync(d_lang_in, cur, lh * 4, cudaMemcpyDeviceToDevice, b.r->st));
+    if (language_done_event) {
+      // the language range of the arena is complete once this stream's deferred column sums are finished: do that
+      // now, on this stream, and tell the caller — it may start reducing the range while the vision stack computes
+      std::vector<FinishJob>& lj = def.jobs[b.lane];
+      if (!lj.empty()) {
+        XLX_TRY(colsum_finish_batched(lj.data(), static_cast<int>(lj.size()), b.r->st));
+        lj.clear();
+      }
+      XLX_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(language_done_event), b.r->st));
+    }
   }
   if (stages & XLX_BWD_VISION) {
     for (int i = nr - 1; i >= 0; --i) {
@@ -935,7 +947,9 @@ int32_t xlx_encoder_bwd(const xlx_dims* d, const float* const* params, const voi
   }
   if (lang_beside) XLX_TRY(join_from(side, r.st));
   // every stream of this call has been joined: finish all deferred column sums in one (or two) launches
-  if (!def.jobs.empty()) XLX_TRY(colsum_finish_batched(def.jobs.data(), static_cast<int>(def.jobs.size()), r.st));
+  for (int lane = 0; lane < 2; ++lane)
+    if (!def.jobs[lane].empty())
+      XLX_TRY(colsum_finish_batched(def.jobs[lane].data(), static_cast<int>(def.jobs[lane].size()), r.st));
   return 0;
 }
 

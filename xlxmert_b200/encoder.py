@@ -107,6 +107,8 @@ class _EncoderSkeleton(nn.Module):
 # language stack runs beside the vision stack on the library's second stream.
 _BWD_STAGES = (1, 2 | 4 | 8)
 _BWD_ALL = 15
+#: set to True to queue the language range's all-reduce behind the whole second backward call (A/B switch)
+_NO_EARLY_LANGUAGE_REDUCE = bool(int(__import__("os").environ.get("XLX_NO_EARLY_LANGUAGE_REDUCE", "0")))
 
 
 def _dist_active(group) -> bool:
@@ -208,12 +210,13 @@ class _EncoderFn(torch.autograd.Function):
         enc.last_grad_arena = grads
         enc.arena_reduced = False
 
-        def run(stages):
+        def run(stages, lang_done=None):
             rc = lib.xlx_encoder_bwd(C.byref(enc._cdims), ctx.parr, ctx.prep.data_ptr(), B, L, V,
                                      ctx.visual_pos.data_ptr(), _ptr(d_lang_out), _ptr(d_vis_out),
                                      d_lang_in.data_ptr(), _ptr(d_feats), grads.data_ptr(), ctx.ws.data_ptr(),
                                      ctx.ws_bytes, enc.passes, stages,
-                                     None if ctx.drop is None else C.byref(ctx.drop), _stream_ptr())
+                                     None if ctx.drop is None else C.byref(ctx.drop),
+                                     None if lang_done is None else lang_done.cuda_event, _stream_ptr())
             _lib.check("xlx_encoder_bwd", rc)
 
         group = enc.grad_sync_group
@@ -226,12 +229,33 @@ class _EncoderFn(torch.autograd.Function):
             pg = None if group is True else group
             avg = dist.get_backend(pg) == "nccl"
             works = []
-            for stage in _BWD_STAGES:
-                run(stage)
-                off, n = enc._stage_range(stage)
+            op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
+
+            def reduce_range(off, n):
                 if n:
-                    works.append(dist.all_reduce(grads[off:off + n], op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM,
-                                                 group=pg, async_op=True))
+                    works.append(dist.all_reduce(grads[off:off + n], op=op, group=pg, async_op=True))
+            early = grads.is_cuda and _BWD_STAGES == (1, 14) and not _NO_EARLY_LANGUAGE_REDUCE
+            for stage in _BWD_STAGES:
+                if early and (stage & 4) and (stage & ~4):
+                    # The call runs the language stack beside the vision stack and finishes it first.  The library
+                    # records `lang_done` the moment the language range of the arena is complete; an auxiliary stream
+                    # that waits on nothing else issues that range's all-reduce, so it overlaps the rest of the call
+                    # instead of queueing behind it.
+                    lang_done = enc.__dict__.setdefault("_lang_done_event", torch.cuda.Event())
+                    aux = enc.__dict__.setdefault("_aux_stream", torch.cuda.Stream(dev))
+                    cur = torch.cuda.current_stream(dev)
+                    lang_done.record(cur)            # creates the CUDA event; the library re-records it
+                    run(stage, lang_done)
+                    l_off, l_n = enc._stage_range(4)
+                    aux.wait_event(lang_done)
+                    with torch.cuda.stream(aux):
+                        reduce_range(l_off, l_n)
+                    grads.record_stream(aux)
+                    for bit in (2, 8):               # vision stack, visual feature encoder: after the call, as before
+                        reduce_range(*enc._stage_range(stage & bit)) if stage & bit else None
+                else:
+                    run(stage)
+                    reduce_range(*enc._stage_range(stage))
             for w in works:
                 w.wait()
             if not avg:

@@ -121,6 +121,15 @@ def objhead_param_specs(d: LxmertDims) -> List[Tuple[str, Tuple[int, ...]]]:
     ]
 
 
+def answerhead_param_specs(d: LxmertDims, num_answers: int) -> List[Tuple[str, Tuple[int, ...]]]:
+    """HF ``LxmertVisualAnswerHead`` (HF modeling_lxmert.py:610-623) — the reference's ``answer_head``
+    (x-lxmert/src/lxrt/modeling.py:89-90)."""
+    H = d.hidden
+    return [("logit_fc.0.weight", (2 * H, H)), ("logit_fc.0.bias", (2 * H,)),
+            ("logit_fc.2.weight", (2 * H,)), ("logit_fc.2.bias", (2 * H,)),
+            ("logit_fc.3.weight", (num_answers, 2 * H)), ("logit_fc.3.bias", (num_answers,))]
+
+
 def init_state_dict(specs, seed: int = 0, std: float = 0.02, dtype=torch.float32,
                     randomize_ln_bias: bool = False) -> Dict[str, torch.Tensor]:
     """Random initialisation in the spirit of HF ``_init_weights`` (``modeling_lxmert.py:668-680``):

@@ -84,3 +84,13 @@ def make_batch(d: LxmertDims, B: int, L: int = 20, V: int = 64, seed: int = 0,
 def visual_feats_from(table: torch.Tensor, cluster_ids: torch.Tensor) -> torch.Tensor:
     """``vis_emb(cluster_ids)`` (x-lxmert/src/lxrt/modeling.py:185-186)."""
     return table[cluster_ids]
+
+
+def feat_qa_targets(d: LxmertDims, B: int, seed: int, num_answers: int, V: int = 64):
+    """Synthetic ``feat_labels`` [B, V, feat_dim] (the grid features the ``feat`` loss regresses to,
+    lxmert_pretrain.py:177-179) and ``qa_labels`` [B] (lxmert_pretrain.py:184-189); unit-variance targets put the
+    SmoothL1 residuals on both sides of its |x| = 1 knee."""
+    g = torch.Generator().manual_seed(seed + 77)
+    feat_labels = torch.randn(B, V, d.feat_dim, generator=g)
+    qa_labels = torch.randint(0, num_answers, (B,), generator=g)
+    return feat_labels, qa_labels
