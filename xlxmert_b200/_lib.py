@@ -102,16 +102,23 @@ def _sig(lib):
     lib.xlx_pooler_fwd.argtypes = [D, I32, I32, P, P, P, P, P, SZ, I32, P]
     lib.xlx_pooler_bwd.restype = I32
     lib.xlx_pooler_bwd.argtypes = [D, I32, I32, P, P, P, P, P, P, SZ, I32, P]
-    for kind in ("objhead", "lmhead"):
+    for kind in ("objhead", "lmhead", "qahead"):
         f = getattr(lib, f"xlx_{kind}_prep_bytes"); f.restype = SZ; f.argtypes = [D, I32]
         f = getattr(lib, f"xlx_{kind}_prepare"); f.restype = I32; f.argtypes = [D, I32, P, P, P]
         f = getattr(lib, f"xlx_{kind}_workspace_bytes"); f.restype = SZ; f.argtypes = [D, I32, I32]
-        f = getattr(lib, f"xlx_{kind}_bwd"); f.restype = I32
-        f.argtypes = [D, I32, P, P, I32, P, P, P, P, P, SZ, I32, P]
     lib.xlx_objhead_fwd.restype = I32
-    lib.xlx_objhead_fwd.argtypes = [D, I32, P, P, I32, P, P, P, P, P, P, P, P, SZ, I32, P]
-    lib.xlx_lmhead_fwd.restype = I32
-    lib.xlx_lmhead_fwd.argtypes = [D, I32, P, P, I32, P, P, P, P, P, SZ, I32, P]
+    lib.xlx_objhead_fwd.argtypes = [D, I32, P, P, I32, P, P, P, P, P, P, P, P, P, P, P, SZ, I32, P]
+    lib.xlx_objhead_bwd.restype = I32
+    lib.xlx_objhead_bwd.argtypes = [D, I32, P, P, I32, P, P, P, P, P, P, P, P, P, P, SZ, I32, P]
+    lib.xlx_feat_row_weight.restype = I32
+    lib.xlx_feat_row_weight.argtypes = [P, I32, I32, I32, P, I32, P, P]
+    for kind in ("lmhead", "qahead"):
+        f = getattr(lib, f"xlx_{kind}_fwd"); f.restype = I32
+        f.argtypes = [D, I32, P, P, I32, P, P, P, P, P, P, P, SZ, I32, P]
+        f = getattr(lib, f"xlx_{kind}_bwd"); f.restype = I32
+        f.argtypes = [D, I32, P, P, I32, P, P, P, P, P, P, SZ, I32, P]
+    lib.xlx_matchhead_bwd_scores.restype = I32
+    lib.xlx_matchhead_bwd_scores.argtypes = [D, I32, P, P, P, P, P, P, P]
     lib.xlx_visual_input_fwd.restype = I32
     lib.xlx_visual_input_fwd.argtypes = [P, P, P, P, I32, I32, P, P]
     lib.xlx_visual_input_bwd.restype = I32

@@ -35,20 +35,24 @@ PoolWs pool_layout(const xlx_dims* d, int B, void* base) {
 
 
 // ---- prediction heads ---------------------------------------------------------------------------------
-// Both heads are  t = LN(gelu(W1·h + b1))  [LxmertPredictionHeadTransform, HF:583-594]  followed by
-//   cluster head:  feat = Wf·t + bf  (H → F);  logits = feat·Centroidsᵀ + bc  (F → C)    lxrt/modeling.py:38-53
-//   LM head:       logits = t·Eᵀ + bias  (H → vocab, E tied to the word embeddings)       HF:597-607
-// `F == 0` selects the LM form.  Cp = C rounded up to a multiple of 8 (GEMM epilogue vector width).
-struct HeadDims { int H, F, C, Cp; float eps; };
+// All three heads are  t = LN(gelu(W1·h + b1))  followed by a classifier:
+//   cluster head:  W1: H→H [LxmertPredictionHeadTransform, HF:583-594]; feat = Wf·t + bf (H → F);
+//                  logits = feat·Centroidsᵀ + bc (F → C)                                     lxrt/modeling.py:38-53
+//   LM head:       W1: H→H; logits = t·Eᵀ + bias (H → vocab, E tied to the word embeddings)   HF:597-607
+//   answer head:   W1: H→2H, LN over 2H; logits = W2·t + b2 (2H → answers)                    HF:610-623
+// T = width of the transform (H or 2H); `F == 0` selects the forms without the feature layer.  Cp = C rounded up to a
+// multiple of 8 (GEMM epilogue vector width).
+struct HeadDims { int H, T, F, C, Cp; float eps; };
+enum HeadKind { HEAD_LM = 0, HEAD_CLUSTER = 1, HEAD_ANSWER = 2 };
 inline int pad8(int c) { return (c + 7) & ~7; }
 
 struct HeadPrep { Split w1, wf, wc; float* bc; size_t bytes; };
 HeadPrep head_prep_layout(const HeadDims& h, void* base) {
   Bump b; b.base = static_cast<char*>(base);
   HeadPrep p;
-  p.w1 = b.split(static_cast<size_t>(h.H) * h.H);
-  if (h.F) p.wf = b.split(static_cast<size_t>(h.F) * h.H);
-  p.wc = b.split(static_cast<size_t>(h.C) * (h.F ? h.F : h.H));
+  p.w1 = b.split(static_cast<size_t>(h.T) * h.H);
+  if (h.F) p.wf = b.split(static_cast<size_t>(h.F) * h.T);
+  p.wc = b.split(static_cast<size_t>(h.C) * (h.F ? h.F : h.T));
   p.bc = b.f32(h.Cp);                                   // class bias, zero padded to Cp
   p.bytes = b.total();
   return p;
@@ -56,31 +60,36 @@ HeadPrep head_prep_layout(const HeadDims& h, void* base) {
 
 struct HeadWs {
   Split x, t, feat, dlogits, dfeat, du;
-  float *u, *g, *mean, *rstd, *logits, *lse, *rowloss, *stats, *dt, *dg, *part, *dbc, *splitk, *rowstat;
+  float *u, *g, *mean, *rstd, *feat32, *featrow, *logits, *lse, *rowloss, *stats, *dt, *dg, *part, *dbc, *splitk, *rowstat;
   size_t bytes;
 };
 HeadWs head_ws_layout(const HeadDims& h, int M, void* base) {
   Bump b; b.base = static_cast<char*>(base);
   HeadWs w;
-  const size_t m = M, H = h.H, F = h.F, Cp = h.Cp;
+  const size_t m = M, H = h.H, T = h.T, F = h.F, Cp = h.Cp;
   w.x = b.split(m * H);
-  w.u = b.f32(m * H);
-  w.g = b.f32(m * H);
-  w.t = b.split(m * H);
+  w.u = b.f32(m * T);
+  w.g = b.f32(m * T);
+  w.t = b.split(m * T);
   w.mean = b.f32(m);
   w.rstd = b.f32(m);
-  if (F) w.feat = b.split(m * F);
+  w.feat32 = w.featrow = nullptr;
+  if (F) {
+    w.feat = b.split(m * F);
+    w.feat32 = b.f32(m * F);      // fp32 features for the regression loss; its gradient overwrites them in the backward
+    w.featrow = b.f32(m);
+  }
   w.logits = b.f32(m * Cp);
   w.lse = b.f32(m);
   w.rowloss = b.f32(m);
-  w.stats = b.f32(4);
+  w.stats = b.f32(8);             // [0] CE loss [1] valid rows [4] feature-regression loss
   // backward scratch
   w.dlogits = b.split(m * Cp);
   if (F) w.dfeat = b.split(m * F);
-  w.dt = b.f32(m * H);
-  w.dg = b.f32(m * H);
-  w.du = b.split(m * H);
-  size_t pe = 3 * static_cast<size_t>(reduce_max_blocks()) * H;
+  w.dt = b.f32(m * T);
+  w.dg = b.f32(m * T);
+  w.du = b.split(m * T);
+  size_t pe = 3 * static_cast<size_t>(reduce_max_blocks()) * T;
   const size_t widest = Cp > F ? Cp : F;
   if (128 * widest > pe) pe = 128 * widest;
   w.part = b.f32(pe);
@@ -91,44 +100,62 @@ HeadWs head_ws_layout(const HeadDims& h, int M, void* base) {
   return w;
 }
 
-// params: [0] transform.dense.weight [1] .bias [2] transform.LayerNorm.weight [3] .bias, then
+// params: [0] first Linear weight [T,H] [1] its bias [2] LayerNorm.weight [T] [3] LayerNorm.bias, then
 //   cluster head: [4] linear_feat.weight [5] .bias [6] out_cluster.weight [7] out_cluster.bias
 //   LM head:      [4] decoder.weight [5] predictions.bias
+//   answer head:  [4] logit_fc.3.weight [5] logit_fc.3.bias
 int head_prepare(const HeadDims& h, const float* const* params, void* prep, cudaStream_t st) {
   HeadPrep p = head_prep_layout(h, prep);
-  const size_t H = h.H;
-  XLX_TRY(split_f32(params[0], p.w1, H * H, st));
+  const size_t H = h.H, T = h.T;
+  XLX_TRY(split_f32(params[0], p.w1, T * H, st));
   const float* wc = params[h.F ? 6 : 4];
   const float* bc = params[h.F ? 7 : 5];
-  if (h.F) XLX_TRY(split_f32(params[4], p.wf, static_cast<size_t>(h.F) * H, st));
-  XLX_TRY(split_f32(wc, p.wc, static_cast<size_t>(h.C) * (h.F ? h.F : H), st));
+  if (h.F) XLX_TRY(split_f32(params[4], p.wf, static_cast<size_t>(h.F) * T, st));
+  XLX_TRY(split_f32(wc, p.wc, static_cast<size_t>(h.C) * (h.F ? h.F : T), st));
   XLX_CUDA(cudaMemsetAsync(p.bc, 0, static_cast<size_t>(h.Cp) * 4, st));
   XLX_CUDA(cudaMemcpyAsync(p.bc, bc, static_cast<size_t>(h.C) * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
+// Feature-regression loss inputs of the cluster head (lxrt/modeling.py:270-284); all null = loss off
+struct FeatLoss {
+  const float* target = nullptr;   // [M, F] feat_labels rows
+  const float* weight = nullptr;   // [M] from xlx_feat_row_weight
+  float* loss = nullptr;           // forward: device scalar out
+  const float* d_loss = nullptr;   // backward: device scalar in
+};
+
 int head_fwd(const HeadDims& h, const float* const* params, const void* prep_base, int M, const float* hidden,
-             const int64_t* labels, float* feat_out, float* logits_out, float* loss, float* pred_prob,
+             const int64_t* labels, FeatLoss fl, float* feat_out, float* logits_out, float* loss, float* pred_prob,
              int64_t* pred_id, void* ws_base, size_t ws_bytes, int passes, cudaStream_t st) {
   HeadPrep p = head_prep_layout(h, const_cast<void*>(prep_base));
   HeadWs w = head_ws_layout(h, M, ws_base);
   if (w.bytes > ws_bytes) return -23;
-  const int H = h.H, F = h.F, C = h.C, Cp = h.Cp;
+  const int H = h.H, T = h.T, F = h.F, C = h.C, Cp = h.Cp;
+  if (fl.target && (!F || !fl.weight)) return -24;
   XLX_TRY(split_f32(hidden, w.x, static_cast<size_t>(M) * H, st));
   {
     GemmEpilogue e;   // u = W1·h + b1 (saved), g = gelu(u)
-    e.bias = params[1]; e.flags = EPI_GELU; e.out_u = w.u; e.ld_u = H; e.out_f32 = w.g; e.ld_out = H;
-    XLX_TRY(gemm_linear(passes, st, w.x, M, H, p.w1, H, e));
+    e.bias = params[1]; e.flags = EPI_GELU; e.out_u = w.u; e.ld_u = T; e.out_f32 = w.g; e.ld_out = T;
+    XLX_TRY(gemm_linear(passes, st, w.x, M, H, p.w1, T, e));
   }
-  XLX_TRY(layernorm_fwd(w.g, params[2], params[3], h.eps, M, H, 1.0f, nullptr, w.t, nullptr, w.mean, w.rstd, st));
+  XLX_TRY(layernorm_fwd(w.g, params[2], params[3], h.eps, M, T, 1.0f, nullptr, w.t, nullptr, w.mean, w.rstd, st));
   Split dec_in = w.t;
-  int Kc = H;
+  int Kc = T;
   if (F) {
     GemmEpilogue e;
-    e.bias = params[5]; e.out_f32 = feat_out; e.ld_out = F; e.out_hi = w.feat.hi; e.out_lo = w.feat.lo; e.ld_split = F;
-    XLX_TRY(gemm_linear(passes, st, w.t, M, H, p.wf, F, e));
+    e.bias = params[5]; e.out_f32 = fl.target ? w.feat32 : feat_out; e.ld_out = F;
+    e.out_hi = w.feat.hi; e.out_lo = w.feat.lo; e.ld_split = F;
+    XLX_TRY(gemm_linear(passes, st, w.t, M, T, p.wf, F, e));
+    if (fl.target) {
+      const size_t bytes = static_cast<size_t>(M) * F * 4;
+      if (feat_out) XLX_CUDA(cudaMemcpyAsync(feat_out, w.feat32, bytes, cudaMemcpyDeviceToDevice, st));
+      XLX_TRY(smooth_l1_fwd(w.feat32, fl.target, fl.weight, M, F, w.featrow, w.stats + 4, st));
+      if (fl.loss) XLX_CUDA(cudaMemcpyAsync(fl.loss, w.stats + 4, 4, cudaMemcpyDeviceToDevice, st));
+    }
     dec_in = w.feat; Kc = F;
   }
+  if (!labels && !logits_out && !pred_prob) return 0;     // features only (--visualLosses feat)
   if (pred_prob && pred_id && !logits_out && !labels) {
     // sampler step (tasks/imggen_model.py:228-235): softmax(logits).max(-1) straight from the accumulators — the
     // [M, classes] logits are never written; per-tile partial statistics (12 B per row and quarter tile) are merged
@@ -156,51 +183,73 @@ int head_fwd(const HeadDims& h, const float* const* params, const void* prep_bas
   return 0;
 }
 
-// grads: device pointers shaped like params (overwritten).  The cluster head's out_cluster.weight ([6]) is the
-// frozen centroid table (lxrt/modeling.py:146-151) and gets no gradient; the LM head's decoder.weight ([4]) does.
+// grads: device pointers shaped like params (overwritten; a null entry is skipped).  The cluster head's
+// out_cluster.weight ([6]) is the frozen centroid table (lxrt/modeling.py:146-151) and gets no gradient; the LM head's
+// decoder.weight ([4]) does.  The logits gradient comes from the fused cross-entropy (labels + d_loss) or from the caller
+// (d_logits [M, C], a differentiable `forward`); the cluster head may instead / also receive a feature gradient: the
+// regression loss (fl) or an upstream d_feat [M, F] — not both.
 int head_bwd(const HeadDims& h, const float* const* params, const void* prep_base, int M, const int64_t* labels,
-             const float* d_loss, float* d_hidden, float* const* grads, void* ws_base, size_t ws_bytes, int passes,
-             cudaStream_t st) {
+             const float* d_loss, const float* d_logits, FeatLoss fl, const float* d_feat, float* d_hidden,
+             float* const* grads, void* ws_base, size_t ws_bytes, int passes, cudaStream_t st) {
   HeadPrep p = head_prep_layout(h, const_cast<void*>(prep_base));
   HeadWs w = head_ws_layout(h, M, ws_base);
   if (w.bytes > ws_bytes) return -23;
-  const int H = h.H, F = h.F, C = h.C, Cp = h.Cp;
+  const int H = h.H, T = h.T, F = h.F, C = h.C, Cp = h.Cp;
+  if (labels && (d_logits || !d_loss)) return -24;
+  if (fl.target && (!F || !fl.weight || !fl.d_loss || d_feat)) return -24;
+  if (d_feat && !F) return -24;
+  const bool have_dlogits = labels || d_logits;
+  if (!have_dlogits && !fl.target && !d_feat) return -24;
   XLX_TRY(gemm_splitk_ws_reset(w.splitk, st));
-  XLX_TRY(ce_bwd(w.logits, Cp, M, C, Cp, labels, -100, w.lse, w.stats, d_loss, w.dlogits, st));
-  // class bias: column sums over the padded width into scratch, first C entries are the gradient
-  XLX_TRY(colsum(nullptr, w.dlogits, M, Cp, Cp, w.part, w.dbc, st));
-  XLX_CUDA(cudaMemcpyAsync(grads[F ? 7 : 5], w.dbc, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToDevice, st));
+  if (labels) XLX_TRY(ce_bwd(w.logits, Cp, M, C, Cp, labels, -100, w.lse, w.stats, d_loss, w.dlogits, st));
+  else if (d_logits) XLX_TRY(split_pad_f32(d_logits, M, C, Cp, w.dlogits, st));
+  float* g_cbias = grads[F ? 7 : 5];
+  if (have_dlogits && g_cbias) {
+    // class bias: column sums over the padded width into scratch, first C entries are the gradient
+    XLX_TRY(colsum(nullptr, w.dlogits, M, Cp, Cp, w.part, w.dbc, st));
+    XLX_CUDA(cudaMemcpyAsync(g_cbias, w.dbc, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToDevice, st));
+  }
   if (F) {
-    GemmEpilogue e;   // dfeat = dlogits · Centroids
-    e.out_hi = w.dfeat.hi; e.out_lo = w.dfeat.lo; e.ld_split = F;
-    XLX_TRY(gemm_dgrad(passes, st, w.dlogits, M, Cp, p.wc, F, e, C));
+    const float* addend = d_feat;
+    if (fl.target) {
+      XLX_TRY(smooth_l1_bwd(w.feat32, fl.target, fl.weight, fl.d_loss, M, F, w.feat32, st));
+      addend = w.feat32;
+    }
+    if (have_dlogits) {
+      GemmEpilogue e;   // dfeat = dlogits · Centroids (+ the feature gradient)
+      e.out_hi = w.dfeat.hi; e.out_lo = w.dfeat.lo; e.ld_split = F; e.addend = addend; e.ld_addend = F;
+      XLX_TRY(gemm_dgrad(passes, st, w.dlogits, M, Cp, p.wc, F, e, C));
+    } else {
+      XLX_TRY(split_f32(addend, w.dfeat, static_cast<size_t>(M) * F, st));
+    }
     XLX_TRY(colsum(nullptr, w.dfeat, M, F, F, w.part, grads[5], st));
-    XLX_TRY(gemm_wgrad(passes, st, w.dfeat, M, F, w.t, H, grads[4], false, 0, w.splitk));
+    XLX_TRY(gemm_wgrad(passes, st, w.dfeat, M, F, w.t, T, grads[4], false, 0, w.splitk));
     GemmEpilogue o;
-    o.out_f32 = w.dt; o.ld_out = H;
-    XLX_TRY(gemm_dgrad(passes, st, w.dfeat, M, F, p.wf, H, o));
+    o.out_f32 = w.dt; o.ld_out = T;
+    XLX_TRY(gemm_dgrad(passes, st, w.dfeat, M, F, p.wf, T, o));
   } else {
-    XLX_TRY(gemm_wgrad(passes, st, w.dlogits, M, C, w.t, H, grads[4], false, Cp, w.splitk));   // dE [vocab, H]
+    XLX_TRY(gemm_wgrad(passes, st, w.dlogits, M, C, w.t, T, grads[4], false, Cp, w.splitk));   // dW [classes, T]
     GemmEpilogue o;
-    o.out_f32 = w.dt; o.ld_out = H;
-    XLX_TRY(gemm_dgrad(passes, st, w.dlogits, M, Cp, p.wc, H, o, C));
+    o.out_f32 = w.dt; o.ld_out = T;
+    XLX_TRY(gemm_dgrad(passes, st, w.dlogits, M, Cp, p.wc, T, o, C));
   }
   int nblk = 0;
-  XLX_TRY(layernorm_bwd(w.dt, 1.0f, w.g, params[2], w.mean, w.rstd, M, H, w.dg, Split(), w.part, &nblk, st));
+  XLX_TRY(layernorm_bwd(w.dt, 1.0f, w.g, params[2], w.mean, w.rstd, M, T, w.dg, Split(), w.part, &nblk, st));
   float* o2[2] = {grads[2], grads[3]};
-  XLX_TRY(colsum_finish(w.part, 2, nblk, H, o2, 0, st));
-  XLX_TRY(gelu_bwd_split(w.dg, w.u, w.du, static_cast<size_t>(M) * H, st));
-  XLX_TRY(colsum(nullptr, w.du, M, H, H, w.part, grads[1], st));
-  XLX_TRY(gemm_wgrad(passes, st, w.du, M, H, w.x, H, grads[0], false, 0, w.splitk));
+  XLX_TRY(colsum_finish(w.part, 2, nblk, T, o2, 0, st));
+  XLX_TRY(gelu_bwd_split(w.dg, w.u, w.du, static_cast<size_t>(M) * T, st));
+  XLX_TRY(colsum(nullptr, w.du, M, T, T, w.part, grads[1], st));
+  XLX_TRY(gemm_wgrad(passes, st, w.du, M, T, w.x, H, grads[0], false, 0, w.splitk));
   GemmEpilogue o;
   o.out_f32 = d_hidden; o.ld_out = H;
-  return gemm_dgrad(passes, st, w.du, M, H, p.w1, H, o);
+  return gemm_dgrad(passes, st, w.du, M, T, p.w1, H, o);
 }
 
-bool head_dims(const xlx_dims* d, int classes, bool cluster, HeadDims* h) {
+bool head_dims(const xlx_dims* d, int classes, int kind, HeadDims* h) {
   if (!hidden_ok(d) || classes < 1) return false;
-  if (cluster && (d->feat_dim < 8 || d->feat_dim % 8)) return false;
-  h->H = d->hidden; h->F = cluster ? d->feat_dim : 0; h->C = classes; h->Cp = pad8(classes); h->eps = d->ln_eps;
+  if (kind == HEAD_CLUSTER && (d->feat_dim < 8 || d->feat_dim % 8)) return false;
+  h->H = d->hidden; h->T = kind == HEAD_ANSWER ? 2 * d->hidden : d->hidden;
+  h->F = kind == HEAD_CLUSTER ? d->feat_dim : 0; h->C = classes; h->Cp = pad8(classes); h->eps = d->ln_eps;
   return true;
 }
 
@@ -336,77 +385,99 @@ int32_t xlx_pooler_bwd(const xlx_dims* d, int32_t B, int32_t L, const float* poo
 }
 
 
-// ---- cluster head (lxrt/modeling.py:8-53) and LM head (HF:597-607) ------------------------------------------
-#define XLX_HEAD_API(NAME, CLUSTER)                                                                                  \
+// ---- cluster head (lxrt/modeling.py:8-53), LM head (HF:597-607), answer head (HF:610-623) ----------------------
+#define XLX_HEAD_API(NAME, KIND)                                                                                     \
   size_t xlx_##NAME##_prep_bytes(const xlx_dims* d, int32_t classes) {                                              \
     HeadDims h;                                                                                                      \
-    return head_dims(d, classes, CLUSTER, &h) ? head_prep_layout(h, nullptr).bytes : 0;                              \
+    return head_dims(d, classes, KIND, &h) ? head_prep_layout(h, nullptr).bytes : 0;                                 \
   }                                                                                                                  \
   int32_t xlx_##NAME##_prepare(const xlx_dims* d, int32_t classes, const float* const* params, void* prep,           \
                                void* stream) {                                                                       \
     HeadDims h;                                                                                                      \
-    if (!head_dims(d, classes, CLUSTER, &h)) return -20;                                                             \
+    if (!head_dims(d, classes, KIND, &h)) return -20;                                                                \
     if (!params || !prep) return -24;                                                                                \
     XLX_TRY(ensure_device(prep));                                                                                    \
     return head_prepare(h, params, prep, static_cast<cudaStream_t>(stream));                                         \
   }                                                                                                                  \
   size_t xlx_##NAME##_workspace_bytes(const xlx_dims* d, int32_t classes, int32_t M) {                               \
     HeadDims h;                                                                                                      \
-    return (head_dims(d, classes, CLUSTER, &h) && M > 0) ? head_ws_layout(h, M, nullptr).bytes : 0;                  \
+    return (head_dims(d, classes, KIND, &h) && M > 0) ? head_ws_layout(h, M, nullptr).bytes : 0;                     \
   }
 
-XLX_HEAD_API(objhead, true)
-XLX_HEAD_API(lmhead, false)
+XLX_HEAD_API(objhead, HEAD_CLUSTER)
+XLX_HEAD_API(lmhead, HEAD_LM)
+XLX_HEAD_API(qahead, HEAD_ANSWER)
 
 int32_t xlx_objhead_fwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep, int32_t M,
-                        const float* hidden, const int64_t* labels, float* feat, float* logits, float* loss,
+                        const float* hidden, const int64_t* labels, const float* feat_target,
+                        const float* feat_weight, float* feat, float* logits, float* loss, float* feat_loss,
                         float* pred_prob, int64_t* pred_id, void* workspace, size_t workspace_bytes, int32_t passes,
                         void* stream) {
   HeadDims h;
-  if (!head_dims(d, classes, true, &h)) return -20;
+  if (!head_dims(d, classes, HEAD_CLUSTER, &h)) return -20;
   if (M < 1) return -21;
   if (!params || !prep || !hidden || !workspace) return -24;
   if (passes != 1 && passes != 3) return -1;
   XLX_TRY(ensure_device(workspace));
-  return head_fwd(h, params, prep, M, hidden, labels, feat, logits, loss, pred_prob, pred_id, workspace,
+  FeatLoss fl;
+  fl.target = feat_target; fl.weight = feat_weight; fl.loss = feat_loss;
+  return head_fwd(h, params, prep, M, hidden, labels, fl, feat, logits, loss, pred_prob, pred_id, workspace,
                   workspace_bytes, passes, static_cast<cudaStream_t>(stream));
 }
 int32_t xlx_objhead_bwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep, int32_t M,
-                        const int64_t* labels, const float* d_loss, float* d_hidden, float* const* grads,
-                        void* workspace, size_t workspace_bytes, int32_t passes, void* stream) {
+                        const int64_t* labels, const float* d_loss, const float* d_logits, const float* feat_target,
+                        const float* feat_weight, const float* d_feat_loss, const float* d_feat, float* d_hidden,
+                        float* const* grads, void* workspace, size_t workspace_bytes, int32_t passes, void* stream) {
   HeadDims h;
-  if (!head_dims(d, classes, true, &h)) return -20;
+  if (!head_dims(d, classes, HEAD_CLUSTER, &h)) return -20;
   if (M < 1) return -21;
-  if (!params || !prep || !labels || !d_loss || !d_hidden || !grads || !workspace) return -24;
+  if (!params || !prep || !d_hidden || !grads || !workspace) return -24;
   if (passes != 1 && passes != 3) return -1;
   XLX_TRY(ensure_device(workspace));
-  return head_bwd(h, params, prep, M, labels, d_loss, d_hidden, grads, workspace, workspace_bytes, passes,
-                  static_cast<cudaStream_t>(stream));
-}
-int32_t xlx_lmhead_fwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep, int32_t M,
-                       const float* hidden, const int64_t* labels, float* scores, float* loss, void* workspace,
-                       size_t workspace_bytes, int32_t passes, void* stream) {
-  HeadDims h;
-  if (!head_dims(d, classes, false, &h)) return -20;
-  if (M < 1) return -21;
-  if (!params || !prep || !hidden || !workspace) return -24;
-  if (passes != 1 && passes != 3) return -1;
-  XLX_TRY(ensure_device(workspace));
-  return head_fwd(h, params, prep, M, hidden, labels, nullptr, scores, loss, nullptr, nullptr, workspace,
+  FeatLoss fl;
+  fl.target = feat_target; fl.weight = feat_weight; fl.d_loss = d_feat_loss;
+  return head_bwd(h, params, prep, M, labels, d_loss, d_logits, fl, d_feat, d_hidden, grads, workspace,
                   workspace_bytes, passes, static_cast<cudaStream_t>(stream));
 }
-int32_t xlx_lmhead_bwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep, int32_t M,
-                       const int64_t* labels, const float* d_loss, float* d_hidden, float* const* grads,
-                       void* workspace, size_t workspace_bytes, int32_t passes, void* stream) {
-  HeadDims h;
-  if (!head_dims(d, classes, false, &h)) return -20;
-  if (M < 1) return -21;
-  if (!params || !prep || !labels || !d_loss || !d_hidden || !grads || !workspace) return -24;
-  if (passes != 1 && passes != 3) return -1;
-  XLX_TRY(ensure_device(workspace));
-  return head_bwd(h, params, prep, M, labels, d_loss, d_hidden, grads, workspace, workspace_bytes, passes,
-                  static_cast<cudaStream_t>(stream));
+int32_t xlx_feat_row_weight(const uint8_t* vis_mask, int32_t B, int32_t V, int32_t feat_dim, const int64_t* rows,
+                            int32_t n, float* weight, void* stream) {
+  if (B < 1 || V < 1 || feat_dim < 1 || n < 0 || (!rows && n != B * V)) return -21;
+  if (!vis_mask || !weight) return -24;
+  XLX_TRY(ensure_device(weight));
+  return feat_row_weight(vis_mask, B, V, feat_dim, rows, n, weight, static_cast<cudaStream_t>(stream));
 }
+
+#define XLX_PLAIN_HEAD_FWD_BWD(NAME, KIND)                                                                           \
+  int32_t xlx_##NAME##_fwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep,         \
+                           int32_t M, const float* hidden, const int64_t* labels, float* scores, float* loss,        \
+                           float* pred_prob, int64_t* pred_id, void* workspace, size_t workspace_bytes,              \
+                           int32_t passes, void* stream) {                                                           \
+    HeadDims h;                                                                                                      \
+    if (!head_dims(d, classes, KIND, &h)) return -20;                                                                \
+    if (M < 1) return -21;                                                                                           \
+    if (!params || !prep || !hidden || !workspace || (!pred_prob != !pred_id)) return -24;                           \
+    if (!labels && !scores && !pred_prob) return -24;                                                                \
+    if (passes != 1 && passes != 3) return -1;                                                                       \
+    XLX_TRY(ensure_device(workspace));                                                                               \
+    return head_fwd(h, params, prep, M, hidden, labels, FeatLoss(), nullptr, scores, loss, pred_prob, pred_id,       \
+                    workspace, workspace_bytes, passes, static_cast<cudaStream_t>(stream));                          \
+  }                                                                                                                  \
+  int32_t xlx_##NAME##_bwd(const xlx_dims* d, int32_t classes, const float* const* params, const void* prep,         \
+                           int32_t M, const int64_t* labels, const float* d_loss, const float* d_logits,             \
+                           float* d_hidden, float* const* grads, void* workspace, size_t workspace_bytes,            \
+                           int32_t passes, void* stream) {                                                           \
+    HeadDims h;                                                                                                      \
+    if (!head_dims(d, classes, KIND, &h)) return -20;                                                                \
+    if (M < 1) return -21;                                                                                           \
+    if (!params || !prep || (!labels && !d_logits) || !d_hidden || !grads || !workspace) return -24;                 \
+    if (passes != 1 && passes != 3) return -1;                                                                       \
+    XLX_TRY(ensure_device(workspace));                                                                               \
+    return head_bwd(h, params, prep, M, labels, d_loss, d_logits, FeatLoss(), nullptr, d_hidden, grads, workspace,   \
+                    workspace_bytes, passes, static_cast<cudaStream_t>(stream));                                     \
+  }
+
+XLX_PLAIN_HEAD_FWD_BWD(lmhead, HEAD_LM)
+XLX_PLAIN_HEAD_FWD_BWD(qahead, HEAD_ANSWER)
 
 // ---- matched head (HF:661,664: seq_relationship = Linear(H, 2) on the pooled output) + its cross-entropy -------
 // (lxrt/modeling.py:227-235).  scratch: xlx_matchhead_scratch_floats(B) floats, passed unchanged to the backward.
@@ -437,6 +508,16 @@ int32_t xlx_matchhead_bwd(const xlx_dims* d, int32_t B, const float* pooled, con
   float* dscores = scratch + 8 + B;
   XLX_TRY(small_ce_bwd(scores, B, 2, labels, -100, scratch, d_loss, dscores, st));
   return small_linear_bwd(dscores, pooled, W, B, d->hidden, 2, dW, dbias, d_pooled, st);
+}
+
+// backward of the bare scores (a caller that brings its own loss): d_scores [B,2] → d_pooled, dW, dbias
+int32_t xlx_matchhead_bwd_scores(const xlx_dims* d, int32_t B, const float* pooled, const float* W,
+                                 const float* d_scores, float* d_pooled, float* dW, float* dbias, void* stream) {
+  if (!hidden_ok(d)) return -20;
+  if (B < 1) return -21;
+  if (!pooled || !W || !d_scores || !d_pooled || !dW || !dbias) return -24;
+  XLX_TRY(ensure_device(d_pooled));
+  return small_linear_bwd(d_scores, pooled, W, B, d->hidden, 2, dW, dbias, d_pooled, static_cast<cudaStream_t>(stream));
 }
 
 // ---- row compaction around the masked-prediction losses --------------------------------------------------------

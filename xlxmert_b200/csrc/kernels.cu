@@ -194,6 +194,92 @@ ce_fwd_kernel(const float* __restrict__ logits, int ld, int C, const int64_t* __
     rowloss[m] = (y == ignore) ? 0.f : l - __ldg(row + y);
   }
 }
+// ---- feature regression loss (lxrt/modeling.py:270-284) -------------------------------------------------------------
+// rowloss[r] = w[r] · Σ_f SmoothL1(feat[r,f] − target[r,f]),  β = 1: 0.5·d² for |d| < 1, |d| − 0.5 otherwise
+// (torch.nn.SmoothL1Loss(reduction='none'), modeling.py:105).  One CTA per row, fixed reduction order.
+__global__ void __launch_bounds__(256)
+smooth_l1_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ target, const float* __restrict__ w, int F,
+                     float* rowloss) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  const float wr = w[r];
+  float acc = 0.f;
+  if (wr != 0.f) {
+    const float4* a = reinterpret_cast<const float4*>(feat + static_cast<size_t>(r) * F);
+    const float4* b = reinterpret_cast<const float4*>(target + static_cast<size_t>(r) * F);
+    for (int c = threadIdx.x; c < F / 4; c += blockDim.x) {
+      const float4 x = __ldg(a + c), y = __ldg(b + c);
+      const float d[4] = {fabsf(x.x - y.x), fabsf(x.y - y.y), fabsf(x.z - y.z), fabsf(x.w - y.w)};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc += d[k] < 1.f ? 0.5f * d[k] * d[k] : d[k] - 0.5f;
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    rowloss[r] = t * wr;
+  }
+}
+// out[r,f] = d_loss · w[r] · clamp(feat[r,f] − target[r,f], −1, 1)   (SmoothL1' with β = 1); out may alias feat
+__global__ void __launch_bounds__(256)
+smooth_l1_bwd_kernel(const float* feat, const float* __restrict__ target, const float* __restrict__ w,
+                     const float* __restrict__ d_loss, int F, float* out) {
+  const int r = blockIdx.x;
+  const float g = w[r] * __ldg(d_loss);
+  const float4* a = reinterpret_cast<const float4*>(feat + static_cast<size_t>(r) * F);
+  const float4* b = reinterpret_cast<const float4*>(target + static_cast<size_t>(r) * F);
+  float4* o = reinterpret_cast<float4*>(out + static_cast<size_t>(r) * F);
+  for (int c = threadIdx.x; c < F / 4; c += blockDim.x) {
+    const float4 x = a[c], y = __ldg(b + c);
+    o[c] = make_float4(g * fminf(fmaxf(x.x - y.x, -1.f), 1.f), g * fminf(fmaxf(x.y - y.y, -1.f), 1.f),
+                       g * fminf(fmaxf(x.z - y.z, -1.f), 1.f), g * fminf(fmaxf(x.w - y.w, -1.f), 1.f));
+  }
+}
+// out[0] = Σ_i x[i] in double, fixed order (single CTA)
+__global__ void __launch_bounds__(1024) sum_rows_kernel(const float* __restrict__ x, int M, float* out) {
+  __shared__ double s_l[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < M; i += 1024) acc += static_cast<double>(x[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_l[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += s_l[i];
+    out[0] = static_cast<float>(t);
+  }
+}
+// w[i] = vis_mask[row] ? 1 / (B · max(Σ_v vis_mask[b, v], 1) · F) : 0 with row = rows ? rows[i] : i, b = row / V:
+// the per-cell weight of  mean_F → masked sum → ÷ n_mask.clamp(min=1) → batch mean  (modeling.py:278-282)
+__global__ void feat_row_weight_kernel(const uint8_t* __restrict__ vis_mask, int B, int V, int F,
+                                       const int64_t* __restrict__ rows, int n, float* w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t row = rows ? rows[i] : i;
+  const int64_t b = row / V;
+  float v = 0.f;
+  if (vis_mask[row]) {
+    int cnt = 0;
+    for (int j = 0; j < V; ++j) cnt += vis_mask[b * V + j] ? 1 : 0;
+    v = 1.0f / (static_cast<float>(B) * static_cast<float>(cnt < 1 ? 1 : cnt) * static_cast<float>(F));
+  }
+  w[i] = v;
+}
+// [M, C] fp32 → split [M, Cp], columns C..Cp-1 zero (an upstream logits gradient entering the padded GEMM layout)
+__global__ void split_pad_kernel(const float* __restrict__ x, int C, int Cp, bf16* hi, bf16* lo) {
+  const size_t r = blockIdx.x;
+  for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+    bf16 h, l;
+    split_bf16(c < C ? x[r * C + c] : 0.f, h, l);
+    hi[r * Cp + c] = h;
+    if (lo) lo[r * Cp + c] = l;
+  }
+}
+
 // single CTA, fixed reduction order: deterministic
 __global__ void __launch_bounds__(1024)
 ce_finish_kernel(const float* __restrict__ rowloss, const int64_t* __restrict__ labels, int64_t ignore, int M,
@@ -830,6 +916,34 @@ int ce_bwd(const float* logits, int ld, int M, int C, int Cp, const int64_t* lab
   ce_bwd_kernel<<<M, CE_T, 0, s>>>(logits, ld, C, Cp, labels, ignore_index, lse, stats, d_loss, dlogits.hi, dlogits.lo);
   return launch_rc();
 }
+int smooth_l1_fwd(const float* feat, const float* target, const float* w, int M, int F, float* rowloss, float* loss,
+                  cudaStream_t s) {
+  if (F % 4) return -2;
+  if (M < 1) return -21;
+  smooth_l1_fwd_kernel<<<M, 256, 0, s>>>(feat, target, w, F, rowloss);
+  int rc = launch_rc();
+  if (rc) return rc;
+  sum_rows_kernel<<<1, 1024, 0, s>>>(rowloss, M, loss);
+  return launch_rc();
+}
+int smooth_l1_bwd(const float* feat, const float* target, const float* w, const float* d_loss, int M, int F, float* out,
+                  cudaStream_t s) {
+  if (F % 4) return -2;
+  if (M < 1) return -21;
+  smooth_l1_bwd_kernel<<<M, 256, 0, s>>>(feat, target, w, d_loss, F, out);
+  return launch_rc();
+}
+int feat_row_weight(const uint8_t* vis_mask, int B, int V, int F, const int64_t* rows, int n, float* w, cudaStream_t s) {
+  if (B < 1 || V < 1 || F < 1) return -21;
+  if (!n) return 0;
+  feat_row_weight_kernel<<<(n + 127) / 128, 128, 0, s>>>(vis_mask, B, V, F, rows, n, w);
+  return launch_rc();
+}
+int split_pad_f32(const float* x, int M, int C, int Cp, Split out, cudaStream_t s) {
+  if (Cp < C || M < 1) return -21;
+  split_pad_kernel<<<M, 256, 0, s>>>(x, C, Cp, out.hi, out.lo);
+  return launch_rc();
+}
 int softmax_argmax(const float* logits, int ld, int M, int C, float* prob, int64_t* id, cudaStream_t s) {
   if (ld % 4) return -2;
   if (M < 1 || C < 1) return -21;
@@ -883,6 +997,8 @@ int small_linear_bwd(const float* dy, const float* x, const float* W, int M, int
     case 512: launch_pdl(KERNEL<4>, dim3(GRID), dim3(256), 0, s, __VA_ARGS__); break;  \
     case 768: launch_pdl(KERNEL<6>, dim3(GRID), dim3(256), 0, s, __VA_ARGS__); break;  \
     case 1024: launch_pdl(KERNEL<8>, dim3(GRID), dim3(256), 0, s, __VA_ARGS__); break; \
+    case 1536: launch_pdl(KERNEL<12>, dim3(GRID), dim3(256), 0, s, __VA_ARGS__); break; \
+    case 2048: launch_pdl(KERNEL<16>, dim3(GRID), dim3(256), 0, s, __VA_ARGS__); break; \
     default: return -4;                                                                \
   }
 

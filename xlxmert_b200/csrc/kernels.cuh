@@ -72,6 +72,18 @@ int ce_fwd(const float* logits, int ld, int M, int C, const int64_t* labels, int
 // C..Cp-1 are written as zero.  Output: split matrix [M, Cp].
 int ce_bwd(const float* logits, int ld, int M, int C, int Cp, const int64_t* labels, int64_t ignore_index,
            const float* lse, const float* stats, const float* d_loss, Split dlogits, cudaStream_t s);
+// Feature-regression loss of the cluster head (lxrt/modeling.py:270-284): SmoothL1(β = 1) per element, mean over the
+// feature axis, masked mean per sample, batch mean — folded into one weight per row (feat_row_weight):
+//   loss = Σ_r w[r] · Σ_f SmoothL1(feat[r,f] − target[r,f]);   rowloss [M] scratch, loss = device scalar.
+int smooth_l1_fwd(const float* feat, const float* target, const float* w, int M, int F, float* rowloss, float* loss,
+                  cudaStream_t s);
+// out[r,f] = d_loss · w[r] · clamp(feat − target, −1, 1); out may alias feat.
+int smooth_l1_bwd(const float* feat, const float* target, const float* w, const float* d_loss, int M, int F, float* out,
+                  cudaStream_t s);
+// w[i] = vis_mask[row_i] / (B · max(n_mask[b], 1) · F), row_i = rows ? rows[i] : i  (rows: compacted row indices).
+int feat_row_weight(const uint8_t* vis_mask, int B, int V, int F, const int64_t* rows, int n, float* w, cudaStream_t s);
+// fp32 [M, C] → split [M, Cp] with zero padding columns.
+int split_pad_f32(const float* x, int M, int C, int Cp, Split out, cudaStream_t s);
 // softmax(logits, -1).max(-1) → (prob, id); ties go to the first index like torch.max
 // (tasks/imggen_model.py:232-235).
 int softmax_argmax(const float* logits, int ld, int M, int C, float* prob, int64_t* id, cudaStream_t s);

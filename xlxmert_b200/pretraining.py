@@ -3,8 +3,10 @@
 Same attribute names (``bert``, ``cls``, ``obj_predict_head``, ``mask_feat``, ``vis_emb``), same state-dict
 keys, same ``forward`` keywords and the same output dict (``lm_loss`` / ``matched_loss`` / ``obj_loss`` /
 ``vis_loss`` detached, ``total_loss`` differentiable), so ``Trainer.forward`` (``lxmert_pretrain.py:143-225``)
-and the sampler (``tasks/imggen_model.py``) call it unchanged.  Canonical task set of ``pretrain.bash:24-26``:
-MaskLM + ObjPredict + Matched, ``--visualLosses obj``; the QA head is not part of that run and is not built.
+and the sampler (``tasks/imggen_model.py``) call it unchanged.  Default = the canonical task set of
+``pretrain.bash:24-26``: MaskLM + ObjPredict + Matched, ``--visualLosses obj``.  ``visual_losses=("obj", "feat")`` adds the
+feature-regression loss (``modeling.py:270-284``; the published default ``--visualLosses obj,feat``, ``param.py:123``)
+and ``task_qa=True`` the answer head whose loss joins every task's (``--taskQA``, ``modeling.py:89-90,286-299``).
 """
 from __future__ import annotations
 
@@ -17,7 +19,7 @@ from torch import nn
 from . import _lib
 from .config import LxmertDims
 from .encoder import dims_from_hf_config
-from .heads import B200LxmertPreTrainingHeads, B200LxmertVisualObjHead
+from .heads import B200LxmertPreTrainingHeads, B200LxmertVisualAnswerHead, B200LxmertVisualObjHead
 from .lxmert import B200LxmertModel
 
 
@@ -60,21 +62,43 @@ class _VisualInputFn(torch.autograd.Function):
 
 
 class B200XLxmertForPretraining(nn.Module):
-    def __init__(self, config, num_clusters: int = 10000, passes: int = 3):
+    def __init__(self, config, num_clusters: int = 10000, passes: int = 3, visual_losses=None,
+                 task_qa: Optional[bool] = None, num_qa_labels: Optional[int] = None):
         super().__init__()
-        dims = config if isinstance(config, LxmertDims) else dims_from_hf_config(config)
+        hf = not isinstance(config, LxmertDims)
+        dims = dims_from_hf_config(config) if hf else config
         if dims.num_clusters != num_clusters:
             dims = LxmertDims(**{**dims.asdict(), "num_clusters": num_clusters})
         self.dims = dims
-        self.config = None if isinstance(config, LxmertDims) else config
+        self.config = config if hf else None
+        if hf:      # modeling.py:66-70,114-137 with the `feat` entry keyed on its own flag
+            if visual_losses is None:
+                visual_losses = [k for k, on in (("obj", getattr(config, "visual_obj_loss", True)),
+                                                 ("feat", getattr(config, "visual_feat_loss", False))) if on]
+            task_qa = getattr(config, "task_qa", False) if task_qa is None else task_qa
+            num_qa_labels = getattr(config, "num_qa_labels", 9500) if num_qa_labels is None else num_qa_labels
+        visual_losses = ("obj",) if visual_losses is None else tuple(visual_losses)
+        bad = set(visual_losses) - {"obj", "feat"}
+        if bad or not visual_losses:
+            raise ValueError(f"visual_losses must be a non-empty subset of ('obj', 'feat') in cluster mode, got "
+                             f"{visual_losses!r} ('attr' needs the non-clustering head, modeling.py:33-36)")
         self.task_mask_lm = self.task_obj_predict = self.task_matched = True
-        self.task_qa = False
+        self.task_qa = bool(task_qa)
+        self.num_qa_labels = int(num_qa_labels) if num_qa_labels is not None else 9500
         self.bert = B200LxmertModel(dims, passes=passes)
         self.cls = B200LxmertPreTrainingHeads(dims, self.bert.embeddings.word_embeddings.weight, passes=passes)
         self.obj_predict_head = B200LxmertVisualObjHead(dims, num_clusters, passes=passes)
+        if self.task_qa:
+            self.answer_head = B200LxmertVisualAnswerHead(dims, self.num_qa_labels, passes=passes)
         self.mask_feat = nn.Parameter(torch.zeros(dims.feat_dim))
         self.vis_emb: Optional[nn.Embedding] = None
-        self.visual_losses = {"obj": {"shape": (-1,), "num": num_clusters, "loss": "visual_ce"}}
+        self.visual_losses = {}
+        if "obj" in visual_losses:
+            self.visual_losses["obj"] = {"shape": (-1,), "num": num_clusters, "loss": "visual_ce"}
+        if "feat" in visual_losses:
+            self.visual_losses["feat"] = {"shape": (-1, dims.feat_dim), "num": dims.feat_dim, "loss": "l2"}
+        self.obj_predict_head.visual_losses = {k: {"shape": v["shape"], "num": v["num"]}
+                                               for k, v in self.visual_losses.items()}
 
     def set_visual_embedding(self, centroids):
         """modeling.py:140-151: frozen centroid table, tied to ``obj_predict_head.out_cluster.weight``."""
@@ -112,10 +136,21 @@ class B200XLxmertForPretraining(nn.Module):
             total_loss = self.cls.matched_loss(pooled_output, label_dict['matched_labels'])
             out_dict['matched_loss'] = total_loss.detach()
         elif task == 'vis_mask':
-            total_loss = self.obj_predict_head.loss(visual_output, label_dict['obj_labels'])
-            out_dict['obj_loss'] = total_loss.detach()
+            keys = self.visual_losses
+            vl = self.obj_predict_head.losses(
+                visual_output, obj_labels=label_dict['obj_labels'] if 'obj' in keys else None,
+                feat_labels=label_dict['feat_labels'] if 'feat' in keys else None, vis_mask=vis_mask)
+            for key in keys:                                                  # modeling.py:242-284, same order
+                total_loss = vl[key] if total_loss is None else total_loss + vl[key]
+                out_dict[f'{key}_loss'] = vl[key].detach()
             out_dict['vis_loss'] = total_loss.detach()
-        else:
-            raise ValueError(f"task must be one of 'word_mask', 'vis_mask', 'matched' (got {task!r})")
+        elif not (task == 'qa' and self.task_qa):
+            raise ValueError(f"task must be one of 'word_mask', 'vis_mask', 'matched'"
+                             f"{' or qa' if self.task_qa else ''} (got {task!r})")
+        if self.task_qa:                                                      # modeling.py:286-299: on every task
+            qa_loss, qa_pred = self.answer_head.loss(pooled_output, label_dict['qa_labels'])
+            total_loss = qa_loss if total_loss is None else total_loss + qa_loss
+            out_dict['qa_loss'] = qa_loss.detach()
+            out_dict['qa_pred'] = qa_pred
         out_dict['total_loss'] = total_loss
         return out_dict
