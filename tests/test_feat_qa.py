@@ -148,7 +148,7 @@ def test_visual_losses_match_oracle(case, compact):
     head.zero_grad(set_to_none=True)
     sum(got.values()).backward()
     for k in want:
-        assert abs(float(got[k]) - float(want[k])) < 1e-4 * abs(float(want[k])), (k, float(got[k]), float(want[k]))
+        assert abs(float(got[k].detach()) - float(want[k].detach())) < 1e-4 * abs(float(want[k].detach())), k
     assert rel_err(hg.grad.cpu(), ho.grad) < 1e-3
     for name, p in head.named_parameters():
         ref = sdo[name].grad

@@ -42,11 +42,11 @@ def test_packed_layout_contract():
     from xlxmert_b200.inputs import packed_layout
     for B, L, V in [(1, 1, 1), (2, 20, 64), (256, 20, 64), (7, 13, 36)]:
         offs, total = packed_layout(B, L, V)
-        sizes = [B * L * 8, B * L * 8, B * 8, B * V * 8, B * V, B * V * 16]
+        sizes = [B * L * 8, B * L * 8, B * 8, B * V * 8, B * V, B * V * 16, B * 8]
         assert offs[0] == 0 and all(o % 256 == 0 for o in offs)
         for o, n, nxt in zip(offs, sizes, offs[1:] + [total]):
             assert o + n <= nxt                      # sections do not overlap
-        assert total % 256 == 0 and total < sum(sizes) + 6 * 256
+        assert len(offs) == 7 and total % 256 == 0 and total < sum(sizes) + 7 * 256
     with pytest.raises(Exception):
         packed_layout(0, 20, 64)
 
@@ -99,3 +99,38 @@ def test_staged_inputs_drive_the_model_like_separate_copies():
             inputs.done()
             want = model(**reference_trainer_forward_args(batch, task, dev))["total_loss"]
             assert torch.equal(got, want), task
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned", [False, True])
+def test_qa_and_feature_labels_equal_reference_statements(pinned):
+    """--taskQA and --visualLosses obj,feat (lxmert_pretrain.py:177-189): ``qa_labels`` with the matched rule applied,
+    ``feat_labels`` = the batch's grid features, bit-identical; the extra copy is counted in ``h2d_bytes``."""
+    from xlxmert_b200.inputs import B200PretrainInputs, TASKS, packed_layout
+    B, L, V, F = 5, 20, 64, D.feat_dim
+    dev = torch.device("cuda", 0)
+    inputs = B200PretrainInputs(dev, qa_labels=True, feat_labels=True)
+    for step, task in enumerate(TASKS * 2):
+        batch = collate_batch(B, L, V, seed=20 + step)
+        g = torch.Generator().manual_seed(step)
+        batch["qa_label"] = torch.randint(0, 9500, (B,), generator=g)
+        batch["vis_feats"] = torch.randn(B, V, F, generator=g)
+        if pinned:
+            batch["vis_feats"] = batch["vis_feats"].pin_memory()
+        inputs.stage(batch, task)
+        kw = inputs.kwargs()
+        torch.cuda.synchronize()
+        qa = batch["qa_label"].clone().to(dev)                             # :185
+        if task == "matched":
+            qa.masked_fill_(batch["matched_label"].to(dev) == 0, -100)     # :186-188
+        assert kw["label_dict"]["qa_labels"].dtype == torch.int64 and torch.equal(kw["label_dict"]["qa_labels"], qa)
+        if task == "vis_mask":
+            assert torch.equal(kw["label_dict"]["feat_labels"], batch["vis_feats"].to(dev))     # :177-179
+            assert inputs.h2d_bytes == packed_layout(B, L, V)[1] + B * V * F * 4
+        else:
+            assert "feat_labels" not in kw["label_dict"]
+            assert inputs.h2d_bytes == packed_layout(B, L, V)[1]
+        ref = reference_trainer_forward_args(batch, task, dev)
+        for k, v in ref["label_dict"].items():
+            assert torch.equal(kw["label_dict"][k], v), (task, k)
+        inputs.done()

@@ -157,7 +157,7 @@ def _sig(lib):
     lib.xlx_pretrain_inputs_layout.restype = I32
     lib.xlx_pretrain_inputs_layout.argtypes = [I32, I32, I32, C.POINTER(I64), C.POINTER(I64)]
     lib.xlx_pretrain_inputs_unpack.restype = I32
-    lib.xlx_pretrain_inputs_unpack.argtypes = [P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P]
+    lib.xlx_pretrain_inputs_unpack.argtypes = [P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P]
     lib.xlx_sampler_nar_update.restype = I32
     lib.xlx_sampler_nar_update.argtypes = [P, P, P, P, P, P, I32, I32, I32, I32, P, P]
     lib.xlx_sampler_ar_update.restype = I32

@@ -15,7 +15,7 @@ namespace {
 constexpr int64_t kIgnore = -100;   // CrossEntropyLoss ignore_index (lxrt/modeling.py:99; lxmert_pretrain.py:163-166)
 
 struct Layout {
-  size_t word_id, word_label, matched_label, cluster_id, vis_mask, box_position, bytes;
+  size_t word_id, word_label, matched_label, cluster_id, vis_mask, box_position, qa_label, bytes;
 };
 inline size_t up256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 Layout layout(int B, int L, int V) {
@@ -27,6 +27,7 @@ Layout layout(int B, int L, int V) {
   o.cluster_id = off;     off = up256(off + static_cast<size_t>(B) * V * 8);
   o.vis_mask = off;       off = up256(off + static_cast<size_t>(B) * V);
   o.box_position = off;   off = up256(off + static_cast<size_t>(B) * V * 16);
+  o.qa_label = off;       off = up256(off + static_cast<size_t>(B) * 8);
   o.bytes = off;
   return o;
 }
@@ -35,7 +36,7 @@ struct UnpackArgs {
   const char* packed;
   Layout lay;
   int B, L, V, task;
-  int64_t *word_id, *word_labels, *matched_labels, *cluster_ids, *obj_labels;
+  int64_t *word_id, *word_labels, *matched_labels, *cluster_ids, *obj_labels, *qa_labels;
   uint8_t *attention_mask, *vis_mask;
   float *additive_mask, *visual_pos;
 };
@@ -68,22 +69,29 @@ __global__ void unpack_kernel(const UnpackArgs a) {
   }
   if (a.matched_labels)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.B; i += stride) a.matched_labels[i] = ml[i];
+  if (a.qa_labels) {
+    // --taskQA: the answer of a caption that was swapped for another image's is ignored        (:184-189)
+    const int64_t* q = reinterpret_cast<const int64_t*>(a.packed + a.lay.qa_label);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.B; i += stride)
+      a.qa_labels[i] = (a.task == XLX_TASK_MATCHED && ml[i] == 0) ? kIgnore : q[i];
+  }
 }
 
 }  // namespace
 
 extern "C" {
 
-int32_t xlx_pretrain_inputs_layout(int32_t B, int32_t L, int32_t V, int64_t* offsets6, int64_t* total_bytes) {
+int32_t xlx_pretrain_inputs_layout(int32_t B, int32_t L, int32_t V, int64_t* offsets7, int64_t* total_bytes) {
   if (B < 1 || L < 1 || V < 1) return -21;
-  if (!offsets6 || !total_bytes) return -24;
+  if (!offsets7 || !total_bytes) return -24;
   const Layout o = layout(B, L, V);
-  offsets6[0] = static_cast<int64_t>(o.word_id);
-  offsets6[1] = static_cast<int64_t>(o.word_label);
-  offsets6[2] = static_cast<int64_t>(o.matched_label);
-  offsets6[3] = static_cast<int64_t>(o.cluster_id);
-  offsets6[4] = static_cast<int64_t>(o.vis_mask);
-  offsets6[5] = static_cast<int64_t>(o.box_position);
+  offsets7[0] = static_cast<int64_t>(o.word_id);
+  offsets7[1] = static_cast<int64_t>(o.word_label);
+  offsets7[2] = static_cast<int64_t>(o.matched_label);
+  offsets7[3] = static_cast<int64_t>(o.cluster_id);
+  offsets7[4] = static_cast<int64_t>(o.vis_mask);
+  offsets7[5] = static_cast<int64_t>(o.box_position);
+  offsets7[6] = static_cast<int64_t>(o.qa_label);
   *total_bytes = static_cast<int64_t>(o.bytes);
   return 0;
 }
@@ -91,7 +99,7 @@ int32_t xlx_pretrain_inputs_layout(int32_t B, int32_t L, int32_t V, int64_t* off
 int32_t xlx_pretrain_inputs_unpack(const void* packed, int32_t B, int32_t L, int32_t V, int32_t task, int64_t* word_id,
                                    uint8_t* attention_mask, float* additive_mask, int64_t* cluster_ids,
                                    uint8_t* vis_mask, float* visual_pos, int64_t* obj_labels, int64_t* word_labels,
-                                   int64_t* matched_labels, void* stream) {
+                                   int64_t* matched_labels, int64_t* qa_labels, void* stream) {
   if (B < 1 || L < 1 || V < 1) return -21;
   if (task < XLX_TASK_VIS_MASK || task > XLX_TASK_MATCHED) return -1;
   if (!packed || !word_id || !attention_mask || !additive_mask || !cluster_ids || !vis_mask || !visual_pos) return -24;
@@ -109,6 +117,7 @@ int32_t xlx_pretrain_inputs_unpack(const void* packed, int32_t B, int32_t L, int
   a.obj_labels = task == XLX_TASK_VIS_MASK ? obj_labels : nullptr;
   a.word_labels = task == XLX_TASK_WORD_MASK ? word_labels : nullptr;
   a.matched_labels = task == XLX_TASK_MATCHED ? matched_labels : nullptr;
+  a.qa_labels = qa_labels;
   const int work = B * V > B * L ? B * V : B * L;
   int blocks = (work + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;

@@ -11,8 +11,12 @@ kernel (``xlx_pretrain_inputs_unpack``: ``attention_mask = word_id > 0``, the ad
     inputs.stage(batch, task)              # host: pack + enqueue (returns at once)
     out = model(**inputs.kwargs())         # same keyword arguments Trainer.forward passes (lxmert_pretrain.py:202-223)
 
-Clustering mode (``--clustering``, pretrain.bash): ``cluster_id`` instead of ``vis_feats``.  Integer / byte work —
-bit-exact against the reference's torch statements (tests/test_inputs.py).  No CPU fallback.
+Clustering mode (``--clustering``, pretrain.bash): ``cluster_id`` instead of ``vis_feats`` as the visual input.
+Optional extras of the published defaults: ``qa_labels=True`` (``--taskQA``) packs ``qa_label`` and applies the
+``matched`` rule (``lxmert_pretrain.py:184-189``); ``feat_labels=True`` (``--visualLosses obj,feat``) ships
+``batch['vis_feats']`` — the regression targets, ``:177-179`` — with one extra copy on the same stream (straight from the
+batch tensor when the DataLoader pinned it).  Integer / byte work — bit-exact against the reference's torch statements
+(tests/test_inputs.py).  No CPU fallback.
 """
 from __future__ import annotations
 
@@ -28,8 +32,8 @@ _WORD_KEY = {"vis_mask": "word_id", "word_mask": "masked_word_id", "matched": "o
 
 
 def packed_layout(B: int, L: int, V: int):
-    """Byte offsets of the six sections of the packed buffer and its total size (the C ABI owns the layout)."""
-    offs, total = (C.c_int64 * 6)(), C.c_int64()
+    """Byte offsets of the seven sections of the packed buffer and its total size (the C ABI owns the layout)."""
+    offs, total = (C.c_int64 * 7)(), C.c_int64()
     _lib.check("xlx_pretrain_inputs_layout", _lib.load().xlx_pretrain_inputs_layout(B, L, V, offs, C.byref(total)))
     return list(offs), int(total.value)
 
@@ -47,7 +51,7 @@ class _Slot:
 
 
 class B200PretrainInputs:
-    def __init__(self, device=None, depth: int = 2):
+    def __init__(self, device=None, depth: int = 2, qa_labels: bool = False, feat_labels: bool = False):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("B200PretrainInputs stages batches onto a CUDA device (sm_100a); there is no CPU fallback")
@@ -56,6 +60,7 @@ class B200PretrainInputs:
         self._staged: List[_Slot] = []
         self._copy_stream = torch.cuda.Stream(self.device)
         self.h2d_bytes = 0
+        self.qa_labels, self.feat_labels = bool(qa_labels), bool(feat_labels)
 
     # ---- host side -------------------------------------------------------------------------------------------------
     def _prepare_slot(self, s: _Slot, B: int, L: int, V: int):
@@ -75,7 +80,9 @@ class B200PretrainInputs:
             visual_pos=torch.empty(B, V, 4, dtype=torch.float32, device=dev),
             obj_labels=torch.empty(B, V, dtype=torch.int64, device=dev),
             word_labels=torch.empty(B, L, dtype=torch.int64, device=dev),
-            matched_labels=torch.empty(B, dtype=torch.int64, device=dev))
+            matched_labels=torch.empty(B, dtype=torch.int64, device=dev),
+            qa_labels=torch.empty(B, dtype=torch.int64, device=dev))
+        s.feat_host = s.feat_dev = None
         s.shape = (B, L, V)
         s.ready = torch.cuda.Event()
         s.free = None
@@ -116,6 +123,23 @@ class B200PretrainInputs:
         self._put(s.host, o[3], batch["cluster_id"], torch.int64)
         self._put(s.host, o[4], batch["vis_mask"], torch.uint8)
         self._put(s.host, o[5], batch["box_position"], torch.float32)
+        if self.qa_labels:
+            self._put(s.host, o[6], batch["qa_label"], torch.int64)
+            if task == "matched" and "matched_label" not in batch:
+                raise KeyError("matched_label")
+        feats = None
+        if self.feat_labels and task == "vis_mask":
+            feats = batch["vis_feats"].detach()
+            if feats.is_cuda or feats.dtype != torch.float32:
+                raise TypeError("vis_feats must be a host float32 tensor [B, V, feat_dim]")
+            feats = feats.contiguous()
+            if s.feat_dev is None or s.feat_dev.shape != feats.shape:
+                s.feat_dev = torch.empty(feats.shape, dtype=torch.float32, device=self.device)
+            if not feats.is_pinned():          # pageable DataLoader output: through this slot's pinned staging buffer
+                if s.feat_host is None or s.feat_host.shape != feats.shape:
+                    s.feat_host = torch.empty(feats.shape, dtype=torch.float32).pin_memory()
+                s.feat_host.copy_(feats)
+                feats = s.feat_host
         lib = _lib.load()
         out = s.out
         with torch.cuda.stream(self._copy_stream):
@@ -124,11 +148,15 @@ class B200PretrainInputs:
                 s.dev.data_ptr(), B, L, V, TASKS.index(task), out["word_id"].data_ptr(),
                 out["attention_mask"].data_ptr(), out["additive_mask"].data_ptr(), out["cluster_ids"].data_ptr(),
                 out["vis_mask"].data_ptr(), out["visual_pos"].data_ptr(), out["obj_labels"].data_ptr(),
-                out["word_labels"].data_ptr(), out["matched_labels"].data_ptr(), self._copy_stream.cuda_stream)
+                out["word_labels"].data_ptr(), out["matched_labels"].data_ptr(),
+                out["qa_labels"].data_ptr() if self.qa_labels else None, self._copy_stream.cuda_stream)
             _lib.check("xlx_pretrain_inputs_unpack", rc)
+            if feats is not None:
+                s.feat_dev.copy_(feats, non_blocking=True)
             s.ready.record(self._copy_stream)
         s.task = task
-        self.h2d_bytes = s.total
+        s.has_feats = feats is not None
+        self.h2d_bytes = s.total + (feats.numel() * 4 if feats is not None else 0)
         self._staged.append(s)
 
     # ---- consumer side ---------------------------------------------------------------------------------------------
@@ -151,6 +179,10 @@ class B200PretrainInputs:
             label_dict["word_labels"] = o["word_labels"]
         else:
             label_dict["matched_labels"] = o["matched_labels"]
+        if self.qa_labels:
+            label_dict["qa_labels"] = o["qa_labels"]
+        if s.has_feats:
+            label_dict["feat_labels"] = s.feat_dev
         s.free = torch.cuda.Event()
         s.free_recorded = False
         self._pending_free = s
