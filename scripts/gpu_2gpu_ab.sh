@@ -8,8 +8,8 @@ run() {
       --master-port 29511 bench.py --gpus 2 --steps 12 --warmup 3 2> gpurun_out/bench2.err | tail -1
 }
 for i in 1 2; do
-  run XLX_NO_EARLY_LANGUAGE_REDUCE=1 > gpurun_out/bench2_late_$i.json
-  run XLX_NO_EARLY_LANGUAGE_REDUCE=0 > gpurun_out/bench2_early_$i.json
+  run XLX_EARLY_LANGUAGE_REDUCE=0 > gpurun_out/bench2_late_$i.json
+  run XLX_EARLY_LANGUAGE_REDUCE=1 > gpurun_out/bench2_early_$i.json
 done
 python - <<'P'
 import json, glob

@@ -152,11 +152,13 @@ def test_encoder_rejects_unsupported_shapes_loudly():
         enc(emb, None, feats, batch["visual_pos"])          # CPU tensors: no fallback
 
 
-@pytest.mark.parametrize("stage_calls", [(1, 14), (1, 2, 4, 8), (1, 4, 2, 8), (3, 12)])
-def test_staged_backward_equals_one_shot(stage_calls):
+@pytest.mark.parametrize("stage_calls,early", [((1, 14), False), ((1, 14), True), ((1, 2, 4, 8), False),
+                                               ((1, 4, 2, 8), False), ((3, 12), False)])
+def test_staged_backward_equals_one_shot(stage_calls, early):
     """Issuing the backward as several stage calls (the data-parallel overlap path; the default split is
     cross-modality layers, then everything below) is bit-identical to one call — whichever way the stages are
-    grouped, i.e. with and without the language stack running beside the vision stack on the second stream."""
+    grouped, i.e. with and without the language stack running beside the vision stack on the second stream, and with
+    the language range handed to the reduce early (event recorded inside the second call)."""
     from xlxmert_b200 import _lib
     import xlxmert_b200.encoder as E
     sd, batch, feats, emb, mask = _case(TINY_DIMS, 4, 9, 12, 3, 4)
@@ -179,9 +181,10 @@ def test_staged_backward_equals_one_shot(stage_calls):
     e = emb.cuda().requires_grad_(True)
     f = feats.cuda().requires_grad_(True)
     (v, _), (l, _), _ = enc2(e, mask.cuda(), f, batch["visual_pos"].cuda())
-    old_active, old_stages = E._dist_active, E._BWD_STAGES
+    old_active, old_stages, old_early = E._dist_active, E._BWD_STAGES, E._NO_EARLY_LANGUAGE_REDUCE
     E._dist_active = (lambda g: True)
     E._BWD_STAGES = stage_calls
+    E._NO_EARLY_LANGUAGE_REDUCE = not early
     enc2.grad_sync_group = True
     import torch.distributed as dist
 
@@ -201,9 +204,10 @@ def test_staged_backward_equals_one_shot(stage_calls):
         (l[-1].sum() + (v[-1] ** 2).sum()).backward()
     finally:
         dist.all_reduce, dist.get_world_size, dist.get_backend = old
-        E._dist_active, E._BWD_STAGES = old_active, old_stages
+        E._dist_active, E._BWD_STAGES, E._NO_EARLY_LANGUAGE_REDUCE = old_active, old_stages, old_early
         enc2.grad_sync_group = None
     assert enc2.arena_reduced
+    assert len(reduced) == (4 if early else len(stage_calls))
     assert torch.equal(a[0], e.grad) and torch.equal(a[1], f.grad) and torch.equal(a[2], enc2.last_grad_arena)
     # the reduced slices tile the arena exactly once
     arena = enc2.last_grad_arena

@@ -107,8 +107,10 @@ class _EncoderSkeleton(nn.Module):
 # language stack runs beside the vision stack on the library's second stream.
 _BWD_STAGES = (1, 2 | 4 | 8)
 _BWD_ALL = 15
-#: set to True to queue the language range's all-reduce behind the whole second backward call (A/B switch)
-_NO_EARLY_LANGUAGE_REDUCE = bool(int(__import__("os").environ.get("XLX_NO_EARLY_LANGUAGE_REDUCE", "0")))
+#: XLX_EARLY_LANGUAGE_REDUCE=1: start the language range's all-reduce while the vision stack of the second backward
+#: call still computes.  Off by default — measured at N = 2 (profiles/r02_ab_early_language_reduce.log) it does not pay:
+#: the reduce kernels take SMs from the overlapped GEMMs and the tail after the backward is not volume-bound.
+_NO_EARLY_LANGUAGE_REDUCE = not bool(int(__import__("os").environ.get("XLX_EARLY_LANGUAGE_REDUCE", "0")))
 
 
 def _dist_active(group) -> bool:
