@@ -1,25 +1,30 @@
-import os, sys, ctypes as C, torch
+#!/usr/bin/env python
+"""Per-launch table of the generator's tcgen05 GEMM / convolution launches at batch B (one forward, events around every
+launch — serialised, so the sum exceeds the overlapped forward).  Usage: gen_gemm_table.py [B] [out.csv]
+Honours XLX_GEMM_DEBUG (pipeline-ablation bits) and every other XLX_* switch."""
+import ctypes as C, os, sys
+import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from xlxmert_b200 import params as P, _lib
+import __graft_entry__ as e
+e.build()
+from xlxmert_b200 import _lib, params as P, synth
+from xlxmert_b200.config import DEFAULT_DIMS as D
 from xlxmert_b200.generator import B200Generator
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+out = sys.argv[2] if len(sys.argv) > 2 else None
+if out:
+    os.environ["XLX_GEMM_LOG"] = out
 lib = _lib.load()
 G = B200Generator(); G.load_state_dict(P.init_generator_state_dict(seed=0), strict=True); G = G.cuda().eval()
-code = torch.rand(B, 8, 8, 2048, device="cuda") * 0.1
+ids = torch.randint(0, D.num_clusters, (B, 64), device="cuda")
+code = synth.centroid_table(D).cuda()[ids]
 for _ in range(2):
-    G(code, train=False)
+    G(code.view(B, 8, 8, 2048), train=False)
 torch.cuda.synchronize()
-os.environ["XLX_GEMM_LOG"] = "gpurun_out/gen_gemm_shapes.csv"
 lib.xlx_profile_gemm_begin()
-for _ in range(2):
-    G(code, train=False)
-a, b, n = C.c_double(), C.c_double(), C.c_int64()
-lib.xlx_profile_gemm_end(C.byref(a), C.byref(b), C.byref(n))
-print("gemm ms per fwd", a.value / 2, "TFLOP/s", b.value / a.value / 1e9, "launches", n.value // 2)
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(5):
-    G(code, train=False)
-e1.record(); torch.cuda.synchronize()
-print("fwd ms", e0.elapsed_time(e1) / 5, "img/s", B * 5 / e0.elapsed_time(e1) * 1e3)
+G(code.view(B, 8, 8, 2048), train=False)
+tot_ms, tot_fl, n = C.c_double(), C.c_double(), C.c_int64()
+_lib.check("xlx_profile_gemm_end", lib.xlx_profile_gemm_end(C.byref(tot_ms), C.byref(tot_fl), C.byref(n)))
+print(f"debug={os.environ.get('XLX_GEMM_DEBUG', '0')} launches={n.value} gemm_ms={tot_ms.value:.3f} "
+      f"algorithmic_tflops={tot_fl.value / tot_ms.value / 1e9:.1f}")

@@ -678,6 +678,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
                           __uint_as_float(r[g * 4 + 3]));
         if (P.tma_out) {
           // plain fp32 output: the staged 32 × 16 block (64-byte-swizzle layout) leaves as one bulk tensor store
+          if (P.epi.bias) {      // bias-only epilogue: added to the thread's own staged row (the accumulator registers
+                                 // are dead by now, so the hot variants keep their register budget)
+            const int nb = n0 + c * EPI_COLS;
+#pragma unroll 1
+            for (int g = 0; g < EPI_COLS / 4; ++g) {
+              if (nb + g * 4 >= P.N) break;
+              float4* sp = reinterpret_cast<float4*>(stage + lane * EPI_COLS + ((g ^ wsw) << 2));
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(P.epi.bias + nb) + g);
+              float4 v = *sp;
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              *sp = v;
+            }
+          }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -1191,7 +1204,15 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
   CUtensorMap mOut = mAhi;
   P.tma_out = 0;
   static const int tma_out_on = env_int("XLX_GEMM_TMA_OUT", 1);
-  if (tma_out_on && plain && P.splits == 1 && !(p.epi.flags & EPI_ACCUM) &&
+  // (a bias is added in registers before the block is staged: bias-only epilogues — the generator's narrow convolutions,
+  // the heads' logits — take this path too; measured on the 32 → 32 convolutions at 256²: their st.global epilogue was
+  // the bottleneck, profiles/r02_generator_ablation.txt)
+  static const int tma_bias_on = env_int("XLX_GEMM_TMA_OUT_BIAS", 1);
+  const bool plain_or_bias = p.epi.out_f32 && !p.epi.addend && !p.epi.addend_hi && !p.epi.out_hi && !p.epi.out_u &&
+                             !p.epi.flags && p.epi.alpha == 1.0f && !p.epi.drop.threshold && !p.epi.spade_x &&
+                             !p.epi.rowstat && !p.epi.colsum_part && (tma_bias_on || !p.epi.bias) &&
+                             !(reinterpret_cast<uintptr_t>(p.epi.bias) & 15);
+  if (tma_out_on && (plain || plain_or_bias) && P.splits == 1 && !(p.epi.flags & EPI_ACCUM) &&
       !(reinterpret_cast<uintptr_t>(p.epi.out_f32) & 15)) {
     if ((rc = make_map_f32(&mOut, p.epi.out_f32, p.N, p.M, p.epi.ld_out, EPI_COLS, 32))) return rc;
     P.tma_out = 1;
