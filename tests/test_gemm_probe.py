@@ -18,6 +18,10 @@ CASES = [
     "256 512 768 3 0 0 0", "256 512 768 3 0 1 0", "256 512 768 3 1 0 0", "256 512 768 3 1 1 0",
     "1000 776 200 3 0 0 13", "1000 776 200 3 1 1 13", "1000 776 200 1 0 1 5",
     "300 64 768 3 0 0 1", "512 768 768 3 0 0 52", "512 768 768 3 0 0 139", "512 768 768 3 0 1 72",
+    # the encoder's forward / dgrad epilogue configurations (compile-time epilogue bodies, gemm_sm100.cu lean_chunk):
+    # FFN-1 forward, projections with and without bias, attention-output / FFN-2 forward, FFN-2 dgrad — ragged shapes
+    "1000 776 328 3 0 0 651", "130 40 96 3 0 0 521", "300 64 768 3 0 0 520", "1000 776 328 3 0 0 1025",
+    "777 3072 768 3 0 0 584", "5120 3072 768 3 0 0 651", "5120 768 3072 3 0 0 1025",
     # split-K weight gradients: dW[N,K] = dYᵀ·X, both operands MN-major, K = B·S rows
     "768 768 16384 3 1 1 256 0 1",      # attention-output / Q,K,V weight at B=256 (vision rows)
     "768 3072 16384 3 1 1 256 0 1",     # FFN W2 gradient

@@ -191,6 +191,90 @@ __device__ __forceinline__ float4 epilogue_vec4(const KParams& P, int row, int n
   return make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// ---- specialised epilogues (EPI 6-9) -----------------------------------------------------------------------------------
+// The generic epilogue decides everything at run time (flags, optional pointers): 268 SASS instructions per 32-lane × 4-
+// column step for the FFN-1 forward, which made that GEMM EPILOGUE-bound (ncu: 83 K warp instructions per 128 × 256 tile,
+// issue-limited at 24 µs against a 13.6 µs main loop; profiles/r02_ffn1_epilogue_ncu.json).  The four configurations that
+// carry most of the training step's epilogue work get compile-time bodies: all four rows of a chunk step in flight
+// together, the bias fetched once per chunk, bf16x2 conversions.
+//   6 GELU_FWD   v = acc + bias;  out_u = gelu'(v) (fp32);  split(gelu(v)) → out_hi/out_lo          FFN-1 forward
+//   7 SPLIT      v = acc (+ bias);  split(v) → out_hi/out_lo                       Q/K/V projections, most dgrads
+//   8 RESID_F32  v = acc + bias + (addend_hi + addend_lo) → out_f32      attention-output / FFN-2 forward (no dropout)
+//   9 MUL_SPLIT  v = acc · u_in (fp32);  split(v) → out_hi/out_lo                       FFN-2 dgrad × saved gelu'
+// Preconditions (checked by the host): alpha = 1, no dropout, no column sums, single split, K-major operands, 3 passes.
+__device__ __forceinline__ void split2_store(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  const float ra = a - __uint_as_float(hi2 << 16), rb = b - __uint_as_float(hi2 & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
+template <int EPI>
+__device__ __forceinline__ void lean_chunk(const KParams& P, const float* stage, int row0, int n, int sub, int cq) {
+  const GemmEpilogue& E = P.epi;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI != 9 && E.bias) bias = __ldg(reinterpret_cast<const float4*>(E.bias + n));
+  float4 acc[4];
+  bool ok[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + sub;
+    ok[it] = row0 + rr < P.M;
+    acc[it] = *reinterpret_cast<const float4*>(stage + rr * EPI_COLS + ((cq ^ ((rr >> 1) & 3)) << 2));
+  }
+  if (EPI == 8) {          // residual as split bf16: all eight loads first
+    uint2 h[4], l[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      if (!ok[it]) continue;
+      const size_t idx = static_cast<size_t>(row0 + it * 8 + sub) * E.ld_addend + n;
+      h[it] = __ldg(reinterpret_cast<const uint2*>(E.addend_hi + idx));
+      l[it] = __ldg(reinterpret_cast<const uint2*>(E.addend_lo + idx));
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      if (!ok[it]) continue;
+      float4 v = acc[it];
+      v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+      v.x += __uint_as_float(h[it].x << 16) + __uint_as_float(l[it].x << 16);
+      v.y += __uint_as_float(h[it].x & 0xffff0000u) + __uint_as_float(l[it].x & 0xffff0000u);
+      v.z += __uint_as_float(h[it].y << 16) + __uint_as_float(l[it].y << 16);
+      v.w += __uint_as_float(h[it].y & 0xffff0000u) + __uint_as_float(l[it].y & 0xffff0000u);
+      *reinterpret_cast<float4*>(E.out_f32 + static_cast<size_t>(row0 + it * 8 + sub) * E.ld_out + n) = v;
+    }
+    return;
+  }
+  float4 u[4];
+  if (EPI == 9) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+      if (ok[it]) u[it] = __ldg(reinterpret_cast<const float4*>(E.u_in + static_cast<size_t>(row0 + it * 8 + sub) * E.ld_u + n));
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    if (!ok[it]) continue;
+    const int row = row0 + it * 8 + sub;
+    float4 v = acc[it];
+    if (EPI == 9) {
+      v.x *= u[it].x; v.y *= u[it].y; v.z *= u[it].z; v.w *= u[it].w;
+    } else {
+      v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+    }
+    if (EPI == 6) {
+      float4 dg;
+      gelu_and_grad(v.x, v.x, dg.x); gelu_and_grad(v.y, v.y, dg.y);
+      gelu_and_grad(v.z, v.z, dg.z); gelu_and_grad(v.w, v.w, dg.w);
+      *reinterpret_cast<float4*>(E.out_u + static_cast<size_t>(row) * E.ld_u + n) = dg;
+    }
+    uint2 hw, lw;
+    split2_store(v.x, v.y, hw.x, lw.x);
+    split2_store(v.z, v.w, hw.y, lw.y);
+    const size_t idx = static_cast<size_t>(row) * E.ld_split + n;
+    *reinterpret_cast<uint2*>(E.out_hi + idx) = hw;
+    *reinterpret_cast<uint2*>(E.out_lo + idx) = lw;
+  }
+}
+
 // A_MN / B_MN: operand stored MN-major; NPARTS: 1 = hi only (1 pass), 2 = hi + lo (3 passes).  Compile-time so that
 // the single MMA-issuing thread's loop is a handful of integer adds per tcgen05.mma (it is the critical path).
 // ACT: the epilogue may contain an activation (GeLU / tanh / ReLU / gelu-grad); kept out of the other instantiations so
@@ -583,7 +667,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[buf]));
         }
-        if (half < 2 && !(P.debug & 1)) {
+        if (half < 2) {
           const GemmEpilogue& E = P.epi;
           const int row = m0 + q * 32 + lane, c0 = half * EPI_COLS;
           if (row < P.M) {
@@ -704,6 +788,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ 
         __syncwarp();
         const int n = n0 + c * EPI_COLS + cq * 4;
         const bool col_ok = n < P.N;
+        if (EPI >= 6) {       // compile-time epilogue bodies (see lean_chunk)
+          if (col_ok) lean_chunk<EPI>(P, stage, m0 + q * 32, n, sub, cq);
+          __syncwarp();
+          continue;
+        }
         if (P.splits > 1) {   // raw partial sums; the reduce kernel finishes the job
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
@@ -1242,7 +1331,29 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
 #define XLX_LAUNCH(A, B, N)                                                                                   \
   lrc = act ? launch_variant<BK, A, B, N, 1>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)             \
             : launch_variant<BK, A, B, N, 0>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)
-    if (p.epi.spade_x) {                       // γ/β convolution of the generator (checked by gemm_launch)
+    // compile-time epilogue bodies for the configurations that carry the training step (see lean_chunk)
+    int lean = 0;
+    static const int lean_on = env_int("XLX_GEMM_LEAN_EPI", 1);
+    if (lean_on && v == 1 && !P.conv && !p.epi.rowstat && !p.epi.spade_x && !P.tile_counter && P.splits == 1 &&
+        !P.tma_out && p.epi.alpha == 1.0f && !p.epi.drop.threshold && !p.epi.colsum_part && !p.epi.addend &&
+        !p.epi.out_u16 && !p.epi.u_in16) {
+      const GemmEpilogue& e = p.epi;
+      const bool split_out = e.out_hi && e.out_lo && !e.out_f32;
+      if (e.flags == (EPI_GELU | EPI_SAVE_DGELU) && e.bias && e.out_u && split_out && !e.addend_hi) lean = 6;
+      else if (e.flags == 0 && split_out && !e.out_u && !e.addend_hi) lean = 7;
+      else if (e.flags == 0 && e.bias && e.addend_hi && e.addend_lo && e.out_f32 && !e.out_hi && !e.out_u) lean = 8;
+      else if (e.flags == EPI_MUL && e.u_in && split_out && !e.out_u && !e.addend_hi && !e.bias) lean = 9;
+    }
+    if (lean) {
+      if constexpr (BK == 32) {
+        if (lean == 6) lrc = launch_variant<BK, 0, 0, 2, 6>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
+        else if (lean == 7) lrc = launch_variant<BK, 0, 0, 2, 7>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
+        else if (lean == 8) lrc = launch_variant<BK, 0, 0, 2, 8>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
+        else lrc = launch_variant<BK, 0, 0, 2, 9>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
+      } else {
+        lrc = -1;
+      }
+    } else if (p.epi.spade_x) {                // γ/β convolution of the generator (checked by gemm_launch)
       lrc = P.nparts == 2 ? launch_variant<BK, 0, 0, 2, 4>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P)
                           : launch_variant<BK, 0, 0, 1, 4>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
     } else if (p.epi.rowstat) {                // K-major operands only (checked by gemm_launch)

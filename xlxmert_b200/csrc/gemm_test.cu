@@ -2,6 +2,9 @@
 //   gemm_test M N K passes a_mn b_mn epi
 // epi bits: 1 bias, 2 gelu(+save u), 4 addend, 8 split output check, 16 gelu-grad, 32 accumulate,
 //           64 multiply by u_in, 128 (with 2) save gelu'(u) instead of u,
+//           512 (with 8) no fp32 output: split only, checked through hi + lo; 1024 residual given as split bf16
+//               (the encoder's forward / dgrad configurations, which take the compile-time epilogue bodies:
+//                651 FFN-1 forward, 521 / 520 projections and dgrads, 1025 attention-output / FFN-2 forward, 584 FFN-2 dgrad),
 //           256 pass a split-K workspace (weight-gradient shapes: small M·N, long K); the problem is then ALSO run without
 //               the workspace and the two outputs must agree to 1e-4 of max|out| (split-K on vs off).  They cannot be
 //               bit-identical: the summation order differs, and the fp32 accumulation of K = 16 384 products in TMEM is
@@ -70,6 +73,19 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(duin, uin.data(), nmn * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dout, out0.data(), nmn * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dOhi, 0, nmn * 2)); CK(cudaMemset(dOlo, 0, nmn * 2)); CK(cudaMemset(dusave, 0, nmn * 4));
+  __nv_bfloat16 *dAddHi = nullptr, *dAddLo = nullptr;
+  std::vector<float> addsplit(nmn, 0.f);            // value of the split residual (hi + lo of `addend`)
+  if (epi & 1024) {
+    std::vector<__nv_bfloat16> ah(nmn), al(nmn);
+    for (size_t i = 0; i < nmn; ++i) {
+      ah[i] = __float2bfloat16_rn(addend[i]);
+      al[i] = __float2bfloat16_rn(addend[i] - __bfloat162float(ah[i]));
+      addsplit[i] = __bfloat162float(ah[i]) + __bfloat162float(al[i]);
+    }
+    CK(cudaMalloc(&dAddHi, nmn * 2)); CK(cudaMalloc(&dAddLo, nmn * 2));
+    CK(cudaMemcpy(dAddHi, ah.data(), nmn * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dAddLo, al.data(), nmn * 2, cudaMemcpyHostToDevice));
+  }
 
   GemmProblem p;
   p.M = M; p.N = N; p.K = K; p.passes = passes;
@@ -84,6 +100,13 @@ int main(int argc, char** argv) {
   if (epi & 32) p.epi.flags |= EPI_ACCUM;
   if (epi & 64) { p.epi.flags |= EPI_MUL; p.epi.u_in = duin; p.epi.ld_u = N; }
   if (epi & 128) p.epi.flags |= EPI_SAVE_DGELU;
+  if (epi & 512) {     // split output only (the encoder's forward GEMMs): no fp32 copy; checked through hi + lo below
+    if (!(epi & 8)) { printf("epi bit 512 needs bit 8\n"); return 1; }
+    p.epi.out_f32 = nullptr;
+  }
+  if (epi & 1024) {    // residual as split bf16 (addend_hi / addend_lo): the uin buffer's split serves as the residual
+    p.epi.addend_hi = dAddHi; p.epi.addend_lo = dAddLo; p.epi.ld_addend = N;
+  }
   std::vector<float> out_nosplit;
   float* dws = nullptr;
   if (epi & 256) {
@@ -119,6 +142,8 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(usave.data(), dusave, nmn * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(ohi.data(), dOhi, nmn * 2, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(olo.data(), dOlo, nmn * 2, cudaMemcpyDeviceToHost));
+  if (epi & 512)
+    for (size_t i = 0; i < nmn; ++i) out[i] = __bfloat162float(ohi[i]) + __bfloat162float(olo[i]);
 
   if (getenv("XLX_TEST_MAP")) {   // per (m-tile, 64-column block): count of wrong entries (exhaustive, small problems only)
     for (int mt = 0; mt < (M + 127) / 128; ++mt) {
@@ -162,6 +187,7 @@ int main(int argc, char** argv) {
     if (epi & 64) v *= uin[idx];
     if (epi & 16) { double x = uin[idx]; v *= 0.5 * (1.0 + erf(x / sqrt(2.0))) + x * exp(-0.5 * x * x) / sqrt(2.0 * M_PI); }
     if (epi & 4) v += addend[idx];
+    if (epi & 1024) v += addsplit[idx];
     if (epi & 32) v += out0[idx];
     if (getenv("XLX_TEST_VERBOSE") && !(fabs(out[idx] - v) < 1e-3 * (1 + fabs(v))) && nbad++ < 24)
       printf("  bad r=%d (mtile %d, r%%128=%d) c=%d (ntile %d, c%%256=%d) got %.5g want %.5g\n", r, r / 128, r % 128, c, c / 256, c % 256, out[idx], v);
