@@ -497,6 +497,10 @@ def run_ours(args):
             extra["encoder_only"] = bench_encoder_only(model, table, dev, B, passes, lib)
         except Exception as ex:      # a sub-record never takes the headline down
             extra["encoder_only"] = {"error": repr(ex)}
+        try:
+            extra["train_mode_dropout_0.1"] = bench_dropout_step(model, step_resident, counter, B)
+        except Exception as ex:
+            extra["train_mode_dropout_0.1"] = {"error": repr(ex)}
         del model, opt, params, resident
         torch.cuda.empty_cache()
         for name, fn in (("generator_b128", bench_generator), ("sampler_nar4_b32", bench_sampler),
@@ -532,6 +536,25 @@ def _timed_simple(fn, iters, warm=3):
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
+
+
+def bench_dropout_step(model, step_resident, counter, B):
+    """The same resident step with the reference's training-mode dropout (nn.Dropout(0.1) at every HF site, generated
+    inside the kernels from a counter-based Philox stream).  The headline and both reference arms run with p = 0 so that
+    they compute the same numbers; this record says what the dropout the reference trains with costs here."""
+    from dataclasses import replace
+    mods = [m for m in model.modules() if hasattr(m, "dims") and hasattr(m.dims, "hidden_dropout")]
+    old = [m.dims for m in mods]
+    try:
+        for m in mods:
+            m.dims = replace(m.dims, hidden_dropout=0.1, attention_dropout=0.1)
+        counter[0] = 0
+        ms = _timed_simple(step_resident, 6, 3)
+    finally:
+        for m, d in zip(mods, old):
+            m.dims = d
+    return {"workload": "full pre-training step, B=256, hidden_dropout = attention_dropout = 0.1 (train mode)",
+            "ms_per_step": ms, "samples_per_s": B / ms * 1e3}
 
 
 def bench_encoder_only(model, table, dev, B, passes, lib):

@@ -201,6 +201,7 @@ __device__ __forceinline__ float4 epilogue_vec4(const KParams& P, int row, int n
 //   7 SPLIT      v = acc (+ bias);  split(v) → out_hi/out_lo                       Q/K/V projections, most dgrads
 //   8 RESID_F32  v = acc + bias + (addend_hi + addend_lo) → out_f32      attention-output / FFN-2 forward (no dropout)
 //   9 MUL_SPLIT  v = acc · u_in (fp32);  split(v) → out_hi/out_lo                       FFN-2 dgrad × saved gelu'
+//  10 RESID_DROP v = dropout(acc + bias) + (addend_hi + addend_lo) → out_f32          the same two in training mode
 // Preconditions (checked by the host): alpha = 1, no dropout, no column sums, single split, K-major operands, 3 passes.
 __device__ __forceinline__ void split2_store(float a, float b, uint32_t& hi2, uint32_t& lo2) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -222,7 +223,7 @@ __device__ __forceinline__ void lean_chunk(const KParams& P, const float* stage,
     ok[it] = row0 + rr < P.M;
     acc[it] = *reinterpret_cast<const float4*>(stage + rr * EPI_COLS + ((cq ^ ((rr >> 1) & 3)) << 2));
   }
-  if (EPI == 8) {          // residual as split bf16: all eight loads first
+  if (EPI == 8 || EPI == 10) {   // residual as split bf16: all eight loads first
     uint2 h[4], l[4];
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
@@ -236,6 +237,10 @@ __device__ __forceinline__ void lean_chunk(const KParams& P, const float* stage,
       if (!ok[it]) continue;
       float4 v = acc[it];
       v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+      if (EPI == 10) {     // dropout(dense(x)) + residual (HF:282-287,344-349): the mask is a function of (site, row, column)
+        const float4 m = drop_hidden4(E.drop, static_cast<size_t>(row0 + it * 8 + sub), P.N, n);
+        v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+      }
       v.x += __uint_as_float(h[it].x << 16) + __uint_as_float(l[it].x << 16);
       v.y += __uint_as_float(h[it].x & 0xffff0000u) + __uint_as_float(l[it].x & 0xffff0000u);
       v.z += __uint_as_float(h[it].y << 16) + __uint_as_float(l[it].y << 16);
@@ -1335,10 +1340,13 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
     int lean = 0;
     static const int lean_on = env_int("XLX_GEMM_LEAN_EPI", 1);
     if (lean_on && v == 1 && !P.conv && !p.epi.rowstat && !p.epi.spade_x && !P.tile_counter && P.splits == 1 &&
-        !P.tma_out && p.epi.alpha == 1.0f && !p.epi.drop.threshold && !p.epi.colsum_part && !p.epi.addend &&
+        !P.tma_out && p.epi.alpha == 1.0f && !p.epi.colsum_part && !p.epi.addend &&
         !p.epi.out_u16 && !p.epi.u_in16) {
       const GemmEpilogue& e = p.epi;
       const bool split_out = e.out_hi && e.out_lo && !e.out_f32;
+      if (e.drop.threshold) {
+        if (e.flags == 0 && e.bias && e.addend_hi && e.addend_lo && e.out_f32 && !e.out_hi && !e.out_u) lean = 10;
+      } else
       if (e.flags == (EPI_GELU | EPI_SAVE_DGELU) && e.bias && e.out_u && split_out && !e.addend_hi) lean = 6;
       else if (e.flags == 0 && split_out && !e.out_u && !e.addend_hi) lean = 7;
       else if (e.flags == 0 && e.bias && e.addend_hi && e.addend_lo && e.out_f32 && !e.out_hi && !e.out_u) lean = 8;
@@ -1349,6 +1357,7 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
         if (lean == 6) lrc = launch_variant<BK, 0, 0, 2, 6>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
         else if (lean == 7) lrc = launch_variant<BK, 0, 0, 2, 7>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
         else if (lean == 8) lrc = launch_variant<BK, 0, 0, 2, 8>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
+        else if (lean == 10) lrc = launch_variant<BK, 0, 0, 2, 10>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
         else lrc = launch_variant<BK, 0, 0, 2, 9>(grid, smem, stream, mAhi, mAlo, mBhi, mBlo, mOut, P);
       } else {
         lrc = -1;
