@@ -199,7 +199,8 @@ __device__ __forceinline__ float4 epilogue_vec4(const KParams& P, int row, int n
 // together, the bias fetched once per chunk, bf16x2 conversions.
 //   6 GELU_FWD   v = acc + bias;  out_u = gelu'(v) (fp32);  split(gelu(v)) → out_hi/out_lo          FFN-1 forward
 //   7 SPLIT      v = acc (+ bias);  split(v) → out_hi/out_lo                       Q/K/V projections, most dgrads
-//   8 RESID_F32  v = acc + bias + (addend_hi + addend_lo) → out_f32      attention-output / FFN-2 forward (no dropout)
+//   8 RESID_F32  v = acc (+ bias) + (addend_hi + addend_lo) → out_f32    attention-output / FFN-2 forward (no dropout),
+//                                                                        dgrads that add the residual path's gradient
 //   9 MUL_SPLIT  v = acc · u_in (fp32);  split(v) → out_hi/out_lo                       FFN-2 dgrad × saved gelu'
 //  10 RESID_DROP v = dropout(acc + bias) + (addend_hi + addend_lo) → out_f32          the same two in training mode
 // Preconditions (checked by the host): alpha = 1, no dropout, no column sums, single split, K-major operands, 3 passes.
@@ -1349,7 +1350,7 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
       } else
       if (e.flags == (EPI_GELU | EPI_SAVE_DGELU) && e.bias && e.out_u && split_out && !e.addend_hi) lean = 6;
       else if (e.flags == 0 && split_out && !e.out_u && !e.addend_hi) lean = 7;
-      else if (e.flags == 0 && e.bias && e.addend_hi && e.addend_lo && e.out_f32 && !e.out_hi && !e.out_u) lean = 8;
+      else if (e.flags == 0 && e.addend_hi && e.addend_lo && e.out_f32 && !e.out_hi && !e.out_u) lean = 8;   // bias optional
       else if (e.flags == EPI_MUL && e.u_in && split_out && !e.out_u && !e.addend_hi && !e.bias) lean = 9;
     }
     if (lean) {
