@@ -34,11 +34,20 @@ inline int krc() {
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }
 
+// hi = rn_bf16(v), lo = rn_bf16(v − hi), two values per conversion instruction (cvt.rn.bf16x2.f32): same values as
+// split_bf16, half the conversions — these kernels are instruction-bound, not byte-bound
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi2 << 16), b - __uint_as_float(hi2 & 0xffff0000u));
+  lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void store_split(bf16* hi, bf16* lo, size_t idx, float4 v) {
-  bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-  split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
-  *reinterpret_cast<uint2*>(hi + idx) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-  *reinterpret_cast<uint2*>(lo + idx) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+  uint2 h, l;
+  split_pair(v.x, v.y, h.x, l.x);
+  split_pair(v.z, v.w, h.y, l.y);
+  *reinterpret_cast<uint2*>(hi + idx) = h;
+  *reinterpret_cast<uint2*>(lo + idx) = l;
 }
 
 // PyTorch upsample_bilinear2d, align_corners=False: source index and weights for output index o.
@@ -244,17 +253,32 @@ spade_hidden_kernel(const float* __restrict__ Ry, const float* __restrict__ bias
   const float* ry = Ry + row * (3 * 8 * HID) + c4 * 4;
   float4 r0[3], r1[3];
   int cx0[3] = {-1, -1, -1}, cx1[3] = {-1, -1, -1};
+  // pixel px reads the positions px − 1, px, px + 1: a sliding window, one new position per pixel (its source columns and
+  // weights are the same for every lane — computing them three times per pixel was a third of this kernel's instructions)
+  int wx0[3], wx1[3];
+  float wl0[3], wl1[3];
+  bool wok[3];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int qx = px0 + m - 1;
+    wok[m + 1] = qx >= 0 && qx < R;
+    bilinear_src(qx, scale, R0, wx0[m + 1], wx1[m + 1], wl0[m + 1], wl1[m + 1]);
+  }
 #pragma unroll
   for (int k = 0; k < PXW; ++k) {
     const int px = px0 + k;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      wok[m] = wok[m + 1]; wx0[m] = wx0[m + 1]; wx1[m] = wx1[m + 1]; wl0[m] = wl0[m + 1]; wl1[m] = wl1[m + 1];
+    }
+    wok[2] = px + 1 < R;
+    bilinear_src(px + 1, scale, R0, wx0[2], wx1[2], wl0[2], wl1[2]);
     float4 acc = bv;
 #pragma unroll
     for (int tx = 0; tx < 3; ++tx) {
-      const int qx = px + tx - 1;
-      if (qx < 0 || qx >= R) continue;
-      int x0, x1;
-      float l0, l1;
-      bilinear_src(qx, scale, R0, x0, x1, l0, l1);
+      if (!wok[tx]) continue;
+      const int x0 = wx0[tx], x1 = wx1[tx];
+      const float l0 = wl0[tx], l1 = wl1[tx];
       if (x0 != cx0[tx]) { r0[tx] = __ldg(reinterpret_cast<const float4*>(ry + (tx * 8 + x0) * HID)); cx0[tx] = x0; }
       if (x1 != cx1[tx]) { r1[tx] = __ldg(reinterpret_cast<const float4*>(ry + (tx * 8 + x1) * HID)); cx1[tx] = x1; }
       acc.x += l0 * r0[tx].x + l1 * r1[tx].x; acc.y += l0 * r0[tx].y + l1 * r1[tx].y;
