@@ -83,11 +83,7 @@ __device__ __forceinline__ void tma_stage(bf16* smem0, uint64_t* bar, const Tile
   __syncthreads();            // barrier initialised before anybody polls it
   mbar_wait(smem_u32(bar), 0);
 }
-__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  bf16 h0, l0, h1, l1;
-  split_bf16(x, h0, l0); split_bf16(y, h1, l1);
-  hi = pack_bf16x2(h0, h1); lo = pack_bf16x2(l0, l1);
-}
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) { split_bf16x2(x, y, hi, lo); }
 __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);

@@ -34,18 +34,10 @@ inline int krc() {
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }
 
-// hi = rn_bf16(v), lo = rn_bf16(v − hi), two values per conversion instruction (cvt.rn.bf16x2.f32): same values as
-// split_bf16, half the conversions — these kernels are instruction-bound, not byte-bound
-__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi2, uint32_t& lo2) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  hi2 = *reinterpret_cast<const uint32_t*>(&h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi2 << 16), b - __uint_as_float(hi2 & 0xffff0000u));
-  lo2 = *reinterpret_cast<const uint32_t*>(&l);
-}
 __device__ __forceinline__ void store_split(bf16* hi, bf16* lo, size_t idx, float4 v) {
   uint2 h, l;
-  split_pair(v.x, v.y, h.x, l.x);
-  split_pair(v.z, v.w, h.y, l.y);
+  split_bf16x2(v.x, v.y, h.x, l.x);       // these kernels are instruction-bound, not byte-bound
+  split_bf16x2(v.z, v.w, h.y, l.y);
   *reinterpret_cast<uint2*>(hi + idx) = h;
   *reinterpret_cast<uint2*>(lo + idx) = l;
 }

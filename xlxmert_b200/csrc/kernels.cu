@@ -29,10 +29,11 @@ __device__ __forceinline__ float bf16hi_to_f32(uint32_t w) { return __uint_as_fl
 
 // store 4 floats as split bf16 (8 bytes to hi, 8 bytes to lo)
 __device__ __forceinline__ void store_split4(bf16* hi, bf16* lo, size_t idx, float4 v) {
-  bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-  split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
-  *reinterpret_cast<uint2*>(hi + idx) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-  if (lo) *reinterpret_cast<uint2*>(lo + idx) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+  uint2 h, l;
+  split_bf16x2(v.x, v.y, h.x, l.x);
+  split_bf16x2(v.z, v.w, h.y, l.y);
+  *reinterpret_cast<uint2*>(hi + idx) = h;
+  if (lo) *reinterpret_cast<uint2*>(lo + idx) = l;
 }
 __device__ __forceinline__ float4 load_split4(const bf16* hi, const bf16* lo, size_t idx) {
   uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + idx));
