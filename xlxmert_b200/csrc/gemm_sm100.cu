@@ -76,18 +76,31 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 //   Φ(x) = ½·erfc(−x/√2),  erfc(z) = e^{−z²}·(a₁t + … + a₅t⁵), t = 1/(1 + p·z), z ≥ 0   (Abramowitz–Stegun 7.1.26,
 //   |error| ≤ 1.5e-7 on erf, i.e. fp32-epsilon class on Φ), and e^{−z²} = e^{−x²/2} is exactly what φ(x) needs.
 //   gelu(x) = x·Φ(x),  gelu'(x) = Φ(x) + x·φ(x).   ≈ 20 instructions instead of erff + expf.
+// The two special-function units are used raw (ex2.approx.ftz / rcp.approx.ftz): __expf and __fdividef wrap the same
+// instructions in range fix-ups (2 compares + 3 predicated multiplies per element) that these arguments never need —
+// the reciprocal's argument is ≥ 1, and an exponent that underflows should flush to zero anyway.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void gelu_and_grad(float x, float& y, float& dy) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  const float e = __expf(-0.5f * x * x);
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float half_erfc = 0.5f * poly * t * e;              // ½·erfc(|x|/√2) = Φ(−|x|)
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  const float e = ex2_approx(x * x * -0.72134752044448170368f);          // e^{−x²/2} = 2^{−x²/2·log2(e)}
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);        // the ½ of ½·erfc folded into the coefficients
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float half_erfc = poly * t * e;                     // ½·erfc(|x|/√2) = Φ(−|x|)
   const float cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
   y = x * cdf;
-  dy = fmaf(x, 0.39894228040143267794f * e, cdf);
+  dy = fmaf(x * e, 0.39894228040143267794f, cdf);
 }
 
 // Global inputs of the epilogue for 4 consecutive columns of one row, fetched ahead of the arithmetic so that the loads
