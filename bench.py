@@ -521,7 +521,7 @@ def run_ours(args):
         del model, opt, params, resident
         torch.cuda.empty_cache()
         for name, fn in (("generator_b128", bench_generator), ("sampler_nar4_b32", bench_sampler),
-                         ("gpu_eager_reference", bench_gpu_eager)):
+                         ("kmeans_assign", bench_kmeans), ("gpu_eager_reference", bench_gpu_eager)):
             try:
                 extra[name] = fn(dev, peaks)
             except Exception as ex:
@@ -649,6 +649,34 @@ def bench_sampler(dev, peaks):
                         "device in, images on the host out",
             "ms": ms, "images_per_s": Bs / ms * 1e3, "algorithmic_tflops_reference_work": tf,
             "note": "FLOPs counted as the reference does the work (language layers recomputed every step)"}
+
+
+def bench_kmeans(dev, peaks):
+    """nearest-centroid assignment of grid features (run_kmeans.py:124-143, faiss IndexFlatL2.search
+    with k = 1): 10 000 centroids x 2048, features resident on the device and streamed from host memory."""
+    import numpy as np
+    import torch
+    from xlxmert_b200 import synth
+    from xlxmert_b200.config import DEFAULT_DIMS as D
+    from xlxmert_b200.kmeans import B200IndexFlatL2
+    cent = synth.centroid_table(D).float()
+    index = B200IndexFlatL2(D.feat_dim)
+    index.add(cent)
+    n = 32768
+    g = torch.Generator().manual_seed(0)
+    x = (cent[torch.randint(0, cent.shape[0], (n,), generator=g)] + 0.3 * torch.randn(n, D.feat_dim, generator=g))
+    xd = x.to(dev)
+    ms = _timed_simple(lambda: index.search(xd, 1), 5, 2)
+    xh = np.ascontiguousarray(np.concatenate([x.numpy()] * 2))        # 65 536 rows = 512 MiB of fp32 features on the host
+    index.search(xh[:n], 1)
+    t0 = time.perf_counter()
+    index.search(xh, 1)
+    dt = time.perf_counter() - t0
+    return {"workload": "B200IndexFlatL2.search(x, 1): 10 000 centroids x 2048 (run_kmeans.py:124-143)",
+            "device_resident": {"rows": n, "ms": ms, "rows_per_s": n / ms * 1e3,
+                                "algorithmic_tflops": 2.0 * n * D.feat_dim * cent.shape[0] / ms / 1e9},
+            "host_streamed": {"rows": int(xh.shape[0]), "ms": dt * 1e3, "rows_per_s": xh.shape[0] / dt,
+                              "h2d_GBps": xh.nbytes / dt / 1e9}}
 
 
 def bench_gpu_eager(dev, peaks):
