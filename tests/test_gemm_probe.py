@@ -22,6 +22,7 @@ CASES = [
     # FFN-1 forward, projections with and without bias, attention-output / FFN-2 forward, FFN-2 dgrad — ragged shapes
     "1000 776 328 3 0 0 651", "130 40 96 3 0 0 521", "300 64 768 3 0 0 520", "1000 776 328 3 0 0 1025",
     "777 3072 768 3 0 0 584", "5120 3072 768 3 0 0 651", "5120 768 3072 3 0 0 1025", "1000 776 328 3 0 0 1024",
+    "1000 776 328 3 0 0 2571",          # inference GeLU (bias + gelu, nothing saved, split output only)
     # split-K weight gradients: dW[N,K] = dYᵀ·X, both operands MN-major, K = B·S rows
     "768 768 16384 3 1 1 256 0 1",      # attention-output / Q,K,V weight at B=256 (vision rows)
     "768 3072 16384 3 1 1 256 0 1",     # FFN W2 gradient

@@ -209,7 +209,7 @@ __device__ __forceinline__ float4 epilogue_vec4(const KParams& P, int row, int n
 // issue-limited at 24 µs against a 13.6 µs main loop; profiles/r02_ffn1_epilogue_ncu.json).  The four configurations that
 // carry most of the training step's epilogue work get compile-time bodies: all four rows of a chunk step in flight
 // together, the bias fetched once per chunk, bf16x2 conversions.
-//   6 GELU_FWD   v = acc + bias;  out_u = gelu'(v) (fp32);  split(gelu(v)) → out_hi/out_lo          FFN-1 forward
+//   6 GELU_FWD   v = acc + bias;  out_u = gelu'(v) (fp32, training only);  split(gelu(v)) → out_hi/out_lo   FFN-1 forward
 //   7 SPLIT      v = acc (+ bias);  split(v) → out_hi/out_lo                       Q/K/V projections, most dgrads
 //   8 RESID_F32  v = acc (+ bias) + (addend_hi + addend_lo) → out_f32    attention-output / FFN-2 forward (no dropout),
 //                                                                        dgrads that add the residual path's gradient
@@ -275,7 +275,7 @@ __device__ __forceinline__ void lean_chunk(const KParams& P, const float* stage,
       float4 dg;
       gelu_and_grad(v.x, v.x, dg.x); gelu_and_grad(v.y, v.y, dg.y);
       gelu_and_grad(v.z, v.z, dg.z); gelu_and_grad(v.w, v.w, dg.w);
-      *reinterpret_cast<float4*>(E.out_u + static_cast<size_t>(row) * E.ld_u + n) = dg;
+      if (E.out_u) *reinterpret_cast<float4*>(E.out_u + static_cast<size_t>(row) * E.ld_u + n) = dg;
     }
     uint2 hw, lw;
     split_bf16x2(v.x, v.y, hw.x, lw.x);
@@ -1350,7 +1350,9 @@ int launch_bk(const GemmProblem& p, cudaStream_t stream) {
       if (e.drop.threshold) {
         if (e.flags == 0 && e.bias && e.addend_hi && e.addend_lo && e.out_f32 && !e.out_hi && !e.out_u) lean = 10;
       } else
-      if (e.flags == (EPI_GELU | EPI_SAVE_DGELU) && e.bias && e.out_u && split_out && !e.addend_hi) lean = 6;
+      if (((e.flags == (EPI_GELU | EPI_SAVE_DGELU) && e.out_u) || (e.flags == EPI_GELU && !e.out_u)) && e.bias && split_out &&
+          !e.addend_hi)
+        lean = 6;          // training (gelu' saved) or inference (nothing saved) FFN-1 forward
       else if (e.flags == 0 && split_out && !e.out_u && !e.addend_hi) lean = 7;
       else if (e.flags == 0 && e.addend_hi && e.addend_lo && e.out_f32 && !e.out_hi && !e.out_u) lean = 8;   // bias optional
       else if (e.flags == EPI_MUL && e.u_in && split_out && !e.out_u && !e.addend_hi && !e.bias) lean = 9;
