@@ -304,7 +304,9 @@ def run_ours(args):
     params = [p for p in model.parameters() if p.requires_grad]
     opt = B200AdamW(lxmert_param_groups(model, 0.01), lr=1e-4)        # lxmert_pretrain.py:110-141 (eps 1e-6, two groups)
     if world > 1 and not args.no_overlap:
-        enable_overlapped_gradient_sync(model)                        # stage-wise all-reduce inside the backward
+        # stage-wise all-reduce inside the backward; XLX_DEFER_SYNC_WAIT=1 also lets the rest of the backward overlap the
+        # last range's reduce (opt-in until measured on several GPUs)
+        enable_overlapped_gradient_sync(model, defer_wait=bool(int(os.environ.get("XLX_DEFER_SYNC_WAIT", "0"))))
 
     # ---- the step's inputs, as collate_fn hands them over (lxmert_data.py:497-652), one batch per task slot
     host = synth.make_batch(D, B, L_TOK, V_GRID, seed=rank)
@@ -434,6 +436,18 @@ def run_ours(args):
     ms_e2e, _ = timed(step_e2e, max(3, args.steps), e2e_warm)
     e2e_steps = [round((b - a) * 1e3, 2) for a, b in zip(e2e_marks[e2e_warm - 1:], e2e_marks[e2e_warm:])]
 
+    # data-parallel correctness (N > 1), checked BEFORE the exchange is switched off below: after all these steps every
+    # replica must hold bit-identical weights (same initial weights, same reduced gradients, deterministic optimiser)
+    in_sync = None
+    if world > 1:
+        try:
+            chk = torch.stack([p.detach().double().sum() for p in params]).sum().reshape(1)
+            both = torch.cat([chk, -chk])                 # one MAX reduction gives max and −min
+            dist.all_reduce(both, op=dist.ReduceOp.MAX)
+            in_sync = bool((both[0] == -both[1]).item())
+        except Exception as ex:      # a diagnostic never takes the bench line down
+            in_sync = f"check failed: {ex!r}"
+
     # exposed gradient-exchange time (N > 1): the same step with the exchange switched off
     exposed = None
     if world > 1:
@@ -504,6 +518,8 @@ def run_ours(args):
         if exposed:
             line["gradient_exchange"] = exposed
     if world > 1:
+        if rank == 0:
+            line["replicas_in_sync"] = in_sync
         dist.barrier()
 
     # ---- sub-records (single GPU only: they describe one device)

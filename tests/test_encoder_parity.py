@@ -208,6 +208,7 @@ def test_staged_backward_equals_one_shot(stage_calls, early):
         enc2.grad_sync_group = None
     assert enc2.arena_reduced
     assert len(reduced) == (4 if early else len(stage_calls))
+    assert enc2._pending_sync is None                    # default: the backward itself waited
     assert torch.equal(a[0], e.grad) and torch.equal(a[1], f.grad) and torch.equal(a[2], enc2.last_grad_arena)
     # the reduced slices tile the arena exactly once
     arena = enc2.last_grad_arena
@@ -282,3 +283,48 @@ def test_workspaces_do_not_leak_without_a_backward():
         del out
     torch.cuda.synchronize()
     assert torch.cuda.memory_allocated() == base
+
+
+def test_deferred_wait_of_the_overlapped_gradient_sync():
+    """``enable_overlapped_gradient_sync(defer_wait=True)``: the backward leaves its all-reduces in flight, the wait (and
+    the 1/world scale of backends without AVG) happens in ``finish_overlapped_sync`` — gradients equal the waited path."""
+    import torch.distributed as dist
+    import xlxmert_b200.encoder as E
+    from xlxmert_b200 import parallel
+    sd, batch, feats, emb, mask = _case(TINY_DIMS, 4, 9, 12, 3, 4)
+    enc = _encoder(TINY_DIMS, O.sub(sd, "encoder")).train()
+
+    waited = []
+
+    class _W:
+        def wait(self):
+            waited.append(1)
+
+    def run(defer):
+        for p in enc.parameters():
+            p.grad = None
+        e = emb.cuda().requires_grad_(True)
+        f = feats.cuda().requires_grad_(True)
+        (v, _), (l, _), _ = enc(e, mask.cuda(), f, batch["visual_pos"].cuda())
+        old = (E._dist_active, dist.all_reduce, dist.get_world_size, dist.get_backend)
+        E._dist_active = (lambda g: True)
+        dist.all_reduce = lambda t, op=None, group=None, async_op=False: _W()
+        dist.get_world_size = lambda g=None: 2
+        dist.get_backend = lambda g=None: "gloo"            # no AVG: the arena is scaled by 1/world after the waits
+        enc.grad_sync_group, enc.defer_sync_wait = True, defer
+        try:
+            (l[-1].sum() + (v[-1] ** 2).sum()).backward()
+            pending = enc._pending_sync is not None
+            n_before = len(waited)
+            parallel.finish_overlapped_sync()
+        finally:
+            E._dist_active, dist.all_reduce, dist.get_world_size, dist.get_backend = old
+            enc.grad_sync_group, enc.defer_sync_wait = None, False
+        return pending, n_before, enc.last_grad_arena.clone()
+
+    p0, n0, a0 = run(False)
+    assert not p0 and n0 == 2
+    waited.clear()
+    p1, n1, a1 = run(True)
+    assert p1 and n1 == 0 and len(waited) == 2 and enc._pending_sync is None and not E._PENDING_SYNC
+    assert torch.equal(a0, a1)                               # both are the un-reduced sum scaled by 1/2

@@ -105,6 +105,26 @@ class _EncoderSkeleton(nn.Module):
 # Backward stage masks (include/xlxmert_b200.h: XLX_BWD_CROSS = 1, _VISION = 2, _LANGUAGE = 4, _VISN_FC = 8) in the order the
 # data-parallel backward issues them: the cross-modality layers first, then everything below them in ONE call so that the
 # language stack runs beside the vision stack on the library's second stream.
+#: encoders whose stage-wise all-reduces are still in flight (defer_sync_wait); see finish_pending_gradient_sync
+_PENDING_SYNC: list = []
+
+
+def finish_pending_gradient_sync() -> None:
+    """Make the current stream wait for every all-reduce an encoder backward left in flight (and apply the 1/world scale
+    of backends without an AVG reduction).  Idempotent; ``parallel.allreduce_gradients`` and ``B200AdamW.step`` call it."""
+    while _PENDING_SYNC:
+        enc = _PENDING_SYNC.pop()
+        pending = enc._pending_sync
+        if pending is None:
+            continue
+        works, scale, arena = pending
+        for w in works:
+            w.wait()
+        if scale is not None:
+            arena.mul_(scale)
+        enc._pending_sync = None
+
+
 _BWD_STAGES = (1, 2 | 4 | 8)
 _BWD_ALL = 15
 #: XLX_EARLY_LANGUAGE_REDUCE=1: start the language range's all-reduce while the vision stack of the second backward
@@ -258,11 +278,18 @@ class _EncoderFn(torch.autograd.Function):
                 else:
                     run(stage)
                     reduce_range(*enc._stage_range(stage))
-            for w in works:
-                w.wait()
-            if not avg:
-                grads.mul_(1.0 / world)
             enc.arena_reduced = True
+            if enc.defer_sync_wait:
+                # the caller's stream does not wait here: the rest of the backward (embeddings, heads' leaf gradients) and
+                # the packing of the parameters outside the encoder overlap the last range's reduce;
+                # parallel.finish_overlapped_sync (called by allreduce_gradients and B200AdamW.step) waits
+                enc._pending_sync = (works, None if avg else 1.0 / world, grads)
+                _PENDING_SYNC.append(enc)
+            else:
+                for w in works:
+                    w.wait()
+                if not avg:
+                    grads.mul_(1.0 / world)
         enc._release_workspace(ctx.ws)
         # the last cross-modality layer's self-attention + FFN of a modality whose output got no upstream gradient are
         # outside the graph: no gradient (None), exactly what the reference's autograd reports
@@ -298,6 +325,8 @@ class B200LxmertEncoder(nn.Module):
         self.config = getattr(source, "config", None)
         self.num_l_layers, self.num_x_layers, self.num_r_layers = dims.l_layers, dims.x_layers, dims.r_layers
         self.dims = dims
+        self.defer_sync_wait = False      # see parallel.enable_overlapped_gradient_sync(defer_wait=True)
+        self._pending_sync = None
         self.passes = passes
         self.output_hidden_states = output_hidden_states
         self._names = encoder_param_names(dims)

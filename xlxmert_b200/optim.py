@@ -69,6 +69,8 @@ class B200AdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.load()
+        from .encoder import finish_pending_gradient_sync
+        finish_pending_gradient_sync()       # gradient all-reduces a data-parallel backward may have left in flight
         sq = self.grad_sqnorm() if max_grad_norm > 0 else None
         for group in self.param_groups:
             ps = [p for p in group["params"] if p.grad is not None]
