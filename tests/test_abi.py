@@ -147,3 +147,27 @@ def test_stage_mask_ranges_and_host_side_argument_checks():
         B200IndexFlatL2(8).search(np.zeros((1, 8), np.float32), 1)
     with pytest.raises(NotImplementedError):
         B200IndexFlatL2(8).search(np.zeros((1, 8), np.float32), 5)
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every entry point `_lib.py` declares argtypes for takes exactly as many parameters as `include/xlxmert_b200.h`
+    says — a changed C signature with a stale ctypes list would pass garbage, not fail."""
+    import __graft_entry__ as entry
+    entry.build()
+    from xlxmert_b200 import _lib
+    lib = _lib.load()
+    src = open(os.path.join(ROOT, "include", "xlxmert_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    decls = re.findall(r"\b(xlx_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(decls) >= 60
+    checked = 0
+    for name, params in decls:
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue
+        params = params.strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
+        checked += 1
+    assert checked >= 40, checked
