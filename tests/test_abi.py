@@ -171,3 +171,25 @@ def test_ctypes_signatures_match_the_header():
         assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
         checked += 1
     assert checked >= 40, checked
+
+
+def test_round2_entry_points_validate_arguments_without_gpu():
+    """Size queries and argument checks of the answer head, the feature-regression weights and the packed inputs run on
+    the host: they must answer (or refuse with the documented codes) before anything touches the device."""
+    from xlxmert_b200 import _lib
+    from xlxmert_b200.config import DEFAULT_DIMS as D
+    lib = _lib.load()
+    cd = _lib.XlxDims.from_dims(D)
+    assert lib.xlx_qahead_prep_bytes(C.byref(cd), 9500) > lib.xlx_lmhead_prep_bytes(C.byref(cd), 9500)      # 2H-wide transform
+    assert lib.xlx_qahead_workspace_bytes(C.byref(cd), 9500, 256) > 0
+    assert lib.xlx_qahead_workspace_bytes(C.byref(cd), 9500, 0) == 0
+    bad = _lib.XlxDims.from_dims(D)
+    bad.hidden = 100
+    assert lib.xlx_qahead_prep_bytes(C.byref(bad), 9500) == 0
+    assert lib.xlx_feat_row_weight(None, 0, 64, 2048, None, 0, None, None) == -21       # B < 1
+    assert lib.xlx_feat_row_weight(None, 2, 64, 2048, None, 5, None, None) == -21       # rows NULL needs n == B·V
+    assert lib.xlx_feat_row_weight(None, 2, 64, 2048, None, 128, None, None) == -24     # NULL pointers
+    offs, total = (C.c_int64 * 7)(), C.c_int64()
+    assert lib.xlx_pretrain_inputs_layout(256, 20, 64, offs, C.byref(total)) == 0
+    assert list(offs) == sorted(offs) and offs[6] + 256 * 8 <= total.value == 495616
+    assert lib.xlx_matchhead_bwd_scores(C.byref(cd), 0, None, None, None, None, None, None, None) == -21
